@@ -1,0 +1,239 @@
+/* dab_b200.h -- C ABI of the B200-native DAB receive hot path (libdab_b200.so).
+ *
+ * This is the drop-in boundary for exactly two reference components and nothing else:
+ *   1. OFDM_Demod            /root/reference/src/ofdm/ofdm_demodulator.h:47-168   (IQ -> int8 soft bits)
+ *   2. DAB_Viterbi_Decoder   /root/reference/src/dab/algorithms/dab_viterbi_decoder.h:12-45 (punctured soft bits -> bytes)
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.  The C++ mirror classes that keep the
+ * reference's own signatures on top of these calls live in dab-radio_b200/cpp/ (see INTEGRATION.md).
+ *
+ * Every entry point needs a CUDA device (sm_100a).  There is no CPU fallback: without a usable device the create
+ * calls fail with DAB_ERR_NO_DEVICE and every other call fails with DAB_ERR_INVALID on the NULL handle.
+ *
+ * All functions returning int return a dab_status (0 = ok, negative = error); dab_last_error() gives the text of the
+ * most recent error on the calling thread.
+ */
+#ifndef DAB_B200_H
+#define DAB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define DAB_API
+#else
+#define DAB_API __attribute__((visibility("default")))
+#endif
+
+typedef enum {
+    DAB_OK = 0,
+    DAB_ERR_INVALID = -1,    /* bad argument / NULL handle */
+    DAB_ERR_NO_DEVICE = -2,  /* no CUDA device, or the device is not sm_100 */
+    DAB_ERR_CUDA = -3,       /* a CUDA runtime call or kernel failed */
+    DAB_ERR_UNDERRUN = -4,   /* Viterbi: fewer punctured symbols than the schedule consumes (dab_viterbi_decoder.cpp:158-162) */
+    DAB_ERR_CAPACITY = -5,   /* block larger than the handle was created for, too many schedules, ... */
+    DAB_ERR_TRACEBACK = -6   /* Viterbi: chainback longer than the decoded bits (viterbi_decoder_core.h:216-218) */
+} dab_status;
+
+DAB_API const char* dab_last_error(void);
+DAB_API const char* dab_version(void);
+/* number of usable sm_100 devices (0 => nothing in this library can run) */
+DAB_API int dab_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * DAB tables (replaces get_DAB_OFDM_params / get_DAB_PRS_reference / get_DAB_mapper_ref,
+ * src/ofdm/dab_ofdm_params_ref.cpp:10, dab_prs_ref.cpp:140, dab_mapper_ref.cpp:10; GetPunctureCode puncture_codes.h:69)
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct { float re, im; } dab_c32; /* layout of std::complex<float> / float2 */
+
+/* same fields and order as OFDM_Params (src/ofdm/ofdm_params.h:5-12) */
+typedef struct {
+    size_t nb_frame_symbols;
+    size_t nb_symbol_period;
+    size_t nb_null_period;
+    size_t nb_cyclic_prefix;
+    size_t nb_fft;
+    size_t nb_data_carriers;
+} dab_ofdm_params;
+
+DAB_API int dab_get_ofdm_params(int transmission_mode, dab_ofdm_params* out);
+DAB_API int dab_get_prs_reference(int transmission_mode, dab_c32* out, size_t nb_fft);
+DAB_API int dab_get_mapper_reference(int* out, size_t nb_data_carriers, size_t nb_fft);
+/* PI_1..PI_24 as 8 counts per 32 mother bits; pi = 0 returns the 6-entry tail code PI_X.  Returns the code length. */
+DAB_API int dab_get_puncture_code(int pi, uint8_t out[8]);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * OFDM demodulator (replaces OFDM_Demod, src/ofdm/ofdm_demodulator.h:109-141)
+ * One handle owns n_streams independent demodulators of one transmission mode on one GPU; every stream keeps its own
+ * state machine (ofdm_demodulator.cpp:235-275) in device memory and streams are batched per kernel launch.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct dab_ofdm dab_ofdm;
+
+/* OFDM_Demod_Config (ofdm_demodulator.h:24-45), flattened */
+typedef struct {
+    float signal_l1_update_beta;
+    int signal_l1_nb_samples;
+    int signal_l1_nb_decimate;
+    float null_l1_thresh_null_start;
+    float null_l1_thresh_null_end;
+    float sync_fine_freq_update_beta;
+    int sync_is_coarse_freq_correction;
+    float sync_max_coarse_freq_correction_norm;
+    float sync_coarse_freq_slow_beta;
+    float sync_impulse_peak_threshold_db;
+    float sync_impulse_peak_distance_probability;
+} dab_ofdm_config;
+
+/* OFDM_Demod::State (ofdm_demodulator.h:50-56) */
+enum {
+    DAB_OFDM_FINDING_NULL_POWER_DIP = 0,
+    DAB_OFDM_READING_NULL_AND_PRS = 1,
+    DAB_OFDM_RUNNING_COARSE_FREQ_SYNC = 2,
+    DAB_OFDM_RUNNING_FINE_TIME_SYNC = 3,
+    DAB_OFDM_READING_SYMBOLS = 4
+};
+
+/* the scalar getters of ofdm_demodulator.h:124-132 in one read */
+typedef struct {
+    int32_t state;
+    int32_t fine_time_offset;
+    int32_t total_frames_read;
+    int32_t total_frames_desync;
+    float signal_average;
+    float fine_frequency_offset;
+    float coarse_frequency_offset;
+    int32_t reserved;
+} dab_ofdm_state;
+
+typedef struct {
+    int64_t frame_start;      /* absolute sample index (per stream, since create/attach) of the PRS cyclic-prefix start */
+    int32_t fine_time_offset;
+    int32_t total_desync;
+    float coarse_offset;      /* used by this frame's PLL */
+    float fine_offset_used;   /* used by this frame's PLL */
+    float fine_offset_after;  /* after this frame's cyclic-prefix update */
+    float signal_average;
+} dab_ofdm_frame_info;
+
+typedef struct {
+    int n_streams;             /* >= 1 */
+    int device;                /* CUDA ordinal */
+    size_t max_block_samples;  /* largest n passed to a process call (0 => 262144) */
+    int keep_debug_taps;       /* 1: also store frame FFT / DQPSK vectors for the GUI getters (doubles HBM writes) */
+    int raw_u8_ingest;         /* 1: the stream rings hold raw uint8 IQ (dab_ofdm_process_batch_u8), dequantised on device */
+} dab_ofdm_options;
+
+/* Replaces On_OFDM_Frame().Attach(...) (ofdm_demodulator.h:140).  `bits` is owned by the library and valid only during the
+ * call, like the reference's span over m_pipeline_out_bits (ofdm_demodulator.cpp:110,635).  Called on the thread that
+ * invoked the process/sync entry point, in frame order per stream. */
+typedef void (*dab_ofdm_frame_cb)(void* user, int stream, const int8_t* bits, size_t n_bits, const dab_ofdm_frame_info* info);
+
+/* OFDM_Demod::OFDM_Demod(params, prs_fft_ref, carrier_mapper, nb_desired_threads) -- the thread count has no meaning here */
+DAB_API dab_ofdm* dab_ofdm_create(const dab_ofdm_params* params, const dab_c32* prs_fft_ref, const int* carrier_mapper,
+                                  const dab_ofdm_options* options, int* status);
+DAB_API void dab_ofdm_destroy(dab_ofdm* h);
+/* run the kernels on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the handle's own stream */
+DAB_API int dab_ofdm_set_cuda_stream(dab_ofdm* h, void* cuda_stream);
+DAB_API int dab_ofdm_set_frame_callback(dab_ofdm* h, dab_ofdm_frame_cb cb, void* user);
+/* GetConfig() is mutable between Process calls (examples/basic_radio_app.cpp:268-269); stream = -1 applies to all */
+DAB_API int dab_ofdm_set_config(dab_ofdm* h, int stream, const dab_ofdm_config* cfg);
+DAB_API int dab_ofdm_get_config(dab_ofdm* h, int stream, dab_ofdm_config* cfg);
+DAB_API void dab_ofdm_default_config(dab_ofdm_config* cfg);
+
+/* OFDM_Demod::Process(span<const complex<float>>) for one stream: host buffer, copied before return; frames completed by
+ * this block are delivered through the callback before the call returns. */
+DAB_API int dab_ofdm_process(dab_ofdm* h, int stream, const dab_c32* iq, size_t n);
+/* The same for every stream at once: iq[s] / n[s] for s < n_streams (n[s] may be 0, iq[s] may then be NULL). */
+DAB_API int dab_ofdm_process_batch(dab_ofdm* h, const dab_c32* const* iq, const size_t* n);
+/* raw 8-bit IQ (examples/app_helpers/app_iq_readers.h:17-69): sample = (u8 - 127.5) / 127.5, dequantised on the device */
+DAB_API int dab_ofdm_process_batch_u8(dab_ofdm* h, const uint8_t* const* iq_u8, const size_t* n);
+
+/* Device-resident streams (the batched B200 path): d_iq points at n_streams rows of `stride_samples` samples already in
+ * HBM.  The demodulator then reads the rows in place -- no ring copy.  dab_ofdm_advance(h, n) is one Process() call of n[s]
+ * further samples per stream.  Soft bits stay on the device (dab_ofdm_device_bits) unless a callback is attached. */
+DAB_API int dab_ofdm_attach_device_streams(dab_ofdm* h, const dab_c32* d_iq, size_t stride_samples, size_t total_samples);
+DAB_API int dab_ofdm_advance(dab_ofdm* h, const size_t* n);
+DAB_API int dab_ofdm_advance_uniform(dab_ofdm* h, size_t n);
+/* device pointer / geometry of the soft-bit output of the most recent process/advance call:
+ * bits[stream][slot][n_bits], frames_in_call[stream] = how many slots are valid */
+DAB_API int dab_ofdm_device_bits(dab_ofdm* h, const int8_t** d_bits, size_t* n_bits, int* slots_per_stream, const int32_t** d_frames_in_call);
+
+DAB_API int dab_ofdm_reset(dab_ofdm* h, int stream);           /* OFDM_Demod::Reset() */
+DAB_API int dab_ofdm_get_state(dab_ofdm* h, int stream, dab_ofdm_state* out);
+DAB_API int dab_ofdm_sync(dab_ofdm* h);                        /* wait for queued GPU work, deliver pending callbacks */
+DAB_API size_t dab_ofdm_frame_bits(const dab_ofdm* h);         /* (nb_frame_symbols-1)*nb_data_carriers*2 */
+DAB_API int dab_ofdm_get_params(const dab_ofdm* h, dab_ofdm_params* out); /* GetOFDMParams() */
+/* GUI getters (ofdm_demodulator.h:133-139), latest values for one stream copied to host memory */
+DAB_API int dab_ofdm_get_impulse_response(dab_ofdm* h, int stream, float* out, size_t nb_fft);
+DAB_API int dab_ofdm_get_coarse_frequency_response(dab_ofdm* h, int stream, float* out, size_t nb_fft);
+DAB_API int dab_ofdm_get_frame_data_bits(dab_ofdm* h, int stream, int8_t* out, size_t n_bits);
+DAB_API int dab_ofdm_get_frame_fft(dab_ofdm* h, int stream, dab_c32* out, size_t n);      /* needs keep_debug_taps */
+DAB_API int dab_ofdm_get_frame_data_vec(dab_ofdm* h, int stream, dab_c32* out, size_t n); /* needs keep_debug_taps */
+/* number of library kernels launched so far by this handle (bench.py's gpu_launches) */
+DAB_API uint64_t dab_ofdm_kernel_launches(const dab_ofdm* h);
+
+/* Stage-level entry used by the parity tests and the roofline measurement: demodulate already aligned frames.
+ * d_frames: n_frames rows of frame_stride samples, row = PRS + data symbols (nb_frame_symbols * nb_symbol_period samples);
+ * freq_offset[n_frames] (host); d_bits: n_frames * frame_bits; d_phase_error: n_frames * nb_frame_symbols floats (per symbol). */
+DAB_API int dab_ofdm_demod_frames_device(dab_ofdm* h, const dab_c32* d_frames, size_t frame_stride, int n_frames,
+                                         const float* freq_offset, int8_t* d_bits, float* d_phase_error);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Viterbi decoder (replaces DAB_Viterbi_Decoder, src/dab/algorithms/dab_viterbi_decoder.h:24-33, on top of
+ * vendor/viterbi_decoder ViterbiDecoder_AVX_u16<7,4>): K = 7, rate 1/4 mother code G = {109, 79, 83, 109}, int8 soft input,
+ * saturating u16 path metrics, tie -> predecessor 1, renormalisation at 60455.  Output is bit-exact with that decoder.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct dab_viterbi dab_viterbi;
+
+#define DAB_VIT_MAX_SEGMENTS 8
+#define DAB_VIT_MAX_SCHEDULES 1024
+
+/* one update(punctured, puncture_code, requested_output_symbols) call (dab_viterbi_decoder.h:26-30) */
+typedef struct {
+    uint8_t counts[8];   /* puncture code as kept-symbol counts per group of 4 mother symbols (puncture_codes.h:42-67) */
+    uint32_t code_len;   /* 1..8, the code is applied cyclically */
+    uint32_t n_out;      /* requested_output_symbols, multiple of 4 */
+} dab_vit_segment;
+
+/* reset(start_state); update(...) x n_seg; chainback(n_out_bytes, end_state) */
+typedef struct {
+    dab_vit_segment seg[DAB_VIT_MAX_SEGMENTS];
+    uint32_t n_seg;
+    uint32_t n_out_bytes;
+    uint32_t start_state;
+    uint32_t end_state;
+} dab_vit_schedule;
+
+typedef struct {
+    uint32_t schedule;     /* id from dab_viterbi_add_schedule */
+    uint32_t n_soft;       /* punctured symbols available at soft_offset */
+    uint64_t soft_offset;  /* into the soft buffer */
+    uint64_t out_offset;   /* into the output byte buffer */
+} dab_vit_job;
+
+DAB_API dab_viterbi* dab_viterbi_create(int device, int* status);
+DAB_API void dab_viterbi_destroy(dab_viterbi* h);
+DAB_API int dab_viterbi_set_cuda_stream(dab_viterbi* h, void* cuda_stream);
+DAB_API int dab_viterbi_add_schedule(dab_viterbi* h, const dab_vit_schedule* s); /* >= 0: id */
+/* punctured symbols consumed by a schedule (what the update() calls would return in total) */
+DAB_API int64_t dab_viterbi_schedule_soft_symbols(const dab_vit_schedule* s);
+/* host buffers in, host buffers out; path_error[n_jobs] may be NULL; job_status[n_jobs] (dab_status per job) may be NULL */
+DAB_API int dab_viterbi_decode_batch(dab_viterbi* h, const int8_t* soft, size_t soft_bytes, const dab_vit_job* jobs, int n_jobs,
+                                     uint8_t* out, size_t out_bytes, uint64_t* path_error, int32_t* job_status);
+/* device buffers in and out, jobs on the host; asynchronous on the handle's stream */
+DAB_API int dab_viterbi_decode_batch_device(dab_viterbi* h, const int8_t* d_soft, size_t soft_bytes, const dab_vit_job* jobs,
+                                            int n_jobs, uint8_t* d_out, size_t out_bytes, uint64_t* d_path_error, int32_t* d_job_status);
+/* jobs already on the device too (nothing crosses PCIe; used by the roofline measurement) */
+DAB_API int dab_viterbi_decode_jobs_device(dab_viterbi* h, const int8_t* d_soft, size_t soft_bytes, const dab_vit_job* d_jobs,
+                                           int n_jobs, uint32_t max_steps, uint8_t* d_out, size_t out_bytes,
+                                           uint64_t* d_path_error, int32_t* d_job_status);
+DAB_API int dab_viterbi_sync(dab_viterbi* h);
+DAB_API uint64_t dab_viterbi_kernel_launches(const dab_viterbi* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

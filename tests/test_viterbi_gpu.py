@@ -1,0 +1,135 @@
+"""GPU parity: CUDA Viterbi (through the C ABI) vs the oracle restatement of DAB_Viterbi_Decoder -- bit-exact bytes and
+equal u64 path error on identical soft bits (north_star)."""
+import importlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _segments(po, spec):
+    return [(po.puncture_code(pi) if pi else po.PI_X, n) for pi, n in spec]
+
+
+def _make_case(po, rng, spec, n_bytes, sigma, garbage=None):
+    segs = _segments(po, spec)
+    if garbage is None:
+        data = rng.integers(0, 256, n_bytes, dtype=np.uint8)
+        tx = po.puncture(po.conv_encode(data), segs)
+        rx = np.clip(np.rint(tx + sigma * rng.standard_normal(tx.size)), -128, 127).astype(np.int8)
+    else:
+        n_soft = sum(int(np.resize(c, n // 4).astype(np.int64).sum()) for c, n in segs)
+        rx = garbage(n_soft)
+    return segs, rx
+
+
+FIC = [(16, 128 * 21), (15, 128 * 3), (0, 24)]
+EEP_3A_48CU = [(8, 128 * 45), (7, 128 * 3), (0, 24)]      # 6n-3, 3 blocks with n = 8 (subchannel_protection_tables.h:121-126)
+UEP_ROW0 = [(5, 128 * 3), (3, 128 * 4), (2, 128 * 17), (0, 24)]
+
+
+@pytest.fixture(scope="module")
+def vit(pkg):
+    v = importlib.import_module("dab-radio_b200.viterbi")
+    return v
+
+
+def _run_batch(vit, po, cases, n_out_bytes_list):
+    vb = vit.ViterbiBatch(0)
+    jobs = np.zeros(len(cases), vit.capi.VIT_JOB_DTYPE)
+    soft_all, out_off, soft_off = [], 0, 0
+    sched_cache = {}
+    for i, ((segs, rx), nb) in enumerate(zip(cases, n_out_bytes_list)):
+        key = (tuple((tuple(c.tolist()), n) for c, n in segs), nb)
+        if key not in sched_cache:
+            sched_cache[key] = vb.add_schedule(vit.make_schedule(segs, nb))
+        jobs[i] = (sched_cache[key], rx.size, soft_off, out_off)
+        soft_all.append(rx)
+        soft_off += rx.size
+        out_off += nb
+    out, err, st = vb.decode_batch(np.concatenate(soft_all), jobs, out_off)
+    assert np.all(st == 0)
+    o = po.OracleViterbi()
+    off = 0
+    for i, ((segs, rx), nb) in enumerate(zip(cases, n_out_bytes_list)):
+        o.set_traceback_length(nb * 8)
+        ref_out, ref_err, used = o.decode_job(rx, segs, nb)
+        assert used == rx.size
+        got = out[off:off + nb]
+        assert np.array_equal(got, ref_out), f"job {i}: {np.count_nonzero(got != ref_out)} bytes differ"
+        assert int(err[i]) == ref_err, f"job {i}: path error {int(err[i])} != {ref_err}"
+        off += nb
+    assert vb.kernel_launches() >= 1
+    vb.close()
+
+
+def test_fic_noise_sweep(vit, oracle):
+    rng = np.random.default_rng(11)
+    cases = [_make_case(oracle, rng, FIC, 96, sigma) for sigma in (0, 40, 80, 120, 200) for _ in range(40)]
+    _run_batch(vit, oracle, cases, [96] * len(cases))
+
+
+def test_fic_noiseless_roundtrip(vit, oracle):
+    """reference vendor test run_punctured_decoder.cpp:139-191: FIC schedule, no noise, zero bit errors"""
+    rng = np.random.default_rng(3)
+    vb = vit.ViterbiBatch(0)
+    sid = vb.add_schedule(vit.fic_schedule())
+    n = 64
+    data = rng.integers(0, 256, (n, 96), dtype=np.uint8)
+    segs = _segments(oracle, FIC)
+    soft = np.concatenate([oracle.puncture(oracle.conv_encode(d), segs) for d in data])
+    jobs = np.zeros(n, vit.capi.VIT_JOB_DTYPE)
+    for i in range(n):
+        jobs[i] = (sid, 2304, i * 2304, i * 96)
+    out, err, st = vb.decode_batch(soft, jobs, n * 96)
+    assert np.array_equal(out.reshape(n, 96), data)
+    assert np.all(err == 792 * 127)  # every punctured position costs |+-127 - 0| on the surviving path
+    vb.close()
+
+
+def test_mixed_schedules_one_launch(vit, oracle):
+    rng = np.random.default_rng(5)
+    cases, nbytes = [], []
+    for spec, nb in ((FIC, 96), (EEP_3A_48CU, 192), (UEP_ROW0, 96)):
+        for sigma in (0, 60, 130):
+            for _ in range(6):
+                cases.append(_make_case(oracle, rng, spec, nb, sigma))
+                nbytes.append(nb)
+    _run_batch(vit, oracle, cases, nbytes)
+
+
+def test_adversarial_ties_and_saturation(vit, oracle):
+    """all-zero (every comparison ties), all -128 / +127 and alternating extremes (fast metric growth, renormalisation,
+    saturating adds), random garbage -- SURVEY.md 8(c)"""
+    rng = np.random.default_rng(9)
+    gens = [lambda n: np.zeros(n, np.int8), lambda n: np.full(n, -128, np.int8), lambda n: np.full(n, 127, np.int8),
+            lambda n: rng.integers(-128, 128, n).astype(np.int8), lambda n: np.where(np.arange(n) % 2, 127, -128).astype(np.int8),
+            lambda n: np.where(np.arange(n) % 5 < 2, -128, 127).astype(np.int8)]
+    cases, nbytes = [], []
+    for g in gens:
+        for pi in (1, 8, 16, 24):
+            L = 60
+            cases.append(_make_case(oracle, rng, [(pi, 128 * L), (0, 24)], 0, 0, garbage=g))
+            nbytes.append(128 * L // 4 // 8)
+    _run_batch(vit, oracle, cases, nbytes)
+
+
+def test_long_trellis_spills_to_global(vit, oracle):
+    """a sub-channel longer than the shared-memory window (EEP 4-B filling most of a CIF)"""
+    rng = np.random.default_rng(21)
+    L = 24 * 12 - 3  # n = 12 -> 180 CU at 4-B
+    spec = [(2, 128 * L), (1, 128 * 3), (0, 24)]
+    nb = (128 * (L + 3)) // 4 // 8
+    cases = [_make_case(oracle, rng, spec, nb, sigma) for sigma in (0, 100)]
+    _run_batch(vit, oracle, cases, [nb] * 2)
+
+
+def test_underrun_is_reported(vit, oracle):
+    vb = vit.ViterbiBatch(0)
+    sid = vb.add_schedule(vit.fic_schedule())
+    jobs = np.zeros(1, vit.capi.VIT_JOB_DTYPE)
+    jobs[0] = (sid, 2000, 0, 0)
+    out, err, st = vb.decode_batch(np.zeros(2304, np.int8), jobs, 96, raise_on_job_error=False)
+    assert st[0] == vit.capi.DAB_ERR_UNDERRUN
+    vb.close()
