@@ -124,9 +124,6 @@ def load():
     L.dab_get_mapper_reference.argtypes = [vp, sz, sz]
     L.dab_get_puncture_code.argtypes = [i32, C.POINTER(C.c_uint8 * 8)]
     # OFDM
-    if not hasattr(L, 'dab_ofdm_create'):  # TEMPORARY while the OFDM translation units are being written
-        _lib = L
-        return _bind_viterbi(L)
     L.dab_ofdm_create.argtypes = [C.POINTER(OfdmParams), vp, vp, C.POINTER(OfdmOptions), ip]
     L.dab_ofdm_create.restype = vp
     L.dab_ofdm_destroy.argtypes = [vp]

@@ -1,0 +1,655 @@
+// Host side of the OFDM demodulator C ABI (include/dab_b200.h): owns the per-stream device state, feeds the stream rings,
+// sequences  control -> frame kernel -> control  passes per Process() call and delivers the soft-bit callback.
+// Replaces OFDM_Demod's constructor / Process / Reset / getters (reference src/ofdm/ofdm_demodulator.cpp:80-146, 235-289)
+// and its coordinator / pipeline threads (ofdm_demodulator_threads.cpp), whose ordering becomes CUDA stream order.
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "ofdm_control.cuh"
+#include "ofdm_frame.cuh"
+
+namespace dabb200 {
+
+__global__ void ofdm_begin_call_kernel(StreamState* states, const uint64_t* n_per_stream, uint64_t n_uniform, int n_streams) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    StreamState& st = states[s];
+    const uint64_t n = n_per_stream ? n_per_stream[s] : n_uniform;
+    st.call_begin = st.call_end;
+    st.call_end = st.call_begin + int64_t(n);
+    st.call_needs_average = (n > 0) ? 1 : 0;
+    st.frames_in_call = 0;
+}
+
+__global__ void ofdm_reset_stream_kernel(StreamState* states, int stream) {
+    // OFDM_Demod::Reset (ofdm_demodulator.cpp:277-289)
+    StreamState& st = states[stream];
+    st.state = DAB_OFDM_FINDING_NULL_POWER_DIP;
+    st.corr_length = 0;
+    st.corr_explicit_len = 0;
+    st.total_frames_desync++;
+    st.is_found_coarse = 0;
+    st.freq_coarse = 0.0f;
+    st.freq_fine = 0.0f;
+    st.fine_time_offset = 0;
+}
+
+struct Ofdm {
+    dab_ofdm_params p{};
+    int nfft = 0;
+    int n_streams = 0;
+    int device = 0;
+    bool raw_u8 = false;
+    bool debug_taps = false;
+    size_t max_block = 0;
+    size_t ring_samples = 0;
+    int slots = 1;
+    size_t frame_bits = 0;
+    int syms_per_chunk = 25;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    // device memory
+    DeviceBuffer<unsigned char> ring_iq;
+    DeviceBuffer<float2> null_ring, corr_explicit, prs_fft_ref_conj, prs_time_ref_conj, fft_tap, vec_tap;
+    DeviceBuffer<float> impulse, freq_resp, phase_err, stage_phase_err;
+    DeviceBuffer<StreamState> states;
+    DeviceBuffer<FrameDesc> descs, stage_descs;
+    DeviceBuffer<dab_ofdm_frame_info> infos;
+    DeviceBuffer<int32_t> frames_in_call;
+    DeviceBuffer<int8_t> bits;
+    DeviceBuffer<int16_t> bin_to_pos, bin_to_carrier;
+    DeviceBuffer<uint64_t> d_n;
+    // external (device resident) streams
+    const void* ext_base = nullptr;
+    size_t ext_stride = 0, ext_total = 0;
+    // host bookkeeping
+    std::vector<uint64_t> fed;       // samples handed to each stream so far
+    std::vector<uint64_t> n_call;
+    PinnedBuffer<uint64_t> h_n;
+    PinnedBuffer<int32_t> h_frames;
+    PinnedBuffer<dab_ofdm_frame_info> h_infos;
+    PinnedBuffer<int8_t> h_bits;
+    dab_ofdm_frame_cb cb = nullptr;
+    void* cb_user = nullptr;
+    uint64_t launches = 0;
+    std::mutex mtx;
+};
+
+static void host_fft(std::vector<std::complex<double>>& x, int sign) {
+    const size_t n = x.size();
+    for (size_t i = 1, j = 0; i < n; i++) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(x[i], x[j]);
+    }
+    const double two_pi = 6.283185307179586476925286766559;
+    for (size_t len = 2; len <= n; len <<= 1) {
+        for (size_t k = 0; k < len / 2; k++) {
+            const double a = double(sign) * two_pi * double(k) / double(len);
+            const std::complex<double> w(std::cos(a), std::sin(a));
+            for (size_t base = 0; base < n; base += len) {
+                const auto u = x[base + k], t = x[base + k + len / 2] * w;
+                x[base + k] = u + t;
+                x[base + k + len / 2] = u - t;
+            }
+        }
+    }
+}
+
+static FrameGeom frame_geom(const Ofdm* o) {
+    FrameGeom g;
+    g.n_symbols = int(o->p.nb_frame_symbols);
+    g.symbol_period = int(o->p.nb_symbol_period);
+    g.cyclic_prefix = int(o->p.nb_cyclic_prefix);
+    g.n_carriers = int(o->p.nb_data_carriers);
+    g.syms_per_chunk = o->syms_per_chunk;
+    g.n_chunks = (g.n_symbols - 1 + g.syms_per_chunk - 1) / g.syms_per_chunk;
+    g.bin_to_pos = o->bin_to_pos.ptr;
+    g.bin_to_carrier = o->bin_to_carrier.ptr;
+    return g;
+}
+
+template <int NFFT, bool RAW>
+static int launch_frame_t(Ofdm* o, const FrameDesc* d_descs, int n_frames) {
+    const FrameGeom g = frame_geom(o);
+    const size_t smem = FrameSmem<NFFT>::total_bytes(g.n_carriers);
+    DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_kernel<NFFT, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    constexpr int GROUPS = FrameSmem<NFFT>::GROUPS;
+    const int n_items = n_frames * g.n_chunks;
+    const int grid = (n_items + GROUPS - 1) / GROUPS;
+    ofdm_frame_kernel<NFFT, RAW><<<grid, FRAME_CTA_THREADS, smem, o->stream>>>(g, d_descs, n_frames);
+    o->launches++;
+    DAB_CUDA_CHECK(cudaGetLastError());
+    return DAB_OK;
+}
+
+static int launch_frame(Ofdm* o, const FrameDesc* d_descs, int n_frames, bool raw) {
+    if (n_frames <= 0) return DAB_OK;
+    switch (o->nfft) {
+    case 2048: return raw ? launch_frame_t<2048, true>(o, d_descs, n_frames) : launch_frame_t<2048, false>(o, d_descs, n_frames);
+    case 1024: return raw ? launch_frame_t<1024, true>(o, d_descs, n_frames) : launch_frame_t<1024, false>(o, d_descs, n_frames);
+    case 512: return raw ? launch_frame_t<512, true>(o, d_descs, n_frames) : launch_frame_t<512, false>(o, d_descs, n_frames);
+    case 256: return raw ? launch_frame_t<256, true>(o, d_descs, n_frames) : launch_frame_t<256, false>(o, d_descs, n_frames);
+    }
+    return set_error(DAB_ERR_INVALID, "unsupported FFT size %d", o->nfft);
+}
+
+static ControlGeom control_geom(const Ofdm* o) {
+    ControlGeom g;
+    g.n_symbols = int(o->p.nb_frame_symbols);
+    g.symbol_period = int(o->p.nb_symbol_period);
+    g.null_period = int(o->p.nb_null_period);
+    g.cyclic_prefix = int(o->p.nb_cyclic_prefix);
+    g.n_carriers = int(o->p.nb_data_carriers);
+    g.slots = o->slots;
+    g.frame_bits = o->frame_bits;
+    if (o->ext_base) {
+        g.mask = ~uint64_t(0);
+        g.stream_stride = o->ext_stride;
+        g.samples = o->ext_base;
+    } else {
+        g.mask = uint64_t(o->ring_samples) - 1;
+        g.stream_stride = o->ring_samples;
+        g.samples = o->ring_iq.ptr;
+    }
+    g.ring = o->null_ring.ptr;
+    g.corr_explicit = o->corr_explicit.ptr;
+    g.prs_fft_ref_conj = o->prs_fft_ref_conj.ptr;
+    g.prs_time_ref_conj = o->prs_time_ref_conj.ptr;
+    g.impulse_response = o->impulse.ptr;
+    g.freq_response = o->freq_resp.ptr;
+    g.states = o->states.ptr;
+    g.descs = o->descs.ptr;
+    g.infos = o->infos.ptr;
+    g.frames_in_call = o->frames_in_call.ptr;
+    g.bits = o->bits.ptr;
+    g.phase_err = o->phase_err.ptr;
+    g.fft_tap = o->debug_taps ? o->fft_tap.ptr : nullptr;
+    g.vec_tap = o->debug_taps ? o->vec_tap.ptr : nullptr;
+    return g;
+}
+
+template <int NFFT, bool RAW>
+static int launch_control_t(Ofdm* o, int pass) {
+    const ControlGeom g = control_geom(o);
+    const size_t smem = ControlSmem<NFFT>::bytes();
+    DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_control_kernel<NFFT, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    ofdm_control_kernel<NFFT, RAW><<<o->n_streams, ControlSmem<NFFT>::THREADS, smem, o->stream>>>(g, pass);
+    o->launches++;
+    DAB_CUDA_CHECK(cudaGetLastError());
+    return DAB_OK;
+}
+
+static int launch_control(Ofdm* o, int pass) {
+    const bool raw = o->raw_u8;
+    switch (o->nfft) {
+    case 2048: return raw ? launch_control_t<2048, true>(o, pass) : launch_control_t<2048, false>(o, pass);
+    case 1024: return raw ? launch_control_t<1024, true>(o, pass) : launch_control_t<1024, false>(o, pass);
+    case 512: return raw ? launch_control_t<512, true>(o, pass) : launch_control_t<512, false>(o, pass);
+    case 256: return raw ? launch_control_t<256, true>(o, pass) : launch_control_t<256, false>(o, pass);
+    }
+    return set_error(DAB_ERR_INVALID, "unsupported FFT size %d", o->nfft);
+}
+
+static size_t sample_bytes(const Ofdm* o) { return o->raw_u8 ? 2 : sizeof(float2); }
+
+// frame completions possible inside one call of n samples: consecutive frame ends are at least frame_cap - cp apart
+static int passes_for(const Ofdm* o, uint64_t n_max) {
+    if (n_max == 0) return 0;
+    const uint64_t frame_cap = o->p.nb_frame_symbols * o->p.nb_symbol_period + o->p.nb_null_period;
+    return 1 + int((n_max - 1) / (frame_cap - o->p.nb_cyclic_prefix));
+}
+
+// one Process() call for every stream: n_call[s] new samples are already visible at [fed[s], fed[s] + n_call[s])
+static int run_call(Ofdm* o, bool uniform, uint64_t n_uniform) {
+    uint64_t n_max = 0;
+    if (uniform) {
+        n_max = n_uniform;
+    } else {
+        for (int s = 0; s < o->n_streams; s++) n_max = std::max(n_max, o->n_call[size_t(s)]);
+        DAB_CUDA_CHECK(o->h_n.reserve(size_t(o->n_streams)));
+        memcpy(o->h_n.ptr, o->n_call.data(), sizeof(uint64_t) * size_t(o->n_streams));
+        DAB_CUDA_CHECK(cudaMemcpyAsync(o->d_n.ptr, o->h_n.ptr, sizeof(uint64_t) * size_t(o->n_streams), cudaMemcpyHostToDevice, o->stream));
+    }
+    const int threads = 128;
+    ofdm_begin_call_kernel<<<(o->n_streams + threads - 1) / threads, threads, 0, o->stream>>>(o->states.ptr, uniform ? nullptr : o->d_n.ptr,
+                                                                                            n_uniform, o->n_streams);
+    o->launches++;
+    DAB_CUDA_CHECK(cudaGetLastError());
+    const int passes = passes_for(o, n_max);
+    if (passes > o->slots) return set_error(DAB_ERR_CAPACITY, "call of %llu samples exceeds max_block_samples", (unsigned long long)n_max);
+    for (int p = 0; p <= passes; p++) {
+        int rc = launch_control(o, p);
+        if (rc != DAB_OK) return rc;
+        if (p < passes) {
+            rc = launch_frame(o, o->descs.ptr + size_t(p) * size_t(o->n_streams), o->n_streams, o->raw_u8);
+            if (rc != DAB_OK) return rc;
+        }
+    }
+    for (int s = 0; s < o->n_streams; s++) o->fed[size_t(s)] += uniform ? n_uniform : o->n_call[size_t(s)];
+    return DAB_OK;
+}
+
+// soft-bit callback delivery (CoordinatorThread's Notify, ofdm_demodulator.cpp:635), in stream then frame order
+static int deliver(Ofdm* o) {
+    if (!o->cb) return DAB_OK;
+    const size_t ns = size_t(o->n_streams), slots = size_t(o->slots);
+    DAB_CUDA_CHECK(o->h_frames.reserve(ns));
+    DAB_CUDA_CHECK(o->h_infos.reserve(ns * slots));
+    DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_frames.ptr, o->frames_in_call.ptr, ns * sizeof(int32_t), cudaMemcpyDeviceToHost, o->stream));
+    DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_infos.ptr, o->infos.ptr, ns * slots * sizeof(dab_ofdm_frame_info), cudaMemcpyDeviceToHost, o->stream));
+    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
+    size_t total = 0;
+    for (size_t s = 0; s < ns; s++) total += size_t(std::max(0, o->h_frames.ptr[s]));
+    if (total == 0) return DAB_OK;
+    DAB_CUDA_CHECK(o->h_bits.reserve(total * o->frame_bits));
+    size_t k = 0;
+    for (size_t s = 0; s < ns; s++)
+        for (int f = 0; f < o->h_frames.ptr[s]; f++, k++)
+            DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_bits.ptr + k * o->frame_bits, o->bits.ptr + (s * slots + size_t(f)) * o->frame_bits, o->frame_bits,
+                                           cudaMemcpyDeviceToHost, o->stream));
+    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
+    k = 0;
+    for (size_t s = 0; s < ns; s++)
+        for (int f = 0; f < o->h_frames.ptr[s]; f++, k++)
+            o->cb(o->cb_user, int(s), o->h_bits.ptr + k * o->frame_bits, o->frame_bits, &o->h_infos.ptr[s * slots + size_t(f)]);
+    return DAB_OK;
+}
+
+static int init_states(Ofdm* o) {
+    std::vector<StreamState> init(size_t(o->n_streams));
+    for (auto& st : init) {
+        memset(&st, 0, sizeof(st));
+        st.state = DAB_OFDM_FINDING_NULL_POWER_DIP;
+        dab_ofdm_default_config(&st.cfg);
+    }
+    DAB_CUDA_CHECK(cudaMemcpy(o->states.ptr, init.data(), init.size() * sizeof(StreamState), cudaMemcpyHostToDevice));
+    DAB_CUDA_CHECK(cudaMemset(o->null_ring.ptr, 0, o->null_ring.count * sizeof(float2)));
+    DAB_CUDA_CHECK(cudaMemset(o->frames_in_call.ptr, 0, o->frames_in_call.count * sizeof(int32_t)));
+    DAB_CUDA_CHECK(cudaMemset(o->descs.ptr, 0, o->descs.count * sizeof(FrameDesc)));
+    std::fill(o->fed.begin(), o->fed.end(), 0);
+    return DAB_OK;
+}
+
+static int create_impl(Ofdm* o, const dab_c32* prs, const int* mapper) {
+    const size_t nfft = o->p.nb_fft, ncarr = o->p.nb_data_carriers, ns = size_t(o->n_streams);
+    const size_t frame_cap = o->p.nb_frame_symbols * o->p.nb_symbol_period + o->p.nb_null_period;
+    o->frame_bits = (o->p.nb_frame_symbols - 1) * ncarr * 2;
+    o->slots = std::max(1, passes_for(o, o->max_block));
+    size_t need = frame_cap + o->p.nb_null_period + o->p.nb_symbol_period + o->max_block + 1024;
+    o->ring_samples = 1;
+    while (o->ring_samples < need) o->ring_samples <<= 1;
+
+    // constant tables: conj(PRS) and conj(IFFT(conj(PRS[i]) PRS[i+1])) (ofdm_demodulator.cpp:128-140), bin -> soft-bit position
+    std::vector<float2> ref_conj(nfft), time_conj(nfft);
+    std::vector<std::complex<double>> rel(nfft);
+    for (size_t i = 0; i < nfft; i++) ref_conj[i] = make_float2(prs[i].re, -prs[i].im);
+    for (size_t i = 0; i + 1 < nfft; i++) {
+        const float ar = prs[i].re, ai = -prs[i].im, br = prs[i + 1].re, bi = prs[i + 1].im;
+        rel[i] = std::complex<double>(double(ar * br - ai * bi), double(ar * bi + ai * br));
+    }
+    rel[nfft - 1] = 0.0;
+    host_fft(rel, +1);
+    for (size_t i = 0; i < nfft; i++) time_conj[i] = make_float2(float(rel[i].real()), -float(rel[i].imag()));
+    std::vector<int16_t> b2p(nfft, int16_t(-1)), b2c(nfft, int16_t(-1));
+    std::vector<int> inverse(ncarr, -1);
+    for (size_t i = 0; i < ncarr; i++) {
+        if (mapper[i] < 0 || size_t(mapper[i]) >= ncarr) return set_error(DAB_ERR_INVALID, "carrier_mapper[%zu] = %d out of range", i, mapper[i]);
+        inverse[size_t(mapper[i])] = int(i);
+    }
+    const int half = int(ncarr / 2);
+    for (int c = 0; c < 2 * half; c++) {  // CalculateDQPSK carrier order: -M..-1, +1..+M (ofdm_demodulator.cpp:853-864)
+        const int k = (c < half) ? (c - half) : (c - half + 1);
+        const size_t bin = size_t((int(nfft) + k) % int(nfft));
+        b2c[bin] = int16_t(c);
+        b2p[bin] = int16_t(inverse[size_t(c)]);
+    }
+
+    DAB_CUDA_CHECK(cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking));
+    o->stream = o->own_stream;
+    DAB_CUDA_CHECK(o->ring_iq.reserve(ns * o->ring_samples * sample_bytes(o)));
+    DAB_CUDA_CHECK(cudaMemset(o->ring_iq.ptr, 0, ns * o->ring_samples * sample_bytes(o)));
+    DAB_CUDA_CHECK(o->null_ring.reserve(ns * o->p.nb_null_period));
+    DAB_CUDA_CHECK(o->corr_explicit.reserve(ns * o->p.nb_null_period));
+    DAB_CUDA_CHECK(o->prs_fft_ref_conj.reserve(nfft));
+    DAB_CUDA_CHECK(o->prs_time_ref_conj.reserve(nfft));
+    DAB_CUDA_CHECK(o->impulse.reserve(ns * nfft));
+    DAB_CUDA_CHECK(o->freq_resp.reserve(ns * nfft));
+    DAB_CUDA_CHECK(cudaMemset(o->impulse.ptr, 0, ns * nfft * sizeof(float)));
+    DAB_CUDA_CHECK(cudaMemset(o->freq_resp.ptr, 0, ns * nfft * sizeof(float)));
+    DAB_CUDA_CHECK(o->states.reserve(ns));
+    DAB_CUDA_CHECK(o->descs.reserve(ns * size_t(o->slots)));
+    DAB_CUDA_CHECK(o->infos.reserve(ns * size_t(o->slots)));
+    DAB_CUDA_CHECK(o->frames_in_call.reserve(ns));
+    DAB_CUDA_CHECK(o->bits.reserve(ns * size_t(o->slots) * o->frame_bits));
+    DAB_CUDA_CHECK(cudaMemset(o->bits.ptr, 0, ns * size_t(o->slots) * o->frame_bits));
+    DAB_CUDA_CHECK(o->phase_err.reserve(ns * size_t(o->slots) * o->p.nb_frame_symbols));
+    DAB_CUDA_CHECK(o->bin_to_pos.reserve(nfft));
+    DAB_CUDA_CHECK(o->bin_to_carrier.reserve(nfft));
+    DAB_CUDA_CHECK(o->d_n.reserve(ns));
+    if (o->debug_taps) {
+        DAB_CUDA_CHECK(o->fft_tap.reserve(ns * o->p.nb_frame_symbols * nfft));
+        DAB_CUDA_CHECK(o->vec_tap.reserve(ns * (o->p.nb_frame_symbols - 1) * ncarr));
+        DAB_CUDA_CHECK(cudaMemset(o->fft_tap.ptr, 0, o->fft_tap.count * sizeof(float2)));
+        DAB_CUDA_CHECK(cudaMemset(o->vec_tap.ptr, 0, o->vec_tap.count * sizeof(float2)));
+    }
+    DAB_CUDA_CHECK(cudaMemcpy(o->prs_fft_ref_conj.ptr, ref_conj.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice));
+    DAB_CUDA_CHECK(cudaMemcpy(o->prs_time_ref_conj.ptr, time_conj.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice));
+    DAB_CUDA_CHECK(cudaMemcpy(o->bin_to_pos.ptr, b2p.data(), nfft * sizeof(int16_t), cudaMemcpyHostToDevice));
+    DAB_CUDA_CHECK(cudaMemcpy(o->bin_to_carrier.ptr, b2c.data(), nfft * sizeof(int16_t), cudaMemcpyHostToDevice));
+    o->fed.assign(ns, 0);
+    o->n_call.assign(ns, 0);
+    return init_states(o);
+}
+
+}  // namespace dabb200
+
+using namespace dabb200;
+
+extern "C" {
+
+void dab_ofdm_default_config(dab_ofdm_config* c) {
+    if (!c) return;
+    c->signal_l1_update_beta = 0.95f;
+    c->signal_l1_nb_samples = 100;
+    c->signal_l1_nb_decimate = 5;
+    c->null_l1_thresh_null_start = 0.35f;
+    c->null_l1_thresh_null_end = 0.75f;
+    c->sync_fine_freq_update_beta = 0.9f;
+    c->sync_is_coarse_freq_correction = 1;
+    c->sync_max_coarse_freq_correction_norm = 0.5f;
+    c->sync_coarse_freq_slow_beta = 0.1f;
+    c->sync_impulse_peak_threshold_db = 20.0f;
+    c->sync_impulse_peak_distance_probability = 0.15f;
+}
+
+dab_ofdm* dab_ofdm_create(const dab_ofdm_params* params, const dab_c32* prs_fft_ref, const int* carrier_mapper, const dab_ofdm_options* options,
+                          int* status) {
+    auto fail = [&](int rc) -> dab_ofdm* { if (status) *status = rc; return nullptr; };
+    if (!params || !prs_fft_ref || !carrier_mapper || !options) return fail(set_error(DAB_ERR_INVALID, "null argument"));
+    if (options->n_streams < 1) return fail(set_error(DAB_ERR_INVALID, "n_streams must be >= 1"));
+    const size_t nfft = params->nb_fft;
+    if (nfft != 256 && nfft != 512 && nfft != 1024 && nfft != 2048) return fail(set_error(DAB_ERR_INVALID, "nb_fft %zu not in {256, 512, 1024, 2048}", nfft));
+    if (params->nb_symbol_period != nfft + params->nb_cyclic_prefix || params->nb_cyclic_prefix > nfft / 4 || params->nb_cyclic_prefix == 0)
+        return fail(set_error(DAB_ERR_INVALID, "symbol period / cyclic prefix not supported (need 0 < cp <= nfft/4)"));
+    if (params->nb_data_carriers >= nfft || params->nb_data_carriers % 8 != 0 || params->nb_frame_symbols < 2 ||
+        params->nb_null_period < params->nb_cyclic_prefix)
+        return fail(set_error(DAB_ERR_INVALID, "unsupported OFDM geometry"));
+    int rc = select_device(options->device);
+    if (rc != DAB_OK) return fail(rc);
+    auto* o = new Ofdm();
+    o->p = *params;
+    o->nfft = int(nfft);
+    o->n_streams = options->n_streams;
+    o->device = options->device;
+    o->raw_u8 = options->raw_u8_ingest != 0;
+    o->debug_taps = options->keep_debug_taps != 0;
+    o->max_block = options->max_block_samples ? options->max_block_samples : 262144;
+    rc = create_impl(o, prs_fft_ref, carrier_mapper);
+    if (rc != DAB_OK) { delete o; return fail(rc); }
+    if (status) *status = DAB_OK;
+    return reinterpret_cast<dab_ofdm*>(o);
+}
+
+void dab_ofdm_destroy(dab_ofdm* h) {
+    auto* o = reinterpret_cast<Ofdm*>(h);
+    if (!o) return;
+    cudaSetDevice(o->device);
+    cudaStreamSynchronize(o->stream);
+    if (o->own_stream) cudaStreamDestroy(o->own_stream);
+    delete o;
+}
+
+#define OFDM_HANDLE(h)                                          \
+    auto* o = reinterpret_cast<Ofdm*>(h);                       \
+    if (!o) return set_error(DAB_ERR_INVALID, "null handle");   \
+    std::lock_guard<std::mutex> lock(o->mtx);                   \
+    DAB_CUDA_CHECK(cudaSetDevice(o->device))
+
+int dab_ofdm_set_cuda_stream(dab_ofdm* h, void* cuda_stream) {
+    OFDM_HANDLE(h);
+    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
+    o->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : o->own_stream;
+    return DAB_OK;
+}
+
+int dab_ofdm_set_frame_callback(dab_ofdm* h, dab_ofdm_frame_cb cb, void* user) {
+    OFDM_HANDLE(h);
+    o->cb = cb;
+    o->cb_user = user;
+    return DAB_OK;
+}
+
+int dab_ofdm_set_config(dab_ofdm* h, int stream, const dab_ofdm_config* cfg) {
+    OFDM_HANDLE(h);
+    if (!cfg || stream < -1 || stream >= o->n_streams) return set_error(DAB_ERR_INVALID, "bad stream / config");
+    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
+    const int lo = (stream < 0) ? 0 : stream, hi = (stream < 0) ? o->n_streams : stream + 1;
+    for (int s = lo; s < hi; s++)
+        DAB_CUDA_CHECK(cudaMemcpy(reinterpret_cast<char*>(o->states.ptr + s) + offsetof(StreamState, cfg), cfg, sizeof(*cfg), cudaMemcpyHostToDevice));
+    return DAB_OK;
+}
+
+int dab_ofdm_get_config(dab_ofdm* h, int stream, dab_ofdm_config* cfg) {
+    OFDM_HANDLE(h);
+    if (!cfg || stream < 0 || stream >= o->n_streams) return set_error(DAB_ERR_INVALID, "bad stream / config");
+    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
+    DAB_CUDA_CHECK(cudaMemcpy(cfg, reinterpret_cast<char*>(o->states.ptr + stream) + offsetof(StreamState, cfg), sizeof(*cfg), cudaMemcpyDeviceToHost));
+    return DAB_OK;
+}
+
+static int ingest_and_run(Ofdm* o, const void* const* iq, const size_t* n, bool raw) {
+    if (o->ext_base) return set_error(DAB_ERR_INVALID, "handle is attached to device-resident streams; use dab_ofdm_advance");
+    if (raw != o->raw_u8) return set_error(DAB_ERR_INVALID, "handle was created with raw_u8_ingest = %d", int(o->raw_u8));
+    const size_t sb = sample_bytes(o);
+    for (int s = 0; s < o->n_streams; s++) {
+        const size_t ns = n[s];
+        if (ns > o->max_block) return set_error(DAB_ERR_CAPACITY, "stream %d: block of %zu samples exceeds max_block_samples %zu", s, ns, o->max_block);
+        if (ns > 0 && !iq[s]) return set_error(DAB_ERR_INVALID, "stream %d: null sample pointer", s);
+        o->n_call[size_t(s)] = ns;
+        if (ns == 0) continue;
+        // the caller's span is only valid during the call (ofdm_demodulator.cpp:235): copy into the stream ring now
+        const size_t pos = size_t(o->fed[size_t(s)] & (o->ring_samples - 1));
+        const size_t first = std::min(ns, o->ring_samples - pos);
+        unsigned char* base = o->ring_iq.ptr + size_t(s) * o->ring_samples * sb;
+        DAB_CUDA_CHECK(cudaMemcpyAsync(base + pos * sb, iq[s], first * sb, cudaMemcpyHostToDevice, o->stream));
+        if (first < ns)
+            DAB_CUDA_CHECK(cudaMemcpyAsync(base, static_cast<const unsigned char*>(iq[s]) + first * sb, (ns - first) * sb, cudaMemcpyHostToDevice, o->stream));
+    }
+    int rc = run_call(o, false, 0);
+    if (rc != DAB_OK) return rc;
+    // pageable source memory may still be in flight in a staging copy: the call must not return before it has left the span
+    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
+    return deliver(o);
+}
+
+int dab_ofdm_process_batch(dab_ofdm* h, const dab_c32* const* iq, const size_t* n) {
+    OFDM_HANDLE(h);
+    if (!iq || !n) return set_error(DAB_ERR_INVALID, "null argument");
+    return ingest_and_run(o, reinterpret_cast<const void* const*>(iq), n, false);
+}
+
+int dab_ofdm_process_batch_u8(dab_ofdm* h, const uint8_t* const* iq_u8, const size_t* n) {
+    OFDM_HANDLE(h);
+    if (!iq_u8 || !n) return set_error(DAB_ERR_INVALID, "null argument");
+    return ingest_and_run(o, reinterpret_cast<const void* const*>(iq_u8), n, true);
+}
+
+int dab_ofdm_process(dab_ofdm* h, int stream, const dab_c32* iq, size_t n) {
+    OFDM_HANDLE(h);
+    if (stream < 0 || stream >= o->n_streams) return set_error(DAB_ERR_INVALID, "stream %d out of range", stream);
+    std::vector<const void*> ptrs(size_t(o->n_streams), nullptr);
+    std::vector<size_t> ns(size_t(o->n_streams), 0);
+    ptrs[size_t(stream)] = iq;
+    ns[size_t(stream)] = n;
+    return ingest_and_run(o, ptrs.data(), ns.data(), false);
+}
+
+int dab_ofdm_attach_device_streams(dab_ofdm* h, const dab_c32* d_iq, size_t stride_samples, size_t total_samples) {
+    OFDM_HANDLE(h);
+    if (!d_iq || stride_samples < total_samples) return set_error(DAB_ERR_INVALID, "bad device stream geometry");
+    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
+    o->ext_base = d_iq;
+    o->ext_stride = stride_samples;
+    o->ext_total = total_samples;
+    return init_states(o);
+}
+
+static int advance_impl(Ofdm* o, const size_t* n, size_t n_uniform) {
+    if (!o->ext_base) return set_error(DAB_ERR_INVALID, "no device-resident streams attached");
+    for (int s = 0; s < o->n_streams; s++) {
+        const size_t ns = n ? n[s] : n_uniform;
+        if (ns > o->max_block) return set_error(DAB_ERR_CAPACITY, "block of %zu samples exceeds max_block_samples %zu", ns, o->max_block);
+        if (o->fed[size_t(s)] + ns > o->ext_total) return set_error(DAB_ERR_CAPACITY, "stream %d: advance past the end of the attached buffer", s);
+        o->n_call[size_t(s)] = ns;
+    }
+    int rc = run_call(o, n == nullptr, n_uniform);
+    if (rc != DAB_OK) return rc;
+    return deliver(o);
+}
+
+int dab_ofdm_advance(dab_ofdm* h, const size_t* n) {
+    OFDM_HANDLE(h);
+    if (!n) return set_error(DAB_ERR_INVALID, "null argument");
+    return advance_impl(o, n, 0);
+}
+
+int dab_ofdm_advance_uniform(dab_ofdm* h, size_t n) {
+    OFDM_HANDLE(h);
+    return advance_impl(o, nullptr, n);
+}
+
+int dab_ofdm_device_bits(dab_ofdm* h, const int8_t** d_bits, size_t* n_bits, int* slots_per_stream, const int32_t** d_frames_in_call) {
+    OFDM_HANDLE(h);
+    if (d_bits) *d_bits = o->bits.ptr;
+    if (n_bits) *n_bits = o->frame_bits;
+    if (slots_per_stream) *slots_per_stream = o->slots;
+    if (d_frames_in_call) *d_frames_in_call = o->frames_in_call.ptr;
+    return DAB_OK;
+}
+
+int dab_ofdm_reset(dab_ofdm* h, int stream) {
+    OFDM_HANDLE(h);
+    if (stream < 0 || stream >= o->n_streams) return set_error(DAB_ERR_INVALID, "stream %d out of range", stream);
+    ofdm_reset_stream_kernel<<<1, 1, 0, o->stream>>>(o->states.ptr, stream);
+    o->launches++;
+    DAB_CUDA_CHECK(cudaGetLastError());
+    return DAB_OK;
+}
+
+int dab_ofdm_get_state(dab_ofdm* h, int stream, dab_ofdm_state* out) {
+    OFDM_HANDLE(h);
+    if (!out || stream < 0 || stream >= o->n_streams) return set_error(DAB_ERR_INVALID, "bad stream / output");
+    StreamState st;
+    DAB_CUDA_CHECK(cudaMemcpyAsync(&st, o->states.ptr + stream, sizeof(st), cudaMemcpyDeviceToHost, o->stream));
+    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
+    out->state = st.state;
+    out->fine_time_offset = st.fine_time_offset;
+    out->total_frames_read = st.total_frames_read;
+    out->total_frames_desync = st.total_frames_desync;
+    out->signal_average = st.l1_average;
+    out->fine_frequency_offset = st.freq_fine;
+    out->coarse_frequency_offset = st.freq_coarse;
+    out->reserved = 0;
+    return DAB_OK;
+}
+
+int dab_ofdm_sync(dab_ofdm* h) {
+    OFDM_HANDLE(h);
+    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
+    return DAB_OK;
+}
+
+size_t dab_ofdm_frame_bits(const dab_ofdm* h) {
+    auto* o = reinterpret_cast<const Ofdm*>(h);
+    return o ? o->frame_bits : 0;
+}
+
+int dab_ofdm_get_params(const dab_ofdm* h, dab_ofdm_params* out) {
+    auto* o = reinterpret_cast<const Ofdm*>(h);
+    if (!o || !out) return set_error(DAB_ERR_INVALID, "null argument");
+    *out = o->p;
+    return DAB_OK;
+}
+
+static int copy_out(Ofdm* o, void* dst, const void* d_src, size_t bytes) {
+    DAB_CUDA_CHECK(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, o->stream));
+    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
+    return DAB_OK;
+}
+
+int dab_ofdm_get_impulse_response(dab_ofdm* h, int stream, float* out, size_t nb_fft) {
+    OFDM_HANDLE(h);
+    if (!out || stream < 0 || stream >= o->n_streams || nb_fft != size_t(o->nfft)) return set_error(DAB_ERR_INVALID, "bad argument");
+    return copy_out(o, out, o->impulse.ptr + size_t(stream) * nb_fft, nb_fft * sizeof(float));
+}
+
+int dab_ofdm_get_coarse_frequency_response(dab_ofdm* h, int stream, float* out, size_t nb_fft) {
+    OFDM_HANDLE(h);
+    if (!out || stream < 0 || stream >= o->n_streams || nb_fft != size_t(o->nfft)) return set_error(DAB_ERR_INVALID, "bad argument");
+    return copy_out(o, out, o->freq_resp.ptr + size_t(stream) * nb_fft, nb_fft * sizeof(float));
+}
+
+int dab_ofdm_get_frame_data_bits(dab_ofdm* h, int stream, int8_t* out, size_t n_bits) {
+    OFDM_HANDLE(h);
+    if (!out || stream < 0 || stream >= o->n_streams || n_bits != o->frame_bits) return set_error(DAB_ERR_INVALID, "bad argument");
+    StreamState st;
+    int rc = copy_out(o, &st, o->states.ptr + stream, sizeof(st));
+    if (rc != DAB_OK) return rc;
+    return copy_out(o, out, o->bits.ptr + (size_t(stream) * size_t(o->slots) + size_t(st.pending_slot)) * o->frame_bits, n_bits);
+}
+
+int dab_ofdm_get_frame_fft(dab_ofdm* h, int stream, dab_c32* out, size_t n) {
+    OFDM_HANDLE(h);
+    const size_t want = o->p.nb_frame_symbols * size_t(o->nfft);
+    if (!o->debug_taps) return set_error(DAB_ERR_INVALID, "handle was created without keep_debug_taps");
+    if (!out || stream < 0 || stream >= o->n_streams || n != want) return set_error(DAB_ERR_INVALID, "bad argument (n must be nb_frame_symbols * nb_fft)");
+    return copy_out(o, out, o->fft_tap.ptr + size_t(stream) * want, want * sizeof(float2));
+}
+
+int dab_ofdm_get_frame_data_vec(dab_ofdm* h, int stream, dab_c32* out, size_t n) {
+    OFDM_HANDLE(h);
+    const size_t want = (o->p.nb_frame_symbols - 1) * o->p.nb_data_carriers;
+    if (!o->debug_taps) return set_error(DAB_ERR_INVALID, "handle was created without keep_debug_taps");
+    if (!out || stream < 0 || stream >= o->n_streams || n != want) return set_error(DAB_ERR_INVALID, "bad argument (n must be (nb_frame_symbols-1) * nb_data_carriers)");
+    return copy_out(o, out, o->vec_tap.ptr + size_t(stream) * want, want * sizeof(float2));
+}
+
+uint64_t dab_ofdm_kernel_launches(const dab_ofdm* h) {
+    auto* o = reinterpret_cast<const Ofdm*>(h);
+    return o ? o->launches : 0;
+}
+
+int dab_ofdm_demod_frames_device(dab_ofdm* h, const dab_c32* d_frames, size_t frame_stride, int n_frames, const float* freq_offset, int8_t* d_bits,
+                                 float* d_phase_error) {
+    OFDM_HANDLE(h);
+    if (!d_frames || !freq_offset || !d_bits || n_frames < 0) return set_error(DAB_ERR_INVALID, "null argument");
+    if (o->raw_u8) return set_error(DAB_ERR_INVALID, "stage-level entry takes complex float frames");
+    if (n_frames == 0) return DAB_OK;
+    std::vector<FrameDesc> descs(static_cast<size_t>(n_frames));
+    for (int f = 0; f < n_frames; f++) {
+        FrameDesc& d = descs[size_t(f)];
+        d.src = reinterpret_cast<const float2*>(d_frames) + size_t(f) * frame_stride;
+        d.mask = ~uint64_t(0);
+        d.start = 0;
+        d.freq = freq_offset[f];
+        d.valid = 1;
+        d.bits = d_bits + size_t(f) * o->frame_bits;
+        d.phase_err = d_phase_error ? d_phase_error + size_t(f) * o->p.nb_frame_symbols : nullptr;
+        d.fft_tap = nullptr;
+        d.vec_tap = nullptr;
+    }
+    DAB_CUDA_CHECK(o->stage_descs.reserve(size_t(n_frames)));
+    DAB_CUDA_CHECK(cudaMemcpyAsync(o->stage_descs.ptr, descs.data(), descs.size() * sizeof(FrameDesc), cudaMemcpyHostToDevice, o->stream));
+    int rc = launch_frame(o, o->stage_descs.ptr, n_frames, false);
+    // `descs` is a local: the upload must have left it before we return
+    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,565 @@
+// Per-stream receive state machine on the device: OFDM_Demod::Process and its five states (reference
+// ofdm_demodulator.cpp:235-577), one CTA per stream.  All per-stream state lives in HBM (StreamState); the samples are
+// never copied into frame / correlation buffers as the reference does (ofdm_frame_buffer.h, reconstruction_buffer.h) --
+// the stream ring (or the caller's resident buffer) is addressed by absolute sample index instead:
+//   correlation buffer element i  ->  explicit copy (first corr_explicit_len elements, cold start only) or stream[corr_base + i]
+//   frame buffer element j        ->  stream[frame_start + j]
+// Ordering is the reference's real-time order: the fine-frequency update of frame k (CoordinatorThread,
+// ofdm_demodulator.cpp:608-618) is applied before frame k+1's PRS synchronisation.  A control pass therefore stops at a
+// frame dispatch; the host launches  control -> frame kernel -> control ...  and the next control pass first folds the
+// frame kernel's per-symbol phase errors into the fine frequency offset, then continues with the remaining samples.
+#pragma once
+#include "ofdm_device.cuh"
+#include "ofdm_frame.cuh"
+
+namespace dabb200 {
+
+struct StreamState {
+    // --- mirrors of the OFDM_Demod members (ofdm_demodulator.h:58-75)
+    int32_t state;
+    int32_t total_frames_read;
+    int32_t total_frames_desync;
+    int32_t is_found_coarse;
+    float freq_coarse;
+    float freq_fine;
+    int32_t fine_time_offset;
+    int32_t null_start_found;
+    int32_t null_end_found;
+    float l1_average;
+    // --- CircularBuffer m_null_power_dip_buffer (circular_buffer.h): index persists across SetLength(0)
+    uint32_t ring_index;
+    uint32_t ring_length;
+    // --- ReconstructionBuffer m_correlation_time_buffer (reconstruction_buffer.h)
+    uint32_t corr_length;
+    uint32_t corr_explicit_len;
+    int64_t corr_base;       // absolute sample index of correlation-buffer element 0
+    // --- OFDM_Frame_Buffer (ofdm_frame_buffer.h): virtual, [frame_start, frame_start + frame_cap)
+    int64_t frame_start;
+    // --- cursor / current Process() call
+    int64_t consumed;        // absolute index of the next unread sample
+    int64_t call_begin;
+    int64_t call_end;
+    int32_t call_needs_average;  // UpdateSignalAverage still to run for this call
+    int32_t pipeline_pending;    // a frame was dispatched; its phase errors still have to update the fine offset
+    int32_t pending_slot;        // output slot of that frame
+    int32_t frames_in_call;      // frames dispatched during this call
+    dab_ofdm_config cfg;
+    dab_ofdm_frame_info pending_info;
+};
+
+struct ControlGeom {
+    int n_symbols, symbol_period, null_period, cyclic_prefix, n_carriers;
+    int slots;               // output slots per stream and call
+    size_t frame_bits;
+    uint64_t mask;           // stream index mask (ring size - 1 or ~0)
+    size_t stream_stride;    // samples between consecutive streams' bases
+    const void* samples;     // base of stream 0
+    float2* ring;            // [n_streams][null_period] null-power-dip ring
+    float2* corr_explicit;   // [n_streams][null_period] cold-start copy of the ring into the correlation buffer
+    const float2* prs_fft_ref_conj;   // [NFFT]  conj(PRS)                               (ofdm_demodulator.cpp:130-132)
+    const float2* prs_time_ref_conj;  // [NFFT]  conj(IFFT(relative phase of PRS))       (ofdm_demodulator.cpp:134-140)
+    float* impulse_response;          // [n_streams][NFFT]
+    float* freq_response;             // [n_streams][NFFT]
+    StreamState* states;
+    FrameDesc* descs;        // [slots][n_streams]
+    dab_ofdm_frame_info* infos;  // [n_streams][slots]
+    int32_t* frames_in_call;     // [n_streams]
+    int8_t* bits;            // [n_streams][slots][frame_bits]
+    float* phase_err;        // [n_streams][slots][n_symbols]
+    float2* fft_tap;         // optional [n_streams][n_symbols * NFFT]
+    float2* vec_tap;         // optional [n_streams][(n_symbols-1) * n_carriers]
+};
+
+constexpr int CTRL_L1_BATCH = 1024;  // windows whose L1 averages are computed in parallel before the sequential scan
+
+template <int NFFT>
+struct ControlSmem {
+    using G = FftGeom<NFFT>;
+    static constexpr int THREADS = (G::T < 32) ? 32 : G::T;
+    static constexpr size_t bytes() {
+        return size_t(G::TW1_SIZE + G::TW2_SIZE + G::E1_SIZE + G::E2_SIZE + NFFT) * sizeof(float2) + size_t(CTRL_L1_BATCH) * sizeof(float) +
+               32 * sizeof(float2) + 64;
+    }
+};
+
+struct ArgMax {
+    float value;
+    int index;
+};
+// larger value wins, equal values keep the smaller index (the reference scans upwards with a strict '>')
+__device__ __forceinline__ ArgMax argmax_combine(ArgMax a, ArgMax b) {
+    const bool take_b = (b.value > a.value) || (b.value == a.value && b.index < a.index);
+    return take_b ? b : a;
+}
+
+template <int NFFT, bool RAW_U8>
+struct Control {
+    using G = FftGeom<NFFT>;
+    static constexpr int T = G::T;
+    static constexpr int THREADS = ControlSmem<NFFT>::THREADS;
+
+    const ControlGeom& geo;
+    StreamState& st;  // shared-memory copy, mutated by thread 0 between barriers
+    const int stream, tid;
+    float2 *tw1, *tw2, *e1, *e2, *nat;
+    float* l1buf;
+    float2* red;
+    const void* src;
+
+    __device__ float2 sample(int64_t abs_index) const { return load_sample<RAW_U8>(src, uint64_t(abs_index) & geo.mask); }
+    // element i of the reference's correlation buffer (null + PRS)
+    __device__ float2 corr_at(int i) const {
+        if (uint32_t(i) < st.corr_explicit_len) return geo.corr_explicit[size_t(stream) * geo.null_period + i];
+        return sample(st.corr_base + i);
+    }
+
+    // ---- CalculateL1Average (ofdm_demodulator.cpp:922-932) of `count` windows of K samples, window w at first + w * step
+    __device__ void l1_windows(int64_t first, int step, int K, int count) {
+        const int lane = tid & 31, warp = tid >> 5, n_warps = THREADS / 32;
+        for (int w = warp; w < count; w += n_warps) {
+            float acc = 0.0f;
+            for (int i = lane; i < K; i += 32) {
+                const float2 v = sample(first + int64_t(w) * step + i);
+                acc += fabsf(v.x) + fabsf(v.y);
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+            if (lane == 0) l1buf[w] = acc / float(K);
+        }
+        __syncthreads();
+    }
+
+    // ---- UpdateSignalAverage (ofdm_demodulator.cpp:934-950)
+    __device__ void update_signal_average() {
+        const int64_t N = st.call_end - st.call_begin;
+        const int K = st.cfg.signal_l1_nb_samples;
+        if (N >= K && K > 0) {
+            const int64_t M = N - K;
+            const int L = K * st.cfg.signal_l1_nb_decimate;
+            const int64_t n_windows = (L > 0) ? (M + L - 1) / L : 0;
+            for (int64_t w0 = 0; w0 < n_windows; w0 += CTRL_L1_BATCH) {
+                const int count = int(min(int64_t(CTRL_L1_BATCH), n_windows - w0));
+                l1_windows(st.call_begin + w0 * L, L, K, count);
+                if (tid == 0) {
+                    const float beta = st.cfg.signal_l1_update_beta;
+                    float avg = st.l1_average;
+                    for (int w = 0; w < count; w++) avg = beta * avg + (1.0f - beta) * l1buf[w];
+                    st.l1_average = avg;
+                }
+                __syncthreads();
+            }
+        }
+        if (tid == 0) st.call_needs_average = 0;
+        __syncthreads();
+    }
+
+    // ---- FindNullPowerDip (ofdm_demodulator.cpp:291-347)
+    __device__ void find_null_power_dip() {
+        const int64_t c0 = st.consumed;
+        const int64_t N = st.call_end - c0;
+        const int K = st.cfg.signal_l1_nb_samples;
+        const int64_t M = N - K;
+        const int64_t n_windows = (M > 0 && K > 0) ? (M + K - 1) / K : 0;
+        __shared__ int64_t nb_read_s;
+        if (tid == 0) nb_read_s = N;
+        __syncthreads();
+        for (int64_t w0 = 0; w0 < n_windows; w0 += CTRL_L1_BATCH) {
+            const int count = int(min(int64_t(CTRL_L1_BATCH), n_windows - w0));
+            l1_windows(c0 + w0 * K, K, K, count);
+            if (tid == 0) {
+                const float start_thresh = st.l1_average * st.cfg.null_l1_thresh_null_start;
+                const float end_thresh = st.l1_average * st.cfg.null_l1_thresh_null_end;
+                for (int w = 0; w < count; w++) {
+                    const float l1 = l1buf[w];
+                    if (st.null_start_found) {
+                        if (l1 > end_thresh) {
+                            st.null_end_found = 1;
+                            nb_read_s = (w0 + w) * K + K;
+                            break;
+                        }
+                    } else if (l1 < start_thresh) {
+                        st.null_start_found = 1;
+                    }
+                }
+            }
+            __syncthreads();
+            if (st.null_end_found) break;
+        }
+        // CircularBuffer::ConsumeBuffer(read_all = true) (circular_buffer.h:18-38): only the last `cap` samples survive
+        const int64_t nb_read = nb_read_s;
+        const uint32_t cap = uint32_t(geo.null_period);
+        float2* ring = geo.ring + size_t(stream) * cap;
+        const int64_t keep = min(nb_read, int64_t(cap));
+        const uint32_t first_slot = uint32_t((int64_t(st.ring_index) + (nb_read - keep)) % cap);
+        for (int64_t j = tid; j < keep; j += THREADS) ring[(first_slot + uint32_t(j)) % cap] = sample(c0 + (nb_read - keep) + j);
+        __syncthreads();
+        if (tid == 0) {
+            st.ring_index = uint32_t((int64_t(st.ring_index) + nb_read) % cap);
+            st.ring_length = uint32_t(min(int64_t(st.ring_length) + nb_read, int64_t(cap)));
+            st.consumed = c0 + nb_read;
+        }
+        __syncthreads();
+        if (!st.null_end_found) return;
+        // copy the ring, oldest slot first, into the head of the correlation buffer (:333-338)
+        const uint32_t L = st.ring_length, start = st.ring_index;
+        float2* dst = geo.corr_explicit + size_t(stream) * cap;
+        for (uint32_t i = tid; i < L; i += THREADS) dst[i] = ring[(i + start) % cap];
+        __syncthreads();
+        if (tid == 0) {
+            st.null_start_found = 0;
+            st.null_end_found = 0;
+            st.corr_length = L;
+            st.corr_explicit_len = L;
+            st.corr_base = st.consumed - int64_t(L);
+            st.ring_length = 0;
+            st.state = DAB_OFDM_READING_NULL_AND_PRS;
+        }
+        __syncthreads();
+    }
+
+    // ---- OFDM_Demod::Reset (ofdm_demodulator.cpp:277-289)
+    __device__ void reset_thread0() {
+        st.state = DAB_OFDM_FINDING_NULL_POWER_DIP;
+        st.corr_length = 0;
+        st.corr_explicit_len = 0;
+        st.total_frames_desync++;
+        st.is_found_coarse = 0;
+        st.freq_coarse = 0.0f;
+        st.freq_fine = 0.0f;
+        st.fine_time_offset = 0;
+    }
+
+    // ---- UpdateFineFrequencyOffset (ofdm_demodulator.cpp:829-840)
+    __device__ void update_fine_thread0(float delta) {
+        const float spacing = 1.0f / float(NFFT);
+        const float wrap = 0.5f * spacing * 1.01f;
+        st.freq_fine += delta;
+        st.freq_fine = fmodf(st.freq_fine, wrap);
+    }
+
+    // forward FFT of v (input layout v[n1] = x[n1 T + t]); result in registers, bin of slot r = fft_out_bin(t, r)
+    __device__ void fft_forward(float2 (&v)[16]) {
+        if (tid < T) fft_pass1<NFFT>(v, tid, e1, tw1);
+        __syncthreads();
+        if (tid < T) fft_pass2<NFFT>(v, tid, e1, e2, tw2);
+        __syncthreads();
+        if (tid < T) fft_pass3<NFFT>(v, tid, e2);
+    }
+    __device__ void store_natural(const float2 (&v)[16], bool conjugate) {
+        if (tid < T) {
+#pragma unroll
+            for (int r = 0; r < 16; r++) nat[fft_out_bin<NFFT>(tid, r)] = conjugate ? cconj(v[r]) : v[r];
+        }
+        __syncthreads();
+    }
+
+    template <typename F>
+    __device__ ArgMax block_argmax(int n, F value_at) {
+        ArgMax best{-INFINITY, 0x7FFFFFFF};
+        for (int i = tid; i < n; i += THREADS) best = argmax_combine(best, ArgMax{value_at(i), i});
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            ArgMax o;
+            o.value = __shfl_xor_sync(0xFFFFFFFFu, best.value, d);
+            o.index = __shfl_xor_sync(0xFFFFFFFFu, best.index, d);
+            best = argmax_combine(best, o);
+        }
+        if ((tid & 31) == 0) red[tid >> 5] = make_float2(best.value, __int_as_float(best.index));
+        __syncthreads();
+        ArgMax r{red[0].x, __float_as_int(red[0].y)};
+        for (int w = 1; w < THREADS / 32; w++) r = argmax_combine(r, ArgMax{red[w].x, __float_as_int(red[w].y)});
+        __syncthreads();
+        return r;
+    }
+
+    // ---- RunCoarseFreqSync (ofdm_demodulator.cpp:360-471)
+    __device__ void run_coarse_freq_sync() {
+        if (!st.cfg.sync_is_coarse_freq_correction) {
+            if (tid == 0) { st.freq_coarse = 0.0f; st.state = DAB_OFDM_RUNNING_FINE_TIME_SYNC; }
+            __syncthreads();
+            return;
+        }
+        float2 v[16];
+        // step 1: FFT of the first NFFT samples of the received PRS symbol window
+        if (tid < T) {
+#pragma unroll
+            for (int n1 = 0; n1 < 16; n1++) v[n1] = corr_at(geo.null_period + n1 * T + tid);
+        }
+        fft_forward(v);
+        store_natural(v, false);
+        // step 2: relative phase conj(X[i]) X[i+1], last bin zero (:901-909); step 3: IFFT = conj(FFT(conj(.)))
+        if (tid < T) {
+#pragma unroll
+            for (int n1 = 0; n1 < 16; n1++) {
+                const int i = n1 * T + tid;
+                const float2 rel = (i < NFFT - 1) ? cmul(cconj(nat[i]), nat[i + 1]) : make_float2(0.0f, 0.0f);
+                v[n1] = cconj(rel);
+            }
+        }
+        __syncthreads();
+        fft_forward(v);
+        store_natural(v, true);
+        // step 4: multiply by conj(IFFT(relative phase of the reference)); step 5: FFT
+        if (tid < T) {
+#pragma unroll
+            for (int n1 = 0; n1 < 16; n1++) {
+                const int i = n1 * T + tid;
+                v[n1] = cmul(nat[i], geo.prs_time_ref_conj[i]);
+            }
+        }
+        __syncthreads();
+        fft_forward(v);
+        // step 6: magnitude in dB, fft-shifted (:911-920)
+        float* resp = geo.freq_response + size_t(stream) * NFFT;
+        float* mag = reinterpret_cast<float*>(nat);
+        if (tid < T) {
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                const int k = fft_out_bin<NFFT>(tid, r);
+                const float m = 20.0f * log10f(sqrtf(v[r].x * v[r].x + v[r].y * v[r].y));
+                const int i = (k + NFFT / 2) % NFFT;
+                mag[i] = m;
+                resp[i] = m;
+            }
+        }
+        __syncthreads();
+        // step 7: peak inside the allowed window, first maximum wins
+        const int Mh = NFFT / 2;
+        int max_off = int(st.cfg.sync_max_coarse_freq_correction_norm * float(NFFT));
+        max_off = max(0, min(max_off, Mh));
+        const int lo = -max_off + Mh;
+        const int hi = min(max_off + Mh, NFFT - 1);  // fft_index == NFFT is skipped by the reference
+        const ArgMax peak = block_argmax(hi - lo + 1, [&](int i) { return mag[lo + i]; });
+        if (tid == 0) {
+            const int max_index = peak.index + lo - Mh;
+            // step 8: magnitude-weighted centroid of the three bins around the peak
+            float pk_mag[3];
+            int pk_idx[3];
+            for (int k = 0; k < 3; k++) {
+                int index = max_index - 1 + k;
+                index = max(-max_off, min(index, max_off));
+                int fi = index + Mh;
+                if (fi >= NFFT) fi = NFFT - 1;
+                pk_mag[k] = powf(10.0f, mag[fi] / 20.0f);
+                pk_idx[k] = fi - Mh;
+            }
+            float peak_sum = 0.0f, lerp = 0.0f;
+            for (int k = 0; k < 3; k++) peak_sum += pk_mag[k];
+            for (int k = 0; k < 3; k++) lerp += float(pk_idx[k]) * pk_mag[k] / peak_sum;
+            const float predicted = -lerp / float(NFFT);
+            const float error = predicted - st.freq_coarse;
+            // steps 9-11: fast / slow update and the counter-adjustment of the fine offset
+            const float large_thresh = 1.5f / float(NFFT);
+            const bool fast = (fabsf(error) > large_thresh) || !st.is_found_coarse;
+            const float beta = fast ? 1.0f : st.cfg.sync_coarse_freq_slow_beta;
+            const float delta = beta * error;
+            st.freq_coarse += delta;
+            st.is_found_coarse = 1;
+            update_fine_thread0(-delta);
+            st.state = DAB_OFDM_RUNNING_FINE_TIME_SYNC;
+        }
+        __syncthreads();
+    }
+
+    // ---- RunFineTimeSync (ofdm_demodulator.cpp:473-548)
+    __device__ void run_fine_time_sync() {
+        const int cp = geo.cyclic_prefix, sp = geo.symbol_period, np = geo.null_period;
+        const float freq_offset = st.freq_coarse + st.freq_fine;
+        float2 v[16];
+        if (tid < T) {
+            const PllSymbol pll = pll_symbol(freq_offset, 0, NFFT);
+#pragma unroll
+            for (int n1 = 0; n1 < 16; n1++) {
+                const int i = n1 * T + tid;
+                v[n1] = pll_rotate(pll, corr_at(np + i), i);
+            }
+        }
+        fft_forward(v);
+        // correlation in time = conjugate product in frequency; then IFFT through conj(FFT(conj(.)))
+        if (tid < T) {
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                const int k = fft_out_bin<NFFT>(tid, r);
+                v[r] = cmul(v[r], geo.prs_fft_ref_conj[k]);
+            }
+        }
+        store_natural(v, true);
+        if (tid < T) {
+#pragma unroll
+            for (int n1 = 0; n1 < 16; n1++) v[n1] = nat[n1 * T + tid];
+        }
+        __syncthreads();
+        fft_forward(v);
+        float* resp = geo.impulse_response + size_t(stream) * NFFT;
+        float* imp = reinterpret_cast<float*>(nat);
+        float partial = 0.0f;
+        if (tid < T) {
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                const int k = fft_out_bin<NFFT>(tid, r);
+                const float a = 20.0f * log10f(sqrtf(v[r].x * v[r].x + v[r].y * v[r].y));
+                imp[k] = a;
+                resp[k] = a;
+                partial += a;
+            }
+        }
+        // mean of the impulse response
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) partial += __shfl_xor_sync(0xFFFFFFFFu, partial, d);
+        if ((tid & 31) == 0) red[16 + (tid >> 5)] = make_float2(partial, 0.0f);
+        __syncthreads();
+        // peak weighted by its distance from the expected position (start value = unweighted sample 0, :503)
+        const float decay = 1.0f - st.cfg.sync_impulse_peak_distance_probability;
+        const ArgMax peak = block_argmax(NFFT, [&](int i) {
+            const float norm_dist = float(abs(cp - i)) / float(sp);
+            return (1.0f - decay * norm_dist) * imp[i];
+        });
+        if (tid == 0) {
+            float avg = 0.0f;
+            for (int w = 0; w < THREADS / 32; w++) avg += red[16 + w].x;
+            avg /= float(NFFT);
+            float max_value = imp[0];
+            int max_index = 0;
+            if (peak.value > max_value) { max_value = peak.value; max_index = peak.index; }
+            if ((max_value - avg) < st.cfg.sync_impulse_peak_threshold_db) {
+                reset_thread0();
+            } else {
+                const int offset = max_index - cp;
+                st.frame_start = st.corr_base + np + offset;
+                st.corr_length = 0;
+                st.fine_time_offset = offset;
+                st.state = DAB_OFDM_READING_SYMBOLS;
+                st.pending_info.frame_start = st.frame_start;
+                st.pending_info.fine_time_offset = offset;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- the fine-frequency half of CoordinatorThread (ofdm_demodulator.cpp:606-618, 632) for the frame dispatched before
+    __device__ void finish_pipeline_thread0() {
+        const float* pe = geo.phase_err + (size_t(stream) * geo.slots + st.pending_slot) * geo.n_symbols;
+        float total = 0.0f;
+        for (int s = 0; s < geo.n_symbols; s++) total += pe[s];
+        const float avg = total / float(geo.n_symbols);
+        const float two_pi = 3.14159265358979323846f * 2.0f;
+        const float fine_error = (1.0f / float(NFFT)) * avg / two_pi;  // CalculateFineFrequencyError :821-823
+        update_fine_thread0(-st.cfg.sync_fine_freq_update_beta * fine_error);
+        st.pending_info.fine_offset_after = st.freq_fine;
+        st.total_frames_read++;
+        geo.infos[size_t(stream) * geo.slots + st.pending_slot] = st.pending_info;
+        st.pipeline_pending = 0;
+    }
+
+    // ---- ReadSymbols (ofdm_demodulator.cpp:550-577): returns true when a frame was dispatched
+    __device__ bool read_symbols_thread0() {
+        const int64_t frame_cap = int64_t(geo.n_symbols) * geo.symbol_period + geo.null_period;
+        const int64_t frame_end = st.frame_start + frame_cap;
+        const int64_t take = min(st.call_end - st.consumed, frame_end - st.consumed);
+        st.consumed += take;
+        if (st.consumed != frame_end) return false;
+        // the trailing NULL symbol becomes the head of the next correlation buffer (:557-562)
+        st.corr_base = frame_end - geo.null_period;
+        st.corr_length = uint32_t(geo.null_period);
+        st.corr_explicit_len = 0;
+        // hand the frame to the frame kernel (SignalStart, :572)
+        const int slot = st.frames_in_call;
+        FrameDesc d;
+        d.src = src;
+        d.mask = geo.mask;
+        d.start = st.frame_start;
+        d.freq = st.freq_coarse + st.freq_fine;
+        d.valid = 1;
+        d.bits = geo.bits + (size_t(stream) * geo.slots + slot) * geo.frame_bits;
+        d.phase_err = geo.phase_err + (size_t(stream) * geo.slots + slot) * geo.n_symbols;
+        d.fft_tap = geo.fft_tap ? geo.fft_tap + size_t(stream) * geo.n_symbols * NFFT : nullptr;
+        d.vec_tap = geo.vec_tap ? geo.vec_tap + size_t(stream) * (geo.n_symbols - 1) * geo.n_carriers : nullptr;
+        geo.descs[size_t(slot) * gridDim.x + stream] = d;
+        st.pending_info.coarse_offset = st.freq_coarse;
+        st.pending_info.fine_offset_used = st.freq_fine;
+        st.pending_info.signal_average = st.l1_average;
+        st.pending_info.total_desync = st.total_frames_desync;
+        st.pending_slot = slot;
+        st.pipeline_pending = 1;
+        st.frames_in_call = slot + 1;
+        st.state = DAB_OFDM_READING_NULL_AND_PRS;
+        return true;
+    }
+};
+
+// pass: index of this control pass within the call (0 = first).  Frame slot `pass` is the one a dispatch in this pass fills.
+template <int NFFT, bool RAW_U8>
+__global__ void __launch_bounds__(ControlSmem<NFFT>::THREADS)
+ofdm_control_kernel(ControlGeom geo, int pass) {
+    using G = FftGeom<NFFT>;
+    using C = Control<NFFT, RAW_U8>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ StreamState st;
+    __shared__ int stop_flag;
+    const int stream = blockIdx.x, tid = threadIdx.x;
+
+    float2* tw1 = reinterpret_cast<float2*>(smem_raw);
+    float2* tw2 = tw1 + G::TW1_SIZE;
+    float2* e1 = tw2 + G::TW2_SIZE;
+    float2* e2 = e1 + G::E1_SIZE;
+    float2* nat = e2 + G::E2_SIZE;
+    float* l1buf = reinterpret_cast<float*>(nat + NFFT);
+    float2* red = reinterpret_cast<float2*>(l1buf + CTRL_L1_BATCH);
+
+    if (tid == 0) {
+        st = geo.states[stream];
+        stop_flag = 0;
+        // descriptor of the slot this pass may fill starts out invalid
+        if (pass < geo.slots) geo.descs[size_t(pass) * gridDim.x + stream].valid = 0;
+    }
+    __syncthreads();
+    // nothing to do: no frame waiting for its fine update and no unread samples
+    if (!st.pipeline_pending && st.consumed >= st.call_end) return;
+
+    fft_fill_twiddles<NFFT>(tw1, tw2, tid, C::THREADS);
+    const void* src = RAW_U8 ? static_cast<const void*>(reinterpret_cast<const uchar2*>(geo.samples) + size_t(stream) * geo.stream_stride)
+                             : static_cast<const void*>(reinterpret_cast<const float2*>(geo.samples) + size_t(stream) * geo.stream_stride);
+    C ctl{geo, st, stream, tid, tw1, tw2, e1, e2, nat, l1buf, red, src};
+
+    if (tid == 0 && st.pipeline_pending) ctl.finish_pipeline_thread0();
+    __syncthreads();
+    if (st.call_needs_average) ctl.update_signal_average();
+
+    // OFDM_Demod::Process main loop (ofdm_demodulator.cpp:245-274)
+    while (st.consumed < st.call_end && !stop_flag) {
+        switch (st.state) {
+        case DAB_OFDM_FINDING_NULL_POWER_DIP:
+            ctl.find_null_power_dip();
+            break;
+        case DAB_OFDM_READING_NULL_AND_PRS:  // ReadNullPRS :349-358
+            if (tid == 0) {
+                const int64_t cap = int64_t(geo.null_period) + geo.symbol_period;
+                const int64_t take = min(st.call_end - st.consumed, cap - int64_t(st.corr_length));
+                st.corr_length += uint32_t(take);
+                st.consumed += take;
+                if (int64_t(st.corr_length) == cap) st.state = DAB_OFDM_RUNNING_COARSE_FREQ_SYNC;
+            }
+            __syncthreads();
+            break;
+        case DAB_OFDM_RUNNING_COARSE_FREQ_SYNC:
+            ctl.run_coarse_freq_sync();
+            break;
+        case DAB_OFDM_RUNNING_FINE_TIME_SYNC:
+            ctl.run_fine_time_sync();
+            break;
+        case DAB_OFDM_READING_SYMBOLS:
+            if (tid == 0) {
+                if (ctl.read_symbols_thread0()) stop_flag = 1;  // wait for the frame kernel before touching the next PRS
+            }
+            __syncthreads();
+            break;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        geo.states[stream] = st;
+        geo.frames_in_call[stream] = st.frames_in_call;
+    }
+}
+
+}  // namespace dabb200
