@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native DAB receive hot path.
+
+Metric (BASELINE.json): MSamples/s IQ -> soft bits, and real-time (2.048 MS/s) DAB Mode I streams, at 1/2/4/8 B200.
+Workload (BASELINE.json configs[1]): DAB Mode I, 1024 independent synthetic streams batched per GPU, OFDM demodulation to
+int8 soft bits.  One step = every stream advances by one transmission frame (196 608 samples) through the full receive path
+(state machine, PRS coarse-frequency + fine-time sync, PLL, cyclic-prefix phase error, FFT, DQPSK, de-interleave, quantise).
+
+  python bench.py --gpus N --steps K --warmup W          our arm (one rank per GPU under torchrun for N > 1)
+  python bench.py --impl reference --steps K --warmup W  the reference's own CPU implementation on the host cores
+
+`value`      device-time throughput with the IQ already resident in HBM (dab_ofdm_attach_device_streams + advance)
+`e2e`        the same metric through the reference-facing C-ABI call dab_ofdm_process_batch with pinned HOST buffers:
+             H2D of every block and D2H of every frame's soft bits (callback) inside the timed region
+`roofline`   dominant kernel (ofdm_frame_kernel): algorithmic bytes / CUDA-event time vs the measured HBM copy peak
+`cpu_baseline` the reference (oracle/_ref, compiled from its own sources) on the host cores, bounded sample, rank 0 at N = 1
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "MSamples/s IQ->soft bits and real-time DAB Mode I streams per GPU at 1/2/4/8 B200"
+MODE = 1
+FS = 2.048e6
+FRAME_LEN = 196608                      # Mode I transmission frame, samples (96 ms)
+FRAME_BITS = 230400
+ALGO_BYTES_PER_FRAME = 196608 * 8 + 230400   # complex64 in + int8 out = 9.172 B/sample
+N_STREAMS = 1024
+POOL_FRAMES = 12                        # distinct modulated frames the synthetic streams are drawn from
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML is polled from a thread every few ms (the timed
+    region of a 10-step run lasts tens of ms, far below what `nvidia-smi -lms` can resolve); same fields as the
+    B200_PROFILING.md nvidia-smi line."""
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.stop_flag = False
+        self.thread = None
+        self.err = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                power = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((time.time(), sm, reasons, power))
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+                return
+            time.sleep(0.002)
+
+    def stop(self, t0, t1):
+        self.stop_flag = True
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
+        self.thread.join(timeout=1.0)
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["no samples"]}
+        sm = sorted(r[1] for r in rows)
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        # nvml clocks event reason bits
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
+        reasons = sorted(n for b, n in names.items() if bits & b)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(rows),
+                "power_w_max": round(max(r[3] for r in rows), 1)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        parts = [p.strip() for p in vis.split(",") if p.strip()]
+        if local_rank < len(parts) and parts[local_rank].isdigit():
+            return int(parts[local_rank])
+    return local_rank
+
+
+def build_streams_on_device(torch, n_streams, n_frames, seed):
+    """Synthetic Mode I streams in HBM: [n_streams, n_frames * FRAME_LEN] complex64.
+
+    A pool of POOL_FRAMES frames is modulated on the CPU exactly as simulate_transmitter does (random payload ->
+    OFDM modulator, scale 4/1536); each stream is a random sequence of pool frames, rotated by a random start offset in
+    [0, FRAME_LEN), shifted by its own carrier frequency offset (multiples of Fs/FRAME_LEN so that the one-frame host block of
+    the e2e leg is phase continuous) and given its own AWGN (SNR 25 dB)."""
+    import dabgen
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(seed)
+    pool = np.stack([po.modulate(MODE, rng.integers(0, 256, dabgen.payload_bytes(MODE), dtype=np.uint8)) for _ in range(POOL_FRAMES)])
+    pool = (pool * np.float32(4.0 / 1536)).astype(np.complex64)
+    sig_pow = float(np.mean(np.abs(pool) ** 2))
+    noise_sigma = float(np.sqrt(sig_pow / 10 ** (25.0 / 10) / 2))
+    d_pool = torch.from_numpy(pool.view(np.float32).reshape(POOL_FRAMES, FRAME_LEN, 2)).cuda()
+    d_pool = torch.view_as_complex(d_pool)
+    total = n_frames * FRAME_LEN
+    out = torch.empty((n_streams, total), dtype=torch.complex64, device="cuda")
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    starts = rng.integers(0, FRAME_LEN, n_streams)
+    cfo_bins = rng.integers(-4800, 4801, n_streams)          # x Fs/FRAME_LEN = 10.4 Hz: +-50 kHz
+    choice = rng.integers(0, POOL_FRAMES, (n_streams, n_frames + 1))
+    chunk = 16
+    ar = torch.arange(total, device="cuda", dtype=torch.int64)
+    for s0 in range(0, n_streams, chunk):
+        s1 = min(n_streams, s0 + chunk)
+        st = torch.from_numpy(starts[s0:s1]).cuda().view(-1, 1)
+        idx = ar.view(1, -1) + st                              # position in the un-rotated stream
+        fi = idx // FRAME_LEN
+        within = idx - fi * FRAME_LEN
+        ch = torch.from_numpy(choice[s0:s1]).cuda()
+        frame_id = torch.gather(ch, 1, fi)
+        x = d_pool[frame_id, within]
+        f = torch.from_numpy(cfo_bins[s0:s1].astype(np.float64) / FRAME_LEN).cuda().view(-1, 1)
+        phase = torch.remainder(f * ar.view(1, -1).to(torch.float64), 1.0) * (2.0 * np.pi)
+        rot = torch.polar(torch.ones_like(phase, dtype=torch.float32), phase.to(torch.float32))
+        noise = torch.randn((s1 - s0, total, 2), device="cuda", generator=g) * noise_sigma
+        out[s0:s1] = x * rot + torch.view_as_complex(noise)
+        del idx, fi, within, frame_id, x, phase, rot, noise
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    pkg = importlib.import_module("dab-radio_b200")
+    ofdm = importlib.import_module("dab-radio_b200.ofdm")
+    if rank == 0 and not os.path.exists(pkg.capi.LIB_PATH):
+        pkg.build()
+    if world > 1:
+        dist.barrier()
+
+    K, W = args.steps, args.warmup
+    n_streams = args.streams
+    n_frames = W + K + 1
+    iq = build_streams_on_device(torch, n_streams, n_frames, seed=1234 + rank)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ value: IQ resident in HBM
+    d = ofdm.OfdmDemodBatch(MODE, n_streams=n_streams, device=local_rank, max_block_samples=FRAME_LEN)
+    d.disable_callback()
+    # a dedicated (non-default) torch stream carries both the library's kernels and the timing events
+    work_stream = torch.cuda.Stream()
+    torch.cuda.set_stream(work_stream)
+    d.set_cuda_stream(work_stream.cuda_stream)
+    d.attach_device_streams(iq.data_ptr(), iq.shape[1], iq.shape[1])
+    for _ in range(W):
+        d.advance_uniform(FRAME_LEN)
+    barrier()
+    frames_before = sum(d.state(s)["total_frames_read"] for s in range(0, n_streams, max(1, n_streams // 16)))
+    launches0 = d.kernel_launches()
+    d.set_kernel_timing(True)
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    ev0.record()
+    for _ in range(K):
+        d.advance_uniform(FRAME_LEN)
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    ms = ev0.elapsed_time(ev1)
+    launches = d.kernel_launches() - launches0
+    kt = d.kernel_times()
+    frames_after = sum(d.state(s)["total_frames_read"] for s in range(0, n_streams, max(1, n_streams // 16)))
+    sampled_streams = len(range(0, n_streams, max(1, n_streams // 16)))
+    frames_per_stream = (frames_after - frames_before) / sampled_streams
+    locked = sum(1 for s in range(n_streams) if d.state(s)["state"] == 4) if n_streams <= 64 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    samples_per_rank = n_streams * FRAME_LEN * K
+    value = world * samples_per_rank / (ms_max * 1e-3) / 1e6
+
+    # roofline of the dominant kernel, pass 0 of every step carries the n_streams frames
+    peak, peak_src = measured_peaks()
+    frame_ms = kt["frame_ms"][0] / max(1, kt["frame_launches"][0])
+    achieved = ALGO_BYTES_PER_FRAME * n_streams * frames_per_stream / K / (frame_ms * 1e-3) / 1e9 if frame_ms > 0 else 0.0
+    kernel_ms_total = sum(kt["frame_ms"]) + sum(kt["control_ms"])
+    roofline = {"bound": "hbm", "kernel": "ofdm_frame_kernel<2048>", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "kernel_ms_per_launch": round(frame_ms, 4), "algorithmic_bytes_per_launch": int(ALGO_BYTES_PER_FRAME * n_streams),
+                "share_of_step": round(kt["frame_ms"][0] / kernel_ms_total, 4) if kernel_ms_total > 0 else None,
+                "control_ms_per_step": round(sum(kt["control_ms"]) / K, 4), "frames_per_stream_per_step": round(frames_per_stream / K, 3),
+                "per_pass_ms_per_step": {"frame": [round(v / K, 4) for v in kt["frame_ms"][:3]],
+                                         "control": [round(v / K, 4) for v in kt["control_ms"][:3]]}}
+    d.set_kernel_timing(False)
+    d.close()
+    del d
+
+    # ------------------------------------------------------------------ e2e: host buffers through dab_ofdm_process_batch
+    e2e = None
+    if not args.no_e2e:
+        n_e2e = n_streams
+        # one frame period of every (periodic) stream in pinned host memory; fed repeatedly it is a continuous stream
+        host = torch.empty((n_e2e, FRAME_LEN), dtype=torch.complex64).pin_memory()
+        host.copy_(iq[:n_e2e, :FRAME_LEN])
+        # make the block periodic: same pool frame everywhere is not needed -- the demodulator is differential per symbol and
+        # re-synchronises on every PRS; the CFO phase is continuous across the block boundary by construction
+        torch.cuda.synchronize()
+        d = ofdm.OfdmDemodBatch(MODE, n_streams=n_e2e, device=local_rank, max_block_samples=FRAME_LEN)
+        d.set_cuda_stream(work_stream.cuda_stream)
+        d.collect = False
+        counter = {"frames": 0, "bytes": 0}
+
+        def on_frame(user, stream, bits, n_bits, info):
+            counter["frames"] += 1
+            counter["bytes"] += n_bits
+        cb = pkg.capi.FRAME_CB(on_frame)
+        pkg.capi.check(d.L.dab_ofdm_set_frame_callback(d.h, cb, None))
+        ptrs = [host[s].data_ptr() for s in range(n_e2e)]
+        ns = [FRAME_LEN] * n_e2e
+        for _ in range(max(W, 3)):
+            d.process_batch_ptrs(ptrs, ns)
+        barrier()
+        counter["frames"] = 0
+        counter["bytes"] = 0
+        t0 = time.perf_counter()
+        for _ in range(K):
+            d.process_batch_ptrs(ptrs, ns)   # returns after the soft bits of every completed frame were delivered
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt_max = float(tt.item())
+        e2e = {"value": round(world * n_e2e * FRAME_LEN * K / dt_max / 1e6, 1), "unit": "MSamples/s",
+               "h2d_bytes_per_step": int(n_e2e * FRAME_LEN * 8), "d2h_bytes_per_step": int(counter["bytes"] / K),
+               "frames_delivered_per_step": counter["frames"] / K, "api": "dab_ofdm_process_batch (pinned host complex64) + frame callback",
+               "realtime_streams": round(world * n_e2e * FRAME_LEN * K / dt_max / FS, 1)}
+        d.close()
+
+    # ------------------------------------------------------------------ cpu baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args, sample_frames=args.cpu_frames)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": "MSamples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(ms_max / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"DAB Mode I, {n_streams} independent synthetic streams per GPU, OFDM demod IQ->int8 soft bits "
+                                   f"(BASELINE.json configs[1]); one step = one 196608-sample frame per stream",
+                       "streams_per_gpu": n_streams, "samples_per_step_per_gpu": n_streams * FRAME_LEN, "block_samples": FRAME_LEN,
+                       "l2": "inputs (1.6 GB per step) are larger than L2 and read once; no flush needed",
+                       "snr_db": 25, "cfo": "+-50 kHz per stream", "parallelism": f"streams sharded, {world} rank(s), no data-path collective"},
+            "realtime_streams": round(value * 1e6 / FS, 1), "realtime_streams_per_gpu": round(value * 1e6 / FS / world, 1),
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "frames_per_stream_in_timed_region": frames_per_stream, "locked_streams": locked,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, sample_frames):
+    """The reference's own OFDM_Demod (oracle/_ref, timing build) on the host cores: one instance + feeder thread per core,
+    nb_desired_threads = 1 each, bounded sample."""
+    import dabgen
+    cores = os.cpu_count() or 1
+    x = dabgen.make_stream(MODE, 1, seed=7, same_frame=True, u8=False, snr_db=25.0)
+    try:
+        from oracle import pyref
+        pool = pyref.RefOfdmPool(MODE, cores, 1, fast=True)
+        kind = "reference"
+        note = ("reference sources compiled unmodified (oracle/_ref/libdabref_fast.so, -O3 -march=x86-64-v3 -ffast-math, AVX2 PLL); "
+                "FFTW3 absent -> vectorised float radix-2 stand-in FFT")
+        run = lambda reps: pool.run(x, 65536, reps)
+    except (FileNotFoundError, OSError):
+        from oracle import pyoracle as po
+        import ctypes as C
+        kind = "port"
+        note = "oracle/dab_oracle.c (scalar C restatement, double-precision FFT)"
+        pool = None
+
+        def run(reps):
+            frames = C.c_uint64()
+            return float(po.lib().orc_ofdm_bench(MODE, cores, x.ctypes.data_as(C.c_void_p), x.size, 65536, reps, C.byref(frames)))
+    run(2)
+    dt = run(sample_frames)
+    if pool is not None:
+        pool.close()
+    v = cores * sample_frames * x.size / dt / 1e6
+    return {"value": round(v, 1), "unit": "MSamples/s", "cores": cores, "kind": kind,
+            "sample": f"{cores} instances x {sample_frames} Mode I frames ({cores * sample_frames * x.size / 1e6:.0f} MSamples), 65536-sample Process() calls, {dt:.1f} s",
+            "note": note, "realtime_streams": round(v * 1e6 / FS, 1)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path, all host threads, same metric/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    import dabgen
+    cores = os.cpu_count() or 1
+    x = dabgen.make_stream(MODE, 1, seed=7, same_frame=True, u8=False, snr_db=25.0)
+    frames_per_step = args.ref_frames
+    try:
+        from oracle import pyref
+        pool = pyref.RefOfdmPool(MODE, cores, 1, fast=True)
+        kind = "reference"
+        run = lambda reps: pool.run(x, 65536, reps)
+    except (FileNotFoundError, OSError):
+        from oracle import pyoracle as po
+        import ctypes as C
+        kind = "port"
+        run = lambda reps: float(po.lib().orc_ofdm_bench(MODE, cores, x.ctypes.data_as(C.c_void_p), x.size, 65536, reps, None))
+    for _ in range(args.warmup):
+        run(2)
+    t = 0.0
+    for _ in range(args.steps):
+        t += run(frames_per_step)
+    samples = cores * frames_per_step * x.size * args.steps
+    v = samples / t / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(v, 1), "unit": "MSamples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(t / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "DAB Mode I OFDM demod IQ->int8 soft bits (BASELINE.json configs[1]) on the host CPU: one OFDM_Demod "
+                               "instance per core, bounded sample per step", "instances": cores, "frames_per_instance_per_step": frames_per_step,
+                   "block_samples": 65536},
+        "realtime_streams": round(v * 1e6 / FS, 1),
+        "cpu_baseline": {"value": round(v, 1), "unit": "MSamples/s", "cores": cores, "kind": kind,
+                         "sample": f"{cores} instances x {frames_per_step} frames per step x {args.steps} steps"},
+        "e2e": {"value": round(v, 1), "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=N_STREAMS)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=2000, help="frames per instance in the cpu_baseline sample")
+    ap.add_argument("--ref-frames", type=int, default=25, help="frames per instance per step for --impl reference")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -74,6 +74,11 @@ class OfdmOptions(C.Structure):
                 ("raw_u8_ingest", C.c_int)]
 
 
+class OfdmKernelTimes(C.Structure):
+    _fields_ = [("frame_ms", C.c_double * 8), ("frame_launches", C.c_uint64 * 8), ("control_ms", C.c_double * 8),
+                ("control_launches", C.c_uint64 * 8)]
+
+
 FRAME_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_int8), C.c_size_t, C.POINTER(OfdmFrameInfo))
 
 
@@ -97,7 +102,7 @@ EXPORTED_SYMBOLS = (
     "dab_ofdm_attach_device_streams", "dab_ofdm_advance", "dab_ofdm_advance_uniform", "dab_ofdm_device_bits", "dab_ofdm_reset",
     "dab_ofdm_get_state", "dab_ofdm_sync", "dab_ofdm_frame_bits", "dab_ofdm_get_params", "dab_ofdm_get_impulse_response",
     "dab_ofdm_get_coarse_frequency_response", "dab_ofdm_get_frame_data_bits", "dab_ofdm_get_frame_fft", "dab_ofdm_get_frame_data_vec",
-    "dab_ofdm_kernel_launches", "dab_ofdm_demod_frames_device",
+    "dab_ofdm_kernel_launches", "dab_ofdm_set_kernel_timing", "dab_ofdm_get_kernel_times", "dab_ofdm_demod_frames_device",
     "dab_viterbi_create", "dab_viterbi_destroy", "dab_viterbi_set_cuda_stream", "dab_viterbi_add_schedule",
     "dab_viterbi_schedule_soft_symbols", "dab_viterbi_decode_batch", "dab_viterbi_decode_batch_device",
     "dab_viterbi_decode_jobs_device", "dab_viterbi_sync", "dab_viterbi_kernel_launches",
@@ -154,6 +159,8 @@ def load():
     L.dab_ofdm_get_frame_data_vec.argtypes = [vp, i32, vp, sz]
     L.dab_ofdm_kernel_launches.argtypes = [vp]
     L.dab_ofdm_kernel_launches.restype = u64
+    L.dab_ofdm_set_kernel_timing.argtypes = [vp, i32]
+    L.dab_ofdm_get_kernel_times.argtypes = [vp, C.POINTER(OfdmKernelTimes)]
     L.dab_ofdm_demod_frames_device.argtypes = [vp, vp, sz, i32, vp, vp, vp]
     _bind_viterbi(L)
     _lib = L

@@ -54,8 +54,9 @@ struct Ofdm {
     cudaStream_t stream = nullptr;
     // device memory
     DeviceBuffer<unsigned char> ring_iq;
-    DeviceBuffer<float2> null_ring, corr_explicit, prs_fft_ref_conj, prs_time_ref_conj, fft_tap, vec_tap;
-    DeviceBuffer<float> impulse, freq_resp, phase_err, stage_phase_err;
+    DeviceBuffer<float2> null_ring, corr_explicit, prs_fft_ref_conj, prs_time_ref_conj, fft_tap, vec_tap, twiddles;
+    DeviceBuffer<float> impulse, freq_resp, phase_err, stage_phase_err, l1_windows;
+    int l1_windows_stride = 0;
     DeviceBuffer<StreamState> states;
     DeviceBuffer<FrameDesc> descs, stage_descs;
     DeviceBuffer<dab_ofdm_frame_info> infos;
@@ -76,8 +77,59 @@ struct Ofdm {
     dab_ofdm_frame_cb cb = nullptr;
     void* cb_user = nullptr;
     uint64_t launches = 0;
+    // optional per-kernel event timing (roofline measurement)
+    bool timing = false;
+    struct TimedLaunch { cudaEvent_t start, stop; int pass; bool is_frame; };
+    std::vector<TimedLaunch> timed;
+    std::vector<cudaEvent_t> event_pool;
+    dab_ofdm_kernel_times times{};
     std::mutex mtx;
 };
+
+static cudaEvent_t take_event(Ofdm* o) {
+    if (!o->event_pool.empty()) {
+        cudaEvent_t e = o->event_pool.back();
+        o->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct ScopedKernelTimer {
+    Ofdm* o;
+    Ofdm::TimedLaunch t{};
+    bool on;
+    ScopedKernelTimer(Ofdm* o_, int pass, bool is_frame) : o(o_), on(o_->timing) {
+        if (!on) return;
+        t.start = take_event(o);
+        t.stop = take_event(o);
+        t.pass = pass;
+        t.is_frame = is_frame;
+        cudaEventRecord(t.start, o->stream);
+    }
+    ~ScopedKernelTimer() {
+        if (!on) return;
+        cudaEventRecord(t.stop, o->stream);
+        o->timed.push_back(t);
+    }
+};
+
+static int collect_times(Ofdm* o) {
+    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
+    for (auto& t : o->timed) {
+        float ms = 0.0f;
+        DAB_CUDA_CHECK(cudaEventElapsedTime(&ms, t.start, t.stop));
+        const int p = std::min(t.pass, DAB_OFDM_TIMING_PASSES - 1);
+        if (t.is_frame) { o->times.frame_ms[p] += ms; o->times.frame_launches[p]++; }
+        else { o->times.control_ms[p] += ms; o->times.control_launches[p]++; }
+        o->event_pool.push_back(t.start);
+        o->event_pool.push_back(t.stop);
+    }
+    o->timed.clear();
+    return DAB_OK;
+}
 
 static void host_fft(std::vector<std::complex<double>>& x, int sign) {
     const size_t n = x.size();
@@ -111,6 +163,7 @@ static FrameGeom frame_geom(const Ofdm* o) {
     g.n_chunks = (g.n_symbols - 1 + g.syms_per_chunk - 1) / g.syms_per_chunk;
     g.bin_to_pos = o->bin_to_pos.ptr;
     g.bin_to_carrier = o->bin_to_carrier.ptr;
+    g.twiddles = o->twiddles.ptr;
     return g;
 }
 
@@ -169,6 +222,9 @@ static ControlGeom control_geom(const Ofdm* o) {
     g.frames_in_call = o->frames_in_call.ptr;
     g.bits = o->bits.ptr;
     g.phase_err = o->phase_err.ptr;
+    g.twiddles = o->twiddles.ptr;
+    g.l1_windows = o->l1_windows.ptr;
+    g.l1_windows_stride = o->l1_windows_stride;
     g.fft_tap = o->debug_taps ? o->fft_tap.ptr : nullptr;
     g.vec_tap = o->debug_taps ? o->vec_tap.ptr : nullptr;
     return g;
@@ -221,15 +277,40 @@ static int run_call(Ofdm* o, bool uniform, uint64_t n_uniform) {
                                                                                             n_uniform, o->n_streams);
     o->launches++;
     DAB_CUDA_CHECK(cudaGetLastError());
+    // UpdateSignalAverage's window averages for this call (default config: one 100-sample window every 500 samples)
+    {
+        // every slot of the window buffer that the current call can reach under ANY config (the kernel skips windows past
+        // the call's end); update_signal_average falls back to in-kernel evaluation beyond the buffer
+        const int max_windows = (n_max >= 1) ? o->l1_windows_stride : 0;
+        const int64_t tasks = int64_t(o->n_streams) * max_windows;
+        const int grid = int(std::min<int64_t>((tasks + 7) / 8, 148 * 8));
+        const ControlGeom g = control_geom(o);
+        if (grid > 0) {
+            ScopedKernelTimer timer(o, DAB_OFDM_TIMING_PASSES - 1, false);
+            if (o->raw_u8) ofdm_l1_windows_kernel<true><<<grid, 256, 0, o->stream>>>(g, o->n_streams, max_windows);
+            else ofdm_l1_windows_kernel<false><<<grid, 256, 0, o->stream>>>(g, o->n_streams, max_windows);
+            o->launches++;
+            DAB_CUDA_CHECK(cudaGetLastError());
+        }
+    }
     const int passes = passes_for(o, n_max);
     if (passes > o->slots) return set_error(DAB_ERR_CAPACITY, "call of %llu samples exceeds max_block_samples", (unsigned long long)n_max);
     for (int p = 0; p <= passes; p++) {
-        int rc = launch_control(o, p);
+        int rc;
+        {
+            ScopedKernelTimer timer(o, p, false);
+            rc = launch_control(o, p);
+        }
         if (rc != DAB_OK) return rc;
         if (p < passes) {
+            ScopedKernelTimer timer(o, p, true);
             rc = launch_frame(o, o->descs.ptr + size_t(p) * size_t(o->n_streams), o->n_streams, o->raw_u8);
             if (rc != DAB_OK) return rc;
         }
+    }
+    if (o->timed.size() > 4096) {
+        int rc = collect_times(o);
+        if (rc != DAB_OK) return rc;
     }
     for (int s = 0; s < o->n_streams; s++) o->fed[size_t(s)] += uniform ? n_uniform : o->n_call[size_t(s)];
     return DAB_OK;
@@ -332,6 +413,21 @@ static int create_impl(Ofdm* o, const dab_c32* prs, const int* mapper) {
     DAB_CUDA_CHECK(o->bin_to_pos.reserve(nfft));
     DAB_CUDA_CHECK(o->bin_to_carrier.reserve(nfft));
     DAB_CUDA_CHECK(o->d_n.reserve(ns));
+    o->l1_windows_stride = int(o->max_block / 500 + 2);
+    DAB_CUDA_CHECK(o->l1_windows.reserve(ns * size_t(o->l1_windows_stride)));
+    {
+        const int n_tw = int(nfft) + 16 * int(nfft / 256);  // TW1_SIZE + TW2_SIZE
+        DAB_CUDA_CHECK(o->twiddles.reserve(size_t(n_tw)));
+        const int blocks = (n_tw + 127) / 128;
+        switch (o->nfft) {
+        case 2048: fft_twiddle_init_kernel<2048><<<blocks, 128>>>(o->twiddles.ptr); break;
+        case 1024: fft_twiddle_init_kernel<1024><<<blocks, 128>>>(o->twiddles.ptr); break;
+        case 512: fft_twiddle_init_kernel<512><<<blocks, 128>>>(o->twiddles.ptr); break;
+        case 256: fft_twiddle_init_kernel<256><<<blocks, 128>>>(o->twiddles.ptr); break;
+        }
+        DAB_CUDA_CHECK(cudaGetLastError());
+        DAB_CUDA_CHECK(cudaDeviceSynchronize());
+    }
     if (o->debug_taps) {
         DAB_CUDA_CHECK(o->fft_tap.reserve(ns * o->p.nb_frame_symbols * nfft));
         DAB_CUDA_CHECK(o->vec_tap.reserve(ns * (o->p.nb_frame_symbols - 1) * ncarr));
@@ -401,6 +497,8 @@ void dab_ofdm_destroy(dab_ofdm* h) {
     if (!o) return;
     cudaSetDevice(o->device);
     cudaStreamSynchronize(o->stream);
+    for (auto& t : o->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
+    for (auto e : o->event_pool) cudaEventDestroy(e);
     if (o->own_stream) cudaStreamDestroy(o->own_stream);
     delete o;
 }
@@ -618,6 +716,24 @@ int dab_ofdm_get_frame_data_vec(dab_ofdm* h, int stream, dab_c32* out, size_t n)
     if (!o->debug_taps) return set_error(DAB_ERR_INVALID, "handle was created without keep_debug_taps");
     if (!out || stream < 0 || stream >= o->n_streams || n != want) return set_error(DAB_ERR_INVALID, "bad argument (n must be (nb_frame_symbols-1) * nb_data_carriers)");
     return copy_out(o, out, o->vec_tap.ptr + size_t(stream) * want, want * sizeof(float2));
+}
+
+int dab_ofdm_set_kernel_timing(dab_ofdm* h, int enable) {
+    OFDM_HANDLE(h);
+    int rc = collect_times(o);
+    if (rc != DAB_OK) return rc;
+    o->timing = enable != 0;
+    memset(&o->times, 0, sizeof(o->times));
+    return DAB_OK;
+}
+
+int dab_ofdm_get_kernel_times(dab_ofdm* h, dab_ofdm_kernel_times* out) {
+    OFDM_HANDLE(h);
+    if (!out) return set_error(DAB_ERR_INVALID, "null argument");
+    int rc = collect_times(o);
+    if (rc != DAB_OK) return rc;
+    *out = o->times;
+    return DAB_OK;
 }
 
 uint64_t dab_ofdm_kernel_launches(const dab_ofdm* h) {

@@ -66,6 +66,9 @@ struct ControlGeom {
     int32_t* frames_in_call;     // [n_streams]
     int8_t* bits;            // [n_streams][slots][frame_bits]
     float* phase_err;        // [n_streams][slots][n_symbols]
+    const float2* twiddles;  // precomputed FFT twiddles (fft_twiddle_init_kernel)
+    float* l1_windows;       // [n_streams][l1_windows_stride] window averages of the current call (ofdm_l1_windows_kernel)
+    int l1_windows_stride;
     float2* fft_tap;         // optional [n_streams][n_symbols * NFFT]
     float2* vec_tap;         // optional [n_streams][(n_symbols-1) * n_carriers]
 };
@@ -129,7 +132,8 @@ struct Control {
         __syncthreads();
     }
 
-    // ---- UpdateSignalAverage (ofdm_demodulator.cpp:934-950)
+    // ---- UpdateSignalAverage (ofdm_demodulator.cpp:934-950): the per-window L1 averages of this call were computed by
+    // ofdm_l1_windows_kernel (all streams, all windows in parallel); only the sequential exponential average is left
     __device__ void update_signal_average() {
         const int64_t N = st.call_end - st.call_begin;
         const int K = st.cfg.signal_l1_nb_samples;
@@ -137,9 +141,15 @@ struct Control {
             const int64_t M = N - K;
             const int L = K * st.cfg.signal_l1_nb_decimate;
             const int64_t n_windows = (L > 0) ? (M + L - 1) / L : 0;
+            const float* win = geo.l1_windows + size_t(stream) * geo.l1_windows_stride;
             for (int64_t w0 = 0; w0 < n_windows; w0 += CTRL_L1_BATCH) {
                 const int count = int(min(int64_t(CTRL_L1_BATCH), n_windows - w0));
-                l1_windows(st.call_begin + w0 * L, L, K, count);
+                if (w0 + count <= geo.l1_windows_stride) {
+                    for (int w = tid; w < count; w += THREADS) l1buf[w] = win[w0 + w];
+                    __syncthreads();
+                } else {
+                    l1_windows(st.call_begin + w0 * L, L, K, count);  // window buffer too small for this call: compute here
+                }
                 if (tid == 0) {
                     const float beta = st.cfg.signal_l1_update_beta;
                     float avg = st.l1_average;
@@ -487,6 +497,35 @@ struct Control {
     }
 };
 
+// CalculateL1Average (ofdm_demodulator.cpp:922-932) for every window UpdateSignalAverage (:934-950) visits in the current call:
+// window w of stream s covers samples [call_begin + w L, + K).  One warp per window, grid-stride over (stream, window).
+template <bool RAW_U8>
+__global__ void __launch_bounds__(256) ofdm_l1_windows_kernel(ControlGeom geo, int n_streams, int max_windows) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int64_t total = int64_t(n_streams) * max_windows;
+    for (int64_t task = int64_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); task < total; task += int64_t(gridDim.x) * warps_per_block) {
+        const int stream = int(task / max_windows), w = int(task % max_windows);
+        const StreamState& st = geo.states[stream];
+        const int K = st.cfg.signal_l1_nb_samples;
+        const int L = K * st.cfg.signal_l1_nb_decimate;
+        const int64_t N = st.call_end - st.call_begin;
+        if (K <= 0 || L <= 0 || N < K) continue;
+        const int64_t first = int64_t(w) * L;
+        if (first >= N - K) continue;  // loop condition i < M
+        const void* src = RAW_U8 ? static_cast<const void*>(reinterpret_cast<const uchar2*>(geo.samples) + size_t(stream) * geo.stream_stride)
+                                 : static_cast<const void*>(reinterpret_cast<const float2*>(geo.samples) + size_t(stream) * geo.stream_stride);
+        float acc = 0.0f;
+        for (int i = lane; i < K; i += 32) {
+            const float2 v = load_sample<RAW_U8>(src, uint64_t(st.call_begin + first + i) & geo.mask);
+            acc += fabsf(v.x) + fabsf(v.y);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+        if (lane == 0) geo.l1_windows[size_t(stream) * geo.l1_windows_stride + w] = acc / float(K);
+    }
+}
+
 // pass: index of this control pass within the call (0 = first).  Frame slot `pass` is the one a dispatch in this pass fills.
 template <int NFFT, bool RAW_U8>
 __global__ void __launch_bounds__(ControlSmem<NFFT>::THREADS)
@@ -516,7 +555,7 @@ ofdm_control_kernel(ControlGeom geo, int pass) {
     // nothing to do: no frame waiting for its fine update and no unread samples
     if (!st.pipeline_pending && st.consumed >= st.call_end) return;
 
-    fft_fill_twiddles<NFFT>(tw1, tw2, tid, C::THREADS);
+    fft_load_twiddles<NFFT>(tw1, geo.twiddles, tid, C::THREADS);
     const void* src = RAW_U8 ? static_cast<const void*>(reinterpret_cast<const uchar2*>(geo.samples) + size_t(stream) * geo.stream_stride)
                              : static_cast<const void*>(reinterpret_cast<const float2*>(geo.samples) + size_t(stream) * geo.stream_stride);
     C ctl{geo, st, stream, tid, tw1, tw2, e1, e2, nat, l1buf, red, src};

@@ -109,24 +109,35 @@ struct FftGeom {
     __device__ static __forceinline__ int e2(int k1, int k2, int n3) { return (k2 * R3 + n3) * 16 + ((k1 + PER3 * n3) & 15); }
 };
 
-// Fills the two twiddle tables (called once per CTA by all threads of the CTA).
+// Twiddle tables: computed once per handle into global memory (fft_twiddle_init_kernel), then copied into shared memory
+// by every CTA that runs transforms.  Layout: tw1[k1][t] = W_N^{t k1} (TW1_SIZE), followed by tw2[k2][n3] = W_T^{n3 k2} (TW2_SIZE).
 template <int NFFT>
-__device__ __forceinline__ void fft_fill_twiddles(float2* tw1, float2* tw2, int tid, int nthreads) {
+__global__ void fft_twiddle_init_kernel(float2* table) {
     using G = FftGeom<NFFT>;
-    for (int i = tid; i < G::TW1_SIZE; i += nthreads) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < G::TW1_SIZE) {
         const int k1 = i / G::T, t = i % G::T;
         const int e = (k1 * t) % NFFT;
         float s, c;
         sincospif(-2.0f * float(e) / float(NFFT), &s, &c);
-        tw1[i] = make_float2(c, s);
-    }
-    for (int i = tid; i < G::TW2_SIZE; i += nthreads) {
-        const int k2 = i / G::R3, n3 = i % G::R3;
+        table[i] = make_float2(c, s);
+    } else if (i < G::TW1_SIZE + G::TW2_SIZE) {
+        const int j = i - G::TW1_SIZE;
+        const int k2 = j / G::R3, n3 = j % G::R3;
         const int e = (k2 * n3) % G::T;
         float s, c;
         sincospif(-2.0f * float(e) / float(G::T), &s, &c);
-        tw2[i] = make_float2(c, s);
+        table[i] = make_float2(c, s);
     }
+}
+
+template <int NFFT>
+__device__ __forceinline__ void fft_load_twiddles(float2* tw_smem, const float2* __restrict__ table, int tid, int nthreads) {
+    using G = FftGeom<NFFT>;
+    // 16-byte copies: both table sizes are even
+    const float4* src = reinterpret_cast<const float4*>(table);
+    float4* dst = reinterpret_cast<float4*>(tw_smem);
+    for (int i = tid; i < (G::TW1_SIZE + G::TW2_SIZE) / 2; i += nthreads) dst[i] = __ldg(src + i);
 }
 
 // Three-pass forward FFT, split at its two barriers so callers can overlap other work with them.

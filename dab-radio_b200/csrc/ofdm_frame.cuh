@@ -35,6 +35,7 @@ struct FrameGeom {
     int n_chunks;          // ceil((S-1) / syms_per_chunk)
     const int16_t* bin_to_pos;      // [NFFT]: de-interleaved soft-bit position of FFT bin k, -1 for DC / guard bins
     const int16_t* bin_to_carrier;  // [NFFT]: carrier index (DQPSK vector order) of bin k, -1 if unused
+    const float2* twiddles;         // [TW1_SIZE + TW2_SIZE] precomputed FFT twiddles
 };
 
 template <bool RAW_U8>
@@ -86,14 +87,19 @@ ofdm_frame_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_fram
     int8_t* stage = reinterpret_cast<int8_t*>(e2 + G::E2_SIZE);
     float2* red = reinterpret_cast<float2*>(stage + SM::stage_bytes(geo.n_carriers));
 
-    fft_fill_twiddles<NFFT>(tw1, tw2, threadIdx.x, FRAME_CTA_THREADS);
-
     const int n_items = n_frames * geo.n_chunks;
     const int item = blockIdx.x * GROUPS + group;
     const int frame = (item < n_items) ? item / geo.n_chunks : 0;
     const int chunk = (item < n_items) ? item % geo.n_chunks : 0;
     const FrameDesc desc = descs[frame];
     const bool active = (item < n_items) && desc.valid != 0;
+    // a CTA without any frame to demodulate (streams that completed no frame in this pass) leaves at once
+    if (GROUPS == 1) {
+        if (!active) return;
+    } else {
+        if (!__syncthreads_or(active ? 1 : 0)) return;
+    }
+    fft_load_twiddles<NFFT>(tw1, geo.twiddles, threadIdx.x, FRAME_CTA_THREADS);
 
     const int S = geo.n_symbols, sp = geo.symbol_period, cp = geo.cyclic_prefix, ncarr = geo.n_carriers;
     const int s_first = chunk * geo.syms_per_chunk;                  // first symbol whose DQPSK output this item owns

@@ -149,6 +149,14 @@ class OfdmDemodBatch:
         capi.check(self.L.dab_ofdm_get_frame_data_vec(self.h, stream, capi.ptr(out), out.size))
         return out
 
+    def set_kernel_timing(self, enable=True):
+        capi.check(self.L.dab_ofdm_set_kernel_timing(self.h, 1 if enable else 0))
+
+    def kernel_times(self):
+        t = capi.OfdmKernelTimes()
+        capi.check(self.L.dab_ofdm_get_kernel_times(self.h, C.byref(t)))
+        return {k: list(getattr(t, k)) for k in ("frame_ms", "frame_launches", "control_ms", "control_launches")}
+
     def kernel_launches(self):
         return int(self.L.dab_ofdm_kernel_launches(self.h))
 

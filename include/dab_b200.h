@@ -174,6 +174,17 @@ DAB_API int dab_ofdm_get_frame_fft(dab_ofdm* h, int stream, dab_c32* out, size_t
 DAB_API int dab_ofdm_get_frame_data_vec(dab_ofdm* h, int stream, dab_c32* out, size_t n); /* needs keep_debug_taps */
 /* number of library kernels launched so far by this handle (bench.py's gpu_launches) */
 DAB_API uint64_t dab_ofdm_kernel_launches(const dab_ofdm* h);
+/* Per-kernel device timing for the roofline measurement: when enabled, every control / frame kernel launch is bracketed by
+ * CUDA events on the launching stream.  Times are accumulated per pass index (pass 0 = first frame completion of a call). */
+#define DAB_OFDM_TIMING_PASSES 8
+typedef struct {
+    double frame_ms[DAB_OFDM_TIMING_PASSES];
+    uint64_t frame_launches[DAB_OFDM_TIMING_PASSES];
+    double control_ms[DAB_OFDM_TIMING_PASSES];
+    uint64_t control_launches[DAB_OFDM_TIMING_PASSES];
+} dab_ofdm_kernel_times;
+DAB_API int dab_ofdm_set_kernel_timing(dab_ofdm* h, int enable);                    /* also clears the accumulators */
+DAB_API int dab_ofdm_get_kernel_times(dab_ofdm* h, dab_ofdm_kernel_times* out);     /* synchronises the stream */
 
 /* Stage-level entry used by the parity tests and the roofline measurement: demodulate already aligned frames.
  * d_frames: n_frames rows of frame_stride samples, row = PRS + data symbols (nb_frame_symbols * nb_symbol_period samples);

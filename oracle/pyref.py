@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF_SO = os.path.join(HERE, "_ref", "libdabref.so")
+REF_SO = os.path.join(HERE, "_ref", "libdabref.so")            # accuracy build (double-precision FFT stand-in): parity tests
+REF_FAST_SO = os.path.join(HERE, "_ref", "libdabref_fast.so")  # timing build (vectorised float FFT stand-in): CPU baselines
 
 
 class FrameInfo(C.Structure):
@@ -45,13 +46,30 @@ def available():
     return os.path.exists(REF_SO)
 
 
+_fast = None
+
+
+def fast_lib():
+    """timing build of the reference (same sources, -O3, vectorised single-precision FFT stand-in)"""
+    global _fast
+    if _fast is None:
+        if not os.path.exists(REF_FAST_SO):
+            raise FileNotFoundError(f"{REF_FAST_SO} missing: run `make -C oracle ref` where /root/reference exists")
+        _fast = _bind(C.CDLL(REF_FAST_SO))
+    return _fast
+
+
 def lib():
     global _lib
     if _lib is not None:
         return _lib
     if not available():
         raise FileNotFoundError(f"{REF_SO} missing: run `make -C oracle ref` where /root/reference exists")
-    L = C.CDLL(REF_SO)
+    _lib = _bind(C.CDLL(REF_SO))
+    return _lib
+
+
+def _bind(L):
     vp, u64, i32, f32 = C.c_void_p, C.c_uint64, C.c_int, C.c_float
     fp = C.POINTER(C.c_float)
     L.ref_get_params.argtypes = [i32, C.POINTER(u64)]
@@ -75,6 +93,13 @@ def lib():
         getattr(L, name).argtypes = [vp, vp]
     L.ref_ofdm_bench.argtypes = [i32, i32, i32, vp, u64, u64, i32, C.POINTER(u64)]
     L.ref_ofdm_bench.restype = C.c_double
+    L.ref_ofdm_pool_create.argtypes = [i32, i32, i32]
+    L.ref_ofdm_pool_create.restype = vp
+    L.ref_ofdm_pool_destroy.argtypes = [vp]
+    L.ref_ofdm_pool_frames.argtypes = [vp]
+    L.ref_ofdm_pool_frames.restype = u64
+    L.ref_ofdm_pool_run.argtypes = [vp, vp, u64, u64, i32]
+    L.ref_ofdm_pool_run.restype = C.c_double
     L.ref_vit_create.restype = vp
     L.ref_vit_destroy.argtypes = [vp]
     L.ref_vit_set_traceback_length.argtypes = [vp, u64]
@@ -92,7 +117,6 @@ def lib():
     L.ref_vit_bench.argtypes = [i32, vp, u64, u64, vp, vp, vp, C.c_uint32, u64, vp, u64]
     L.ref_vit_bench.restype = C.c_double
     L.ref_build_info.restype = C.c_char_p
-    _lib = L
     return L
 
 
@@ -234,3 +258,26 @@ class RefViterbi:
             self.close()
         except Exception:
             pass
+
+
+class RefOfdmPool:
+    """n independent reference OFDM_Demod instances, one feeder thread each (bench.py --impl reference / cpu_baseline)."""
+
+    def __init__(self, mode, n_instances, threads_each=1, fast=True):
+        self.L = fast_lib() if fast else lib()
+        self.h = self.L.ref_ofdm_pool_create(mode, n_instances, threads_each)
+        if not self.h:
+            raise RuntimeError("ref_ofdm_pool_create failed")
+        self.n_instances = n_instances
+
+    def run(self, iq, block, repeats):
+        iq = np.ascontiguousarray(iq, np.complex64)
+        return float(self.L.ref_ofdm_pool_run(self.h, _p(iq), iq.size, block, repeats))
+
+    def frames(self):
+        return int(self.L.ref_ofdm_pool_frames(self.h))
+
+    def close(self):
+        if self.h:
+            self.L.ref_ofdm_pool_destroy(self.h)
+            self.h = None

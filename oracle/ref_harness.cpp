@@ -37,6 +37,7 @@
 #define private public
 #include "ofdm/ofdm_demodulator.h"
 #undef private
+#include "ofdm/ofdm_demodulator_threads.h"
 #include "ofdm/dab_mapper_ref.h"
 #include "ofdm/dab_ofdm_params_ref.h"
 #include "ofdm/dab_prs_ref.h"
@@ -326,6 +327,61 @@ double ref_ofdm_bench(int mode, int n_instances, int threads_each, const float* 
     const auto t1 = std::chrono::steady_clock::now();
     for (auto* c : cs) { frames += c->frames_done; delete c; }
     if (frames_out) *frames_out = frames;
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// Persistent pool for bench.py --impl reference: instances stay locked between timed steps.
+struct OfdmPool {
+    std::vector<void*> hs;
+};
+void* ref_ofdm_pool_create(int mode, int n_instances, int threads_each) {
+    auto* p = new OfdmPool();
+    for (int i = 0; i < n_instances; i++) {
+        void* h = ref_ofdm_create(mode, threads_each, 0);
+        if (!h) { for (auto* x : p->hs) ref_ofdm_destroy(x); delete p; return nullptr; }
+        p->hs.push_back(h);
+    }
+    return p;
+}
+void ref_ofdm_pool_destroy(void* pool) {
+    auto* p = static_cast<OfdmPool*>(pool);
+    if (!p) return;
+    for (auto* h : p->hs) ref_ofdm_destroy(h);
+    delete p;
+}
+uint64_t ref_ofdm_pool_frames(void* pool) {
+    auto* p = static_cast<OfdmPool*>(pool);
+    uint64_t n = 0;
+    for (auto* h : p->hs) n += ref_ofdm_frames_done(h);
+    return n;
+}
+// every instance consumes the n samples `repeats` times in `block`-sample Process() calls (stock, file-mode Process) from its
+// own thread; the clock stops when every dispatched frame's callback has fired.  Returns wall seconds.
+double ref_ofdm_pool_run(void* pool, const float* iq_interleaved, uint64_t n, uint64_t block, int repeats) {
+    auto* p = static_cast<OfdmPool*>(pool);
+    auto* x = reinterpret_cast<const std::complex<float>*>(iq_interleaved);
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> workers;
+    for (size_t i = 0; i < p->hs.size(); i++) {
+        workers.emplace_back([&, i]() {
+            auto* c = static_cast<OfdmCtx*>(p->hs[i]);
+            for (int r = 0; r < repeats; r++)
+                for (uint64_t off = 0; off < n; off += block) c->demod->Process({x + off, size_t(std::min<uint64_t>(block, n - off))});
+            // wait for the pipeline of the last dispatched frame (the same wait ReadSymbols performs, ofdm_demodulator.cpp:565),
+            // hand the "ended" token back, then let the coordinator's Notify (:632-635) land
+            c->demod->m_coordinator->WaitEnd();
+            c->demod->m_coordinator->SignalEnd();
+            for (int spin = 0; spin < 5000; spin++) {
+                {
+                    std::lock_guard<std::mutex> lock(c->mtx);
+                    if (c->frames_done >= size_t(c->demod->GetTotalFramesRead())) break;
+                }
+                std::this_thread::sleep_for(std::chrono::microseconds(100));
+            }
+        });
+    }
+    for (auto& w : workers) w.join();
+    const auto t1 = std::chrono::steady_clock::now();
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
