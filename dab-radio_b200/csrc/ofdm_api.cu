@@ -4,6 +4,7 @@
 // and its coordinator / pipeline threads (ofdm_demodulator_threads.cpp), whose ordering becomes CUDA stream order.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <complex>
 #include <mutex>
 #include <vector>
@@ -11,6 +12,7 @@
 #include "common.cuh"
 #include "ofdm_control.cuh"
 #include "ofdm_frame.cuh"
+#include "ofdm_frame_dab.cuh"
 
 namespace dabb200 {
 
@@ -50,6 +52,7 @@ struct Ofdm {
     int slots = 1;
     size_t frame_bits = 0;
     int syms_per_chunk = 25;
+    bool force_generic_kernel = false;  // DAB_B200_GENERIC_FRAME_KERNEL=1: run the generic-geometry frame kernel (tests)
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     // device memory
@@ -170,6 +173,18 @@ static FrameGeom frame_geom(const Ofdm* o) {
 template <int NFFT, bool RAW>
 static int launch_frame_t(Ofdm* o, const FrameDesc* d_descs, int n_frames) {
     const FrameGeom g = frame_geom(o);
+    if (DabGeom<NFFT>::matches(g.symbol_period, g.cyclic_prefix, g.n_carriers) && !o->force_generic_kernel) {
+        // the four DAB transmission modes: geometry known at compile time
+        constexpr size_t smem = FrameDabSmem<NFFT>::TOTAL_BYTES;
+        DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_dab_kernel<NFFT, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        constexpr int GROUPS = FrameDabSmem<NFFT>::GROUPS;
+        const int n_items = n_frames * g.n_chunks;
+        const int grid = (n_items + GROUPS - 1) / GROUPS;
+        ofdm_frame_dab_kernel<NFFT, RAW><<<grid, FRAME_CTA_THREADS, smem, o->stream>>>(g, d_descs, n_frames);
+        o->launches++;
+        DAB_CUDA_CHECK(cudaGetLastError());
+        return DAB_OK;
+    }
     const size_t smem = FrameSmem<NFFT>::total_bytes(g.n_carriers);
     DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_kernel<NFFT, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     constexpr int GROUPS = FrameSmem<NFFT>::GROUPS;
@@ -486,6 +501,8 @@ dab_ofdm* dab_ofdm_create(const dab_ofdm_params* params, const dab_c32* prs_fft_
     o->raw_u8 = options->raw_u8_ingest != 0;
     o->debug_taps = options->keep_debug_taps != 0;
     o->max_block = options->max_block_samples ? options->max_block_samples : 262144;
+    if (const char* e = getenv("DAB_B200_GENERIC_FRAME_KERNEL")) o->force_generic_kernel = (e[0] == '1');
+    if (const char* e = getenv("DAB_B200_SYMS_PER_CHUNK")) { const int c = atoi(e); if (c >= 1 && c <= 1024) o->syms_per_chunk = c; }
     rc = create_impl(o, prs_fft_ref, carrier_mapper);
     if (rc != DAB_OK) { delete o; return fail(rc); }
     if (status) *status = DAB_OK;
