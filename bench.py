@@ -115,6 +115,21 @@ def physical_gpu_index(local_rank):
     return local_rank
 
 
+def aggregate(ms_local, samples_per_rank, world, dist=None, device="cuda"):
+    """MAX over ranks of the device time; value = whole-job MSamples/s (every rank processes samples_per_rank)."""
+    import torch
+    t = torch.tensor([ms_local], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    return ms_max, world * samples_per_rank / (ms_max * 1e-3) / 1e6
+
+
+def shard_streams(n_global, rank, world):
+    """global stream ids owned by `rank`: stream i -> rank i mod world; no data crosses ranks"""
+    return range(rank, n_global, world)
+
+
 def build_streams_on_device(torch, n_streams, n_frames, seed):
     """Synthetic Mode I streams in HBM: [n_streams, n_frames * FRAME_LEN] complex64.
 
@@ -221,12 +236,8 @@ def run_ours(args):
     sampled_streams = len(range(0, n_streams, max(1, n_streams // 16)))
     frames_per_stream = (frames_after - frames_before) / sampled_streams
     locked = sum(1 for s in range(n_streams) if d.state(s)["state"] == 4) if n_streams <= 64 else None
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
     samples_per_rank = n_streams * FRAME_LEN * K
-    value = world * samples_per_rank / (ms_max * 1e-3) / 1e6
+    ms_max, value = aggregate(ms, samples_per_rank, world, dist)
 
     # roofline of the dominant kernel, pass 0 of every step carries the n_streams frames
     peak, peak_src = measured_peaks()
@@ -276,10 +287,7 @@ def run_ours(args):
             d.process_batch_ptrs(ptrs, ns)   # returns after the soft bits of every completed frame were delivered
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt_max = float(tt.item())
+        dt_max = aggregate(dt * 1e3, 0, world, dist)[0] * 1e-3
         e2e = {"value": round(world * n_e2e * FRAME_LEN * K / dt_max / 1e6, 1), "unit": "MSamples/s",
                "h2d_bytes_per_step": int(n_e2e * FRAME_LEN * 8), "d2h_bytes_per_step": int(counter["bytes"] / K),
                "frames_delivered_per_step": counter["frames"] / K, "api": "dab_ofdm_process_batch (pinned host complex64) + frame callback",

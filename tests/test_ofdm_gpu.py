@@ -101,3 +101,109 @@ def test_stream_matches_oracle(ofdm, oracle, mode, block, cfo_hz, start, min_fra
         assert o.state()["total_frames_desync"] > 0
     d.close()
     o.close()
+
+
+def _golden_cases():
+    import goldenutil
+    return goldenutil.ofdm_cases()
+
+
+@pytest.mark.parametrize("case", _golden_cases())
+def test_stream_against_reference_golden(ofdm, oracle, case):
+    """CUDA demodulator vs outputs of the reference's own OFDM_Demod in real-time order (tests/golden/ofdm_*.npz)"""
+    import goldenutil
+    g = goldenutil.load(f"ofdm_{case}.npz")
+    mode, block = int(g["mode"][0]), int(g["block"][0])
+    nfft = oracle.params(mode)["nb_fft"]
+    x = dabgen.dequantise_u8(g["iq_u8"])
+    d = ofdm.OfdmDemodBatch(mode, n_streams=1, max_block_samples=max(block, 4096))
+    for off in range(0, x.size, block):
+        d.process(0, x[off:off + block])
+    got = d.frames[0]
+    assert len(got) == g["bits"].shape[0]
+    for i, (info, bits) in enumerate(got):
+        assert [info["frame_start"], info["fine_time_offset"], info["total_desync"]] == g["frame_ints"][i].tolist()
+        f = np.array([info["coarse_offset"], info["fine_offset_used"], info["fine_offset_after"]], np.float32)
+        assert np.all(np.abs(f - g["frame_floats"][i]) * nfft < FREQ_TOL_BINS)
+        eq, lsb1, mx = dabgen.compare_bits(bits, g["bits"][i])
+        assert lsb1 >= LSB1_MIN, (i, eq, lsb1, mx)
+    st = d.state(0)
+    assert [st["state"], st["total_frames_read"], st["total_frames_desync"]] == g["final_state"].tolist()
+    d.close()
+
+
+def test_raw_u8_ingest_matches_float_path(ofdm, oracle):
+    """raw 8-bit IQ dequantised on the device == dequantised on the host (app_iq_readers.h:57-69)"""
+    import goldenutil
+    g = goldenutil.load("ofdm_mode2_cfo2500.npz")
+    mode, block = int(g["mode"][0]), int(g["block"][0])
+    iq8 = g["iq_u8"]
+    d = ofdm.OfdmDemodBatch(mode, n_streams=1, max_block_samples=block, raw_u8=True)
+    for off in range(0, iq8.size // 2, block):
+        d.process_batch_u8([iq8[2 * off:2 * (off + block)]])
+    got = d.frames[0]
+    assert len(got) == g["bits"].shape[0] >= 2
+    for i, (info, bits) in enumerate(got):
+        assert info["frame_start"] == int(g["frame_ints"][i][0])
+        eq, lsb1, mx = dabgen.compare_bits(bits, g["bits"][i])
+        assert lsb1 >= LSB1_MIN, (i, eq, lsb1, mx)
+    d.close()
+
+
+def test_batched_streams_are_independent(ofdm, oracle):
+    """config 2 in small: several streams with different offsets / CFO in one handle give the same frames as one by one"""
+    mode, block, n = 1, 65536, 6
+    xs = [dabgen.make_stream(mode, 4, seed=60 + s, cfo_hz=[0.0, 333.0, -2500.0, 50000.0, -333.0, 2500.0][s], start=s * 31000 + 17,
+                             snr_db=25.0) for s in range(n)]
+    d = ofdm.OfdmDemodBatch(mode, n_streams=n, max_block_samples=block)
+    for off in range(0, xs[0].size, block):
+        d.process_batch([x[off:off + block] for x in xs])
+    for s in range(n):
+        o = oracle.OracleOfdmDemod(mode)
+        o.process_blocks(xs[s], block)
+        _assert_stream_parity(oracle, mode, o, d, stream=s, min_frames=2)
+        o.close()
+    d.close()
+
+
+def test_ragged_and_empty_blocks(ofdm, oracle):
+    """block partition is part of the test vector: ragged block sizes, zero-length and sub-window blocks"""
+    mode = 2
+    x = dabgen.make_stream(mode, 5, seed=9, cfo_hz=333.0, start=30000)
+    sizes = [1, 0, 99, 100, 101, 4096, 7, 30000, 638, 664, 1302, 50000, 3, 65536]
+    o = oracle.OracleOfdmDemod(mode)
+    d = ofdm.OfdmDemodBatch(mode, n_streams=1, max_block_samples=65536)
+    off, i = 0, 0
+    while off < x.size:
+        n = min(sizes[i % len(sizes)], x.size - off)
+        o.process(x[off:off + n])
+        d.process(0, x[off:off + n])
+        off += n
+        i += 1
+    _assert_stream_parity(oracle, mode, o, d, min_frames=2)
+    d.close()
+    o.close()
+
+
+def test_reset_and_config_are_honoured(ofdm, oracle):
+    mode, block = 1, 65536
+    x = dabgen.make_stream(mode, 5, seed=12, cfo_hz=333.0, start=5000)
+    o = oracle.OracleOfdmDemod(mode)
+    d = ofdm.OfdmDemodBatch(mode, n_streams=1, max_block_samples=block)
+    cfg = d.get_config(0)
+    assert abs(cfg.signal_l1_update_beta - 0.95) < 1e-7 and cfg.signal_l1_nb_samples == 100      # defaults (ofdm_demodulator.h:24-45)
+    cfg.sync_impulse_peak_threshold_db = 18.0
+    cfg.sync_fine_freq_update_beta = 0.5
+    d.set_config(cfg)
+    o.config.impulse_peak_threshold_db = 18.0
+    o.config.fine_freq_update_beta = 0.5
+    for k, off in enumerate(range(0, x.size, block)):
+        if k == 7:  # explicit Reset() mid-stream (ofdm_demodulator.cpp:277-289)
+            o.reset()
+            d.reset(0)
+        o.process(x[off:off + block])
+        d.process(0, x[off:off + block])
+    _assert_stream_parity(oracle, mode, o, d, min_frames=2)
+    assert d.state(0)["total_frames_desync"] >= 1
+    d.close()
+    o.close()

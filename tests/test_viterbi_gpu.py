@@ -133,3 +133,30 @@ def test_underrun_is_reported(vit, oracle):
     out, err, st = vb.decode_batch(np.zeros(2304, np.int8), jobs, 96, raise_on_job_error=False)
     assert st[0] == vit.capi.DAB_ERR_UNDERRUN
     vb.close()
+
+
+def test_against_reference_golden_vectors(vit, oracle):
+    """CUDA decoder vs outputs of the reference's own AVX2 decoder (tests/golden/viterbi.npz): bit-exact bytes and path error"""
+    import goldenutil
+    g = goldenutil.load("viterbi.npz")
+    vb = vit.ViterbiBatch(0)
+    keys = goldenutil.viterbi_cases()
+    sched = {}
+    jobs = np.zeros(len(keys), vit.capi.VIT_JOB_DTYPE)
+    softs, want, off_s, off_o = [], [], 0, 0
+    for i, key in enumerate(keys):
+        segs, nbytes, soft, out, err = goldenutil.viterbi_case(g, oracle, key)
+        name = key.split("__")[0]
+        if name not in sched:
+            sched[name] = vb.add_schedule(vit.make_schedule(segs, nbytes))
+        jobs[i] = (sched[name], soft.size, off_s, off_o)
+        softs.append(soft)
+        want.append((off_o, out, err))
+        off_s += soft.size
+        off_o += nbytes
+    got, errs, st = vb.decode_batch(np.concatenate(softs), jobs, off_o)
+    assert np.all(st == 0)
+    for i, (o, out, err) in enumerate(want):
+        assert np.array_equal(got[o:o + out.size], out), keys[i]
+        assert int(errs[i]) == err, keys[i]
+    vb.close()
