@@ -101,11 +101,11 @@ EXPORTED_SYMBOLS = (
     "dab_ofdm_get_config", "dab_ofdm_default_config", "dab_ofdm_process", "dab_ofdm_process_batch", "dab_ofdm_process_batch_u8",
     "dab_ofdm_attach_device_streams", "dab_ofdm_advance", "dab_ofdm_advance_uniform", "dab_ofdm_device_bits", "dab_ofdm_reset",
     "dab_ofdm_get_state", "dab_ofdm_sync", "dab_ofdm_frame_bits", "dab_ofdm_get_params", "dab_ofdm_get_impulse_response",
-    "dab_ofdm_get_coarse_frequency_response", "dab_ofdm_get_frame_data_bits", "dab_ofdm_get_frame_fft", "dab_ofdm_get_frame_data_vec",
+    "dab_ofdm_get_coarse_frequency_response", "dab_ofdm_get_correlation_time_buffer", "dab_ofdm_get_frame_data_bits", "dab_ofdm_get_frame_fft", "dab_ofdm_get_frame_data_vec",
     "dab_ofdm_kernel_launches", "dab_ofdm_set_kernel_timing", "dab_ofdm_get_kernel_times", "dab_ofdm_demod_frames_device",
     "dab_viterbi_create", "dab_viterbi_destroy", "dab_viterbi_set_cuda_stream", "dab_viterbi_add_schedule",
     "dab_viterbi_schedule_soft_symbols", "dab_viterbi_decode_batch", "dab_viterbi_decode_batch_device",
-    "dab_viterbi_decode_jobs_device", "dab_viterbi_sync", "dab_viterbi_kernel_launches",
+    "dab_viterbi_decode_jobs_device", "dab_viterbi_decode_one", "dab_viterbi_sync", "dab_viterbi_kernel_launches",
 )
 
 _lib = None
@@ -154,6 +154,7 @@ def load():
     L.dab_ofdm_get_params.argtypes = [vp, C.POINTER(OfdmParams)]
     L.dab_ofdm_get_impulse_response.argtypes = [vp, i32, vp, sz]
     L.dab_ofdm_get_coarse_frequency_response.argtypes = [vp, i32, vp, sz]
+    L.dab_ofdm_get_correlation_time_buffer.argtypes = [vp, i32, vp, sz]
     L.dab_ofdm_get_frame_data_bits.argtypes = [vp, i32, vp, sz]
     L.dab_ofdm_get_frame_fft.argtypes = [vp, i32, vp, sz]
     L.dab_ofdm_get_frame_data_vec.argtypes = [vp, i32, vp, sz]
@@ -181,6 +182,7 @@ def _bind_viterbi(L):
     L.dab_viterbi_decode_batch.argtypes = [vp, vp, sz, vp, i32, vp, sz, vp, vp]
     L.dab_viterbi_decode_batch_device.argtypes = [vp, vp, sz, vp, i32, vp, sz, vp, vp]
     L.dab_viterbi_decode_jobs_device.argtypes = [vp, vp, sz, vp, i32, u32, vp, sz, vp, vp]
+    L.dab_viterbi_decode_one.argtypes = [vp, C.POINTER(VitSchedule), vp, sz, vp, C.POINTER(u64)]
     L.dab_viterbi_sync.argtypes = [vp]
     L.dab_viterbi_kernel_launches.argtypes = [vp]
     L.dab_viterbi_kernel_launches.restype = u64

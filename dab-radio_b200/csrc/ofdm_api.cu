@@ -719,6 +719,39 @@ int dab_ofdm_get_frame_data_bits(dab_ofdm* h, int stream, int8_t* out, size_t n_
     return copy_out(o, out, o->bits.ptr + (size_t(stream) * size_t(o->slots) + size_t(st.pending_slot)) * o->frame_bits, n_bits);
 }
 
+int dab_ofdm_get_correlation_time_buffer(dab_ofdm* h, int stream, dab_c32* out, size_t n) {
+    OFDM_HANDLE(h);
+    const size_t cap = o->p.nb_null_period + o->p.nb_symbol_period;
+    if (!out || stream < 0 || stream >= o->n_streams || n != cap) return set_error(DAB_ERR_INVALID, "bad argument (n must be nb_null_period + nb_symbol_period)");
+    if (o->raw_u8) return set_error(DAB_ERR_INVALID, "not available with raw_u8_ingest");
+    StreamState st;
+    int rc = copy_out(o, &st, o->states.ptr + stream, sizeof(st));
+    if (rc != DAB_OK) return rc;
+    memset(out, 0, cap * sizeof(dab_c32));
+    const size_t filled = std::min<size_t>(cap, st.corr_length);
+    const size_t expl = std::min<size_t>(filled, st.corr_explicit_len);
+    if (expl) {
+        rc = copy_out(o, out, o->corr_explicit.ptr + size_t(stream) * o->p.nb_null_period, expl * sizeof(float2));
+        if (rc != DAB_OK) return rc;
+    }
+    for (size_t i = expl; i < filled;) {  // stream-backed part, split where the ring wraps
+        const uint64_t abs_index = uint64_t(st.corr_base + int64_t(i));
+        size_t run = filled - i;
+        const float2* src;
+        if (o->ext_base) {
+            src = reinterpret_cast<const float2*>(o->ext_base) + size_t(stream) * o->ext_stride + abs_index;
+        } else {
+            const uint64_t pos = abs_index & (o->ring_samples - 1);
+            run = std::min<size_t>(run, o->ring_samples - pos);
+            src = reinterpret_cast<const float2*>(o->ring_iq.ptr) + size_t(stream) * o->ring_samples + pos;
+        }
+        rc = copy_out(o, out + i, src, run * sizeof(float2));
+        if (rc != DAB_OK) return rc;
+        i += run;
+    }
+    return DAB_OK;
+}
+
 int dab_ofdm_get_frame_fft(dab_ofdm* h, int stream, dab_c32* out, size_t n) {
     OFDM_HANDLE(h);
     const size_t want = o->p.nb_frame_symbols * size_t(o->nfft);

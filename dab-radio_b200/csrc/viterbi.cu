@@ -264,6 +264,7 @@ struct Viterbi {
     DeviceBuffer<int32_t> d_status;
     DeviceBuffer<uint2> d_scratch;
     int max_smem_optin = 0;
+    int oneshot_slot = -1;  // schedule slot reused by dab_viterbi_decode_one
     uint64_t launches = 0;
     std::mutex mtx;
 };
@@ -476,6 +477,34 @@ int dab_viterbi_decode_batch(dab_viterbi* h, const int8_t* soft, size_t soft_byt
         if (st[size_t(i)] != DAB_OK && first_bad == DAB_OK) first_bad = set_error(st[size_t(i)], "job %d failed with status %d", i, st[size_t(i)]);
     }
     return first_bad;
+}
+
+int dab_viterbi_decode_one(dab_viterbi* h, const dab_vit_schedule* s, const int8_t* soft, size_t n_soft, uint8_t* out, uint64_t* path_error) {
+    auto* v = reinterpret_cast<Viterbi*>(h);
+    if (!v) return set_error(DAB_ERR_INVALID, "null handle");
+    if (!s || !soft || !out) return set_error(DAB_ERR_INVALID, "null argument");
+    DevSchedule d;
+    int rc = digest_schedule(s, &d);
+    if (rc != DAB_OK) return rc;
+    {
+        std::lock_guard<std::mutex> lock(v->mtx);
+        if (v->oneshot_slot < 0) {
+            if (v->schedules.size() >= DAB_VIT_MAX_SCHEDULES) return set_error(DAB_ERR_CAPACITY, "no schedule slot left");
+            v->schedules.push_back(d);
+            v->oneshot_slot = int(v->schedules.size()) - 1;
+        } else {
+            v->schedules[size_t(v->oneshot_slot)] = d;
+        }
+        v->schedules_dirty = true;
+    }
+    dab_vit_job job;
+    job.schedule = uint32_t(v->oneshot_slot);
+    job.n_soft = uint32_t(n_soft);
+    job.soft_offset = 0;
+    job.out_offset = 0;
+    int32_t st = 0;
+    rc = dab_viterbi_decode_batch(h, soft, n_soft, &job, 1, out, s->n_out_bytes, path_error, &st);
+    return rc;
 }
 
 int dab_viterbi_sync(dab_viterbi* h) {

@@ -170,6 +170,8 @@ DAB_API int dab_ofdm_get_params(const dab_ofdm* h, dab_ofdm_params* out); /* Get
 DAB_API int dab_ofdm_get_impulse_response(dab_ofdm* h, int stream, float* out, size_t nb_fft);
 DAB_API int dab_ofdm_get_coarse_frequency_response(dab_ofdm* h, int stream, float* out, size_t nb_fft);
 DAB_API int dab_ofdm_get_frame_data_bits(dab_ofdm* h, int stream, int8_t* out, size_t n_bits);
+/* GetCorrelationTimeBuffer(): the NULL + PRS window (nb_null_period + nb_symbol_period samples) the next / last sync works on */
+DAB_API int dab_ofdm_get_correlation_time_buffer(dab_ofdm* h, int stream, dab_c32* out, size_t n);
 DAB_API int dab_ofdm_get_frame_fft(dab_ofdm* h, int stream, dab_c32* out, size_t n);      /* needs keep_debug_taps */
 DAB_API int dab_ofdm_get_frame_data_vec(dab_ofdm* h, int stream, dab_c32* out, size_t n); /* needs keep_debug_taps */
 /* number of library kernels launched so far by this handle (bench.py's gpu_launches) */
@@ -241,6 +243,9 @@ DAB_API int dab_viterbi_decode_batch_device(dab_viterbi* h, const int8_t* d_soft
 DAB_API int dab_viterbi_decode_jobs_device(dab_viterbi* h, const int8_t* d_soft, size_t soft_bytes, const dab_vit_job* d_jobs,
                                            int n_jobs, uint32_t max_steps, uint8_t* d_out, size_t out_bytes,
                                            uint64_t* d_path_error, int32_t* d_job_status);
+/* One trellis with an ad-hoc schedule (what the streaming reset/update/chainback mirror class issues on chainback) */
+DAB_API int dab_viterbi_decode_one(dab_viterbi* h, const dab_vit_schedule* s, const int8_t* soft, size_t n_soft, uint8_t* out,
+                                   uint64_t* path_error);
 DAB_API int dab_viterbi_sync(dab_viterbi* h);
 DAB_API uint64_t dab_viterbi_kernel_launches(const dab_viterbi* h);
 
