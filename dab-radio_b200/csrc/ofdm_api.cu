@@ -52,6 +52,7 @@ struct Ofdm {
     int slots = 1;
     size_t frame_bits = 0;
     int syms_per_chunk = 25;
+    int frame_min_blocks = 3;           // DAB_B200_FRAME_MIN_BLOCKS: resident CTAs per SM the frame kernel is compiled for (3 or 4)
     bool force_generic_kernel = false;  // DAB_B200_GENERIC_FRAME_KERNEL=1: run the generic-geometry frame kernel (tests)
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -176,11 +177,19 @@ static int launch_frame_t(Ofdm* o, const FrameDesc* d_descs, int n_frames) {
     if (DabGeom<NFFT>::matches(g.symbol_period, g.cyclic_prefix, g.n_carriers) && !o->force_generic_kernel) {
         // the four DAB transmission modes: geometry known at compile time
         constexpr size_t smem = FrameDabSmem<NFFT>::TOTAL_BYTES;
-        DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_dab_kernel<NFFT, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         constexpr int GROUPS = FrameDabSmem<NFFT>::GROUPS;
         const int n_items = n_frames * g.n_chunks;
         const int grid = (n_items + GROUPS - 1) / GROUPS;
-        ofdm_frame_dab_kernel<NFFT, RAW><<<grid, FRAME_CTA_THREADS, smem, o->stream>>>(g, d_descs, n_frames);
+        if (o->frame_min_blocks == 3) {
+            DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_dab_kernel<NFFT, RAW, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            ofdm_frame_dab_kernel<NFFT, RAW, 3><<<grid, FRAME_CTA_THREADS, smem, o->stream>>>(g, d_descs, n_frames);
+        } else if (o->frame_min_blocks == 2) {
+            DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_dab_kernel<NFFT, RAW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            ofdm_frame_dab_kernel<NFFT, RAW, 2><<<grid, FRAME_CTA_THREADS, smem, o->stream>>>(g, d_descs, n_frames);
+        } else {
+            DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_dab_kernel<NFFT, RAW, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            ofdm_frame_dab_kernel<NFFT, RAW, 4><<<grid, FRAME_CTA_THREADS, smem, o->stream>>>(g, d_descs, n_frames);
+        }
         o->launches++;
         DAB_CUDA_CHECK(cudaGetLastError());
         return DAB_OK;
@@ -502,6 +511,7 @@ dab_ofdm* dab_ofdm_create(const dab_ofdm_params* params, const dab_c32* prs_fft_
     o->debug_taps = options->keep_debug_taps != 0;
     o->max_block = options->max_block_samples ? options->max_block_samples : 262144;
     if (const char* e = getenv("DAB_B200_GENERIC_FRAME_KERNEL")) o->force_generic_kernel = (e[0] == '1');
+    if (const char* e = getenv("DAB_B200_FRAME_MIN_BLOCKS")) { const int b = atoi(e); o->frame_min_blocks = (b >= 2 && b <= 4) ? b : 3; }
     if (const char* e = getenv("DAB_B200_SYMS_PER_CHUNK")) { const int c = atoi(e); if (c >= 1 && c <= 1024) o->syms_per_chunk = c; }
     rc = create_impl(o, prs_fft_ref, carrier_mapper);
     if (rc != DAB_OK) { delete o; return fail(rc); }

@@ -68,8 +68,8 @@ __device__ __forceinline__ float2 load_sample_ptr(const void* p) {
     return v;
 }
 
-template <int NFFT, bool RAW_U8>
-__global__ void __launch_bounds__(FRAME_CTA_THREADS, 4)
+template <int NFFT, bool RAW_U8, int MIN_BLOCKS>
+__global__ void __launch_bounds__(FRAME_CTA_THREADS, MIN_BLOCKS)
 ofdm_frame_dab_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_frames) {
     using G = FftGeom<NFFT>;
     using D = DabGeom<NFFT>;
@@ -129,9 +129,11 @@ ofdm_frame_dab_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_
 
     // per-thread PLL constants: sample i = CP + t + T j of a symbol has i & 3 == k for every j (T is a multiple of 4)
     const int k_fft = (CP + t) & 3;
-    const float fi_fft = float(CP + t - k_fft);   // float(i & ~3) for j = 0; + T j is exact in float
+    float fi_fft = float(CP + t - k_fft);         // float(i & ~3) for j = 0; + T j is exact in float
     const int k_head = (t + T * 12 - TAIL0) & 3;  // head sample index i = t + T j - TAIL0, j >= 12
-    const float fi_head = float(t + T * 12 - TAIL0 - k_head);
+    float fi_head = float(t + T * 12 - TAIL0 - k_head);
+    // keep these as float registers: otherwise the compiler re-derives every fi + T j as an integer add plus an I2FP
+    asm volatile("" : "+f"(fi_fft), "+f"(fi_head));
 
     float2 prev[16];
 #pragma unroll
@@ -182,9 +184,12 @@ ofdm_frame_dab_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_
 
     __syncthreads();  // twiddle tables ready
 
-    for (int si = 0; si <= geo.syms_per_chunk; si++) {
+    // one group per CTA: run exactly the symbols this item owns; several groups share the CTA barriers, so they all run the
+    // full chunk length and idle (sym_active == false) past their own end
+    const int n_iter = (GROUPS == 1) ? (s_out_end - s_first) : geo.syms_per_chunk;
+    for (int si = 0; si <= n_iter; si++) {
         const int s = s_first + si;
-        const bool sym_active = active && (s <= s_out_end);
+        const bool sym_active = (GROUPS == 1) ? true : (active && (s <= s_out_end));
         float2 v[16];
         float2 corr = make_float2(0.0f, 0.0f);
         if (sym_active) {
@@ -224,7 +229,7 @@ ofdm_frame_dab_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_
             for (int j = 0; j < 16; j++) v[j] = make_float2(0.0f, 0.0f);
         }
         // request the next symbol's samples now: they travel while this symbol goes through its FFT
-        if (active && (s + 1 <= s_out_end) && si < geo.syms_per_chunk) load_symbol(s + 1, raw, head);
+        if (active && (s + 1 <= s_out_end) && si < n_iter) load_symbol(s + 1, raw, head);
 
         corr = group_reduce_sum<RED_WIDTH>(corr);
         if (WARPS_PER_GROUP > 1 && (t & 31) == 0) red[t >> 5] = corr;
