@@ -13,6 +13,7 @@
 #include "ofdm_control.cuh"
 #include "ofdm_frame.cuh"
 #include "ofdm_frame_dab.cuh"
+#include "ofdm_frame_v3.cuh"
 
 namespace dabb200 {
 
@@ -53,6 +54,7 @@ struct Ofdm {
     size_t frame_bits = 0;
     int syms_per_chunk = 25;
     int frame_min_blocks = 3;           // DAB_B200_FRAME_MIN_BLOCKS: resident CTAs per SM the frame kernel is compiled for (3 or 4)
+    int frame_kernel_version = 3;       // DAB_B200_FRAME_KERNEL=2: the previous register-prefetch kernel (A/B runs)
     bool force_generic_kernel = false;  // DAB_B200_GENERIC_FRAME_KERNEL=1: run the generic-geometry frame kernel (tests)
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -174,6 +176,23 @@ static FrameGeom frame_geom(const Ofdm* o) {
 template <int NFFT, bool RAW>
 static int launch_frame_t(Ofdm* o, const FrameDesc* d_descs, int n_frames) {
     const FrameGeom g = frame_geom(o);
+    if (DabGeom<NFFT>::matches(g.symbol_period, g.cyclic_prefix, g.n_carriers) && !o->force_generic_kernel && o->frame_kernel_version >= 3) {
+        // the four DAB transmission modes, TMA-fed kernel with the separable PLL (ofdm_frame_v3.cuh)
+        constexpr size_t smem = FrameV3Smem<NFFT, RAW>::TOTAL_BYTES;
+        constexpr int GROUPS = FrameV3Smem<NFFT, RAW>::GROUPS;
+        const int n_items = n_frames * g.n_chunks;
+        const int grid = (n_items + GROUPS - 1) / GROUPS;
+        if (o->debug_taps) {
+            DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_v3_kernel<NFFT, RAW, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            ofdm_frame_v3_kernel<NFFT, RAW, true, 3><<<grid, FRAME_CTA_THREADS, smem, o->stream>>>(g, d_descs, n_frames);
+        } else {
+            DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_v3_kernel<NFFT, RAW, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            ofdm_frame_v3_kernel<NFFT, RAW, false, 3><<<grid, FRAME_CTA_THREADS, smem, o->stream>>>(g, d_descs, n_frames);
+        }
+        o->launches++;
+        DAB_CUDA_CHECK(cudaGetLastError());
+        return DAB_OK;
+    }
     if (DabGeom<NFFT>::matches(g.symbol_period, g.cyclic_prefix, g.n_carriers) && !o->force_generic_kernel) {
         // the four DAB transmission modes: geometry known at compile time
         constexpr size_t smem = FrameDabSmem<NFFT>::TOTAL_BYTES;
@@ -227,10 +246,12 @@ static ControlGeom control_geom(const Ofdm* o) {
     g.frame_bits = o->frame_bits;
     if (o->ext_base) {
         g.mask = ~uint64_t(0);
+        g.limit = o->ext_total;
         g.stream_stride = o->ext_stride;
         g.samples = o->ext_base;
     } else {
         g.mask = uint64_t(o->ring_samples) - 1;
+        g.limit = o->ring_samples;
         g.stream_stride = o->ring_samples;
         g.samples = o->ring_iq.ptr;
     }
@@ -511,6 +532,7 @@ dab_ofdm* dab_ofdm_create(const dab_ofdm_params* params, const dab_c32* prs_fft_
     o->debug_taps = options->keep_debug_taps != 0;
     o->max_block = options->max_block_samples ? options->max_block_samples : 262144;
     if (const char* e = getenv("DAB_B200_GENERIC_FRAME_KERNEL")) o->force_generic_kernel = (e[0] == '1');
+    if (const char* e = getenv("DAB_B200_FRAME_KERNEL")) o->frame_kernel_version = atoi(e);
     if (const char* e = getenv("DAB_B200_FRAME_MIN_BLOCKS")) { const int b = atoi(e); o->frame_min_blocks = (b >= 2 && b <= 4) ? b : 3; }
     if (const char* e = getenv("DAB_B200_SYMS_PER_CHUNK")) { const int c = atoi(e); if (c >= 1 && c <= 1024) o->syms_per_chunk = c; }
     rc = create_impl(o, prs_fft_ref, carrier_mapper);
@@ -812,6 +834,7 @@ int dab_ofdm_demod_frames_device(dab_ofdm* h, const dab_c32* d_frames, size_t fr
         FrameDesc& d = descs[size_t(f)];
         d.src = reinterpret_cast<const float2*>(d_frames) + size_t(f) * frame_stride;
         d.mask = ~uint64_t(0);
+        d.limit = o->p.nb_frame_symbols * o->p.nb_symbol_period;
         d.start = 0;
         d.freq = freq_offset[f];
         d.valid = 1;

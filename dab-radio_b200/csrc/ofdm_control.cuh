@@ -50,8 +50,11 @@ struct StreamState {
 struct ControlGeom {
     int n_symbols, symbol_period, null_period, cyclic_prefix, n_carriers;
     int slots;               // output slots per stream and call
+    int n_streams;           // streams of the handle (row length of descs)
+    int stream0;             // first stream this launch covers (launches are split into pipeline ways, see run_call)
     size_t frame_bits;
     uint64_t mask;           // stream index mask (ring size - 1 or ~0)
+    uint64_t limit;          // samples addressable per stream (ring size, or the attached buffer's length)
     size_t stream_stride;    // samples between consecutive streams' bases
     const void* samples;     // base of stream 0
     float2* ring;            // [n_streams][null_period] null-power-dip ring
@@ -477,6 +480,7 @@ struct Control {
         FrameDesc d;
         d.src = src;
         d.mask = geo.mask;
+        d.limit = geo.limit;
         d.start = st.frame_start;
         d.freq = st.freq_coarse + st.freq_fine;
         d.valid = 1;
@@ -484,7 +488,7 @@ struct Control {
         d.phase_err = geo.phase_err + (size_t(stream) * geo.slots + slot) * geo.n_symbols;
         d.fft_tap = geo.fft_tap ? geo.fft_tap + size_t(stream) * geo.n_symbols * NFFT : nullptr;
         d.vec_tap = geo.vec_tap ? geo.vec_tap + size_t(stream) * (geo.n_symbols - 1) * geo.n_carriers : nullptr;
-        geo.descs[size_t(slot) * gridDim.x + stream] = d;
+        geo.descs[size_t(slot) * geo.n_streams + stream] = d;
         st.pending_info.coarse_offset = st.freq_coarse;
         st.pending_info.fine_offset_used = st.freq_fine;
         st.pending_info.signal_average = st.l1_average;
@@ -498,31 +502,54 @@ struct Control {
 };
 
 // CalculateL1Average (ofdm_demodulator.cpp:922-932) for every window UpdateSignalAverage (:934-950) visits in the current call:
-// window w of stream s covers samples [call_begin + w L, + K).  One warp per window, grid-stride over (stream, window).
+// window w of stream s covers samples [call_begin + w L, + K).  One warp per group of L1_WB windows, every load of the group
+// issued before the first use (the access pattern -- 800 bytes out of every 4000 -- is DRAM-latency bound otherwise).
+constexpr int L1_WB = 4;
 template <bool RAW_U8>
 __global__ void __launch_bounds__(256) ofdm_l1_windows_kernel(ControlGeom geo, int n_streams, int max_windows) {
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
-    const int64_t total = int64_t(n_streams) * max_windows;
+    const int groups = (max_windows + L1_WB - 1) / L1_WB;
+    const int64_t total = int64_t(n_streams) * groups;
     for (int64_t task = int64_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); task < total; task += int64_t(gridDim.x) * warps_per_block) {
-        const int stream = int(task / max_windows), w = int(task % max_windows);
+        const int stream = geo.stream0 + int(task / groups), w0 = int(task % groups) * L1_WB;
         const StreamState& st = geo.states[stream];
         const int K = st.cfg.signal_l1_nb_samples;
         const int L = K * st.cfg.signal_l1_nb_decimate;
         const int64_t N = st.call_end - st.call_begin;
         if (K <= 0 || L <= 0 || N < K) continue;
-        const int64_t first = int64_t(w) * L;
-        if (first >= N - K) continue;  // loop condition i < M
         const void* src = RAW_U8 ? static_cast<const void*>(reinterpret_cast<const uchar2*>(geo.samples) + size_t(stream) * geo.stream_stride)
                                  : static_cast<const void*>(reinterpret_cast<const float2*>(geo.samples) + size_t(stream) * geo.stream_stride);
-        float acc = 0.0f;
-        for (int i = lane; i < K; i += 32) {
-            const float2 v = load_sample<RAW_U8>(src, uint64_t(st.call_begin + first + i) & geo.mask);
-            acc += fabsf(v.x) + fabsf(v.y);
+        bool live[L1_WB];
+        float acc[L1_WB];
+#pragma unroll
+        for (int b = 0; b < L1_WB; b++) {
+            live[b] = (w0 + b < max_windows) && (int64_t(w0 + b) * L < N - K);  // loop condition i < M of the reference
+            acc[b] = 0.0f;
+        }
+        for (int i0 = 0; i0 < K; i0 += 128) {
+            float2 v[L1_WB][4];
+#pragma unroll
+            for (int b = 0; b < L1_WB; b++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int i = i0 + lane + 32 * q;
+                    v[b][q] = (live[b] && i < K) ? load_sample<RAW_U8>(src, uint64_t(st.call_begin + int64_t(w0 + b) * L + i) & geo.mask)
+                                                 : make_float2(0.0f, 0.0f);
+                }
+#pragma unroll
+            for (int b = 0; b < L1_WB; b++)
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (i0 + lane + 32 * q < K) acc[b] += fabsf(v[b][q].x) + fabsf(v[b][q].y);
         }
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
-        if (lane == 0) geo.l1_windows[size_t(stream) * geo.l1_windows_stride + w] = acc / float(K);
+        for (int b = 0; b < L1_WB; b++) {
+            float a = acc[b];
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, d);
+            if (lane == 0 && live[b]) geo.l1_windows[size_t(stream) * geo.l1_windows_stride + w0 + b] = a / float(K);
+        }
     }
 }
 
@@ -535,7 +562,7 @@ ofdm_control_kernel(ControlGeom geo, int pass) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ StreamState st;
     __shared__ int stop_flag;
-    const int stream = blockIdx.x, tid = threadIdx.x;
+    const int stream = geo.stream0 + blockIdx.x, tid = threadIdx.x;
 
     float2* tw1 = reinterpret_cast<float2*>(smem_raw);
     float2* tw2 = tw1 + G::TW1_SIZE;
@@ -549,7 +576,7 @@ ofdm_control_kernel(ControlGeom geo, int pass) {
         st = geo.states[stream];
         stop_flag = 0;
         // descriptor of the slot this pass may fill starts out invalid
-        if (pass < geo.slots) geo.descs[size_t(pass) * gridDim.x + stream].valid = 0;
+        if (pass < geo.slots) geo.descs[size_t(pass) * geo.n_streams + stream].valid = 0;
     }
     __syncthreads();
     // nothing to do: no frame waiting for its fine update and no unread samples

@@ -24,6 +24,8 @@ struct FrameDesc {
     float* phase_err;      // out: S cyclic-prefix phase errors (radians), one per symbol
     float2* fft_tap;       // optional GUI tap: S * NFFT spectra (natural bin order), else nullptr
     float2* vec_tap;       // optional GUI tap: (S-1) * ncarr DQPSK vectors (carrier order), else nullptr
+    uint64_t limit;        // samples addressable from src without wrapping (ring size, or the length of a linear buffer):
+                           // bounds the 16-byte-granular bulk copies of the v3 kernel
 };
 
 struct FrameGeom {

