@@ -212,10 +212,10 @@ def run_ours(args):
     d.attach_device_streams(iq.data_ptr(), iq.shape[1], iq.shape[1])
     for _ in range(W):
         d.advance_uniform(FRAME_LEN)
+    d.join()
     barrier()
     frames_before = sum(d.state(s)["total_frames_read"] for s in range(0, n_streams, max(1, n_streams // 16)))
     launches0 = d.kernel_launches()
-    d.set_kernel_timing(True)
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
     time.sleep(0.3)
@@ -225,32 +225,56 @@ def run_ours(args):
     ev0.record()
     for _ in range(K):
         d.advance_uniform(FRAME_LEN)
+    d.join()            # the handle's stream (= work_stream) now waits for every pipeline way: ev1 closes the whole job
     ev1.record()
     barrier()
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1)
     ms = ev0.elapsed_time(ev1)
     launches = d.kernel_launches() - launches0
-    kt = d.kernel_times()
     frames_after = sum(d.state(s)["total_frames_read"] for s in range(0, n_streams, max(1, n_streams // 16)))
     sampled_streams = len(range(0, n_streams, max(1, n_streams // 16)))
     frames_per_stream = (frames_after - frames_before) / sampled_streams
     locked = sum(1 for s in range(n_streams) if d.state(s)["state"] == 4) if n_streams <= 64 else None
     samples_per_rank = n_streams * FRAME_LEN * K
     ms_max, value = aggregate(ms, samples_per_rank, world, dist)
+    d.close()
+    del d
 
-    # roofline of the dominant kernel, pass 0 of every step carries the n_streams frames
+    # ------------------------------------------------------------------ roofline: the same K steps once more with the pipeline
+    # ways switched off, so that every kernel runs alone on the stream and its CUDA-event time is its own
+    os.environ["DAB_B200_PIPELINE_WAYS"] = "1"
+    d = ofdm.OfdmDemodBatch(MODE, n_streams=n_streams, device=local_rank, max_block_samples=FRAME_LEN)
+    del os.environ["DAB_B200_PIPELINE_WAYS"]
+    d.disable_callback()
+    d.set_cuda_stream(work_stream.cuda_stream)
+    d.attach_device_streams(iq.data_ptr(), iq.shape[1], iq.shape[1])
+    for _ in range(W):
+        d.advance_uniform(FRAME_LEN)
+    barrier()
+    d.set_kernel_timing(True)
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record()
+    for _ in range(K):
+        d.advance_uniform(FRAME_LEN)
+    ev3.record()
+    barrier()
+    serial_ms = ev2.elapsed_time(ev3)
+    kt = d.kernel_times()
     peak, peak_src = measured_peaks()
     frame_ms = kt["frame_ms"][0] / max(1, kt["frame_launches"][0])
     achieved = ALGO_BYTES_PER_FRAME * n_streams * frames_per_stream / K / (frame_ms * 1e-3) / 1e9 if frame_ms > 0 else 0.0
     kernel_ms_total = sum(kt["frame_ms"]) + sum(kt["control_ms"])
-    roofline = {"bound": "hbm", "kernel": "ofdm_frame_kernel<2048>", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "ofdm_frame_v3_kernel<2048>", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                 "kernel_ms_per_launch": round(frame_ms, 4), "algorithmic_bytes_per_launch": int(ALGO_BYTES_PER_FRAME * n_streams),
+                "timed": "separate pass of the same K steps with DAB_B200_PIPELINE_WAYS=1 (every kernel alone on the stream)",
+                "serial_ms_per_step": round(serial_ms / K, 4),
                 "share_of_step": round(kt["frame_ms"][0] / kernel_ms_total, 4) if kernel_ms_total > 0 else None,
                 "control_ms_per_step": round(sum(kt["control_ms"]) / K, 4), "frames_per_stream_per_step": round(frames_per_stream / K, 3),
                 "per_pass_ms_per_step": {"frame": [round(v / K, 4) for v in kt["frame_ms"][:3]],
-                                         "control": [round(v / K, 4) for v in kt["control_ms"][:3]]}}
+                                         "control": [round(v / K, 4) for v in kt["control_ms"][:3]],
+                                         "l1_windows": round(kt["control_ms"][7] / K, 4)}}
     d.set_kernel_timing(False)
     d.close()
     del d

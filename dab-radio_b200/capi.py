@@ -100,7 +100,7 @@ EXPORTED_SYMBOLS = (
     "dab_ofdm_create", "dab_ofdm_destroy", "dab_ofdm_set_cuda_stream", "dab_ofdm_set_frame_callback", "dab_ofdm_set_config",
     "dab_ofdm_get_config", "dab_ofdm_default_config", "dab_ofdm_process", "dab_ofdm_process_batch", "dab_ofdm_process_batch_u8",
     "dab_ofdm_attach_device_streams", "dab_ofdm_advance", "dab_ofdm_advance_uniform", "dab_ofdm_device_bits", "dab_ofdm_reset",
-    "dab_ofdm_get_state", "dab_ofdm_sync", "dab_ofdm_frame_bits", "dab_ofdm_get_params", "dab_ofdm_get_impulse_response",
+    "dab_ofdm_get_state", "dab_ofdm_sync", "dab_ofdm_join", "dab_ofdm_frame_bits", "dab_ofdm_get_params", "dab_ofdm_get_impulse_response",
     "dab_ofdm_get_coarse_frequency_response", "dab_ofdm_get_correlation_time_buffer", "dab_ofdm_get_frame_data_bits", "dab_ofdm_get_frame_fft", "dab_ofdm_get_frame_data_vec",
     "dab_ofdm_kernel_launches", "dab_ofdm_set_kernel_timing", "dab_ofdm_get_kernel_times", "dab_ofdm_demod_frames_device",
     "dab_viterbi_create", "dab_viterbi_destroy", "dab_viterbi_set_cuda_stream", "dab_viterbi_add_schedule",
@@ -147,6 +147,7 @@ def load():
     L.dab_ofdm_advance_uniform.argtypes = [vp, sz]
     L.dab_ofdm_device_bits.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), ip, C.POINTER(vp)]
     L.dab_ofdm_reset.argtypes = [vp, i32]
+    L.dab_ofdm_join.argtypes = [vp]
     L.dab_ofdm_get_state.argtypes = [vp, i32, C.POINTER(OfdmState)]
     L.dab_ofdm_sync.argtypes = [vp]
     L.dab_ofdm_frame_bits.argtypes = [vp]

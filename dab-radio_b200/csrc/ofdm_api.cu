@@ -58,6 +58,16 @@ struct Ofdm {
     bool force_generic_kernel = false;  // DAB_B200_GENERIC_FRAME_KERNEL=1: run the generic-geometry frame kernel (tests)
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    // pipeline ways: the streams of a handle are split into `ways` contiguous groups, each sequenced on its own CUDA stream, so
+    // that the latency-bound control passes of one group overlap the frame kernel of another (DAB_B200_PIPELINE_WAYS, default 2)
+    static constexpr int MAX_WAYS = 4;
+    int ways = 2;
+    cudaStream_t way_stream[MAX_WAYS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t way_done[MAX_WAYS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t counts_ready[MAX_WAYS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t bits_ready[MAX_WAYS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork_event = nullptr;
+    bool ways_pending = false;          // way streams carry work the handle's stream has not been ordered after yet
     // device memory
     DeviceBuffer<unsigned char> ring_iq;
     DeviceBuffer<float2> null_ring, corr_explicit, prs_fft_ref_conj, prs_time_ref_conj, fft_tap, vec_tap, twiddles;
@@ -107,23 +117,40 @@ struct ScopedKernelTimer {
     Ofdm* o;
     Ofdm::TimedLaunch t{};
     bool on;
-    ScopedKernelTimer(Ofdm* o_, int pass, bool is_frame) : o(o_), on(o_->timing) {
+    cudaStream_t st;
+    ScopedKernelTimer(Ofdm* o_, cudaStream_t st_, int pass, bool is_frame) : o(o_), on(o_->timing), st(st_) {
         if (!on) return;
         t.start = take_event(o);
         t.stop = take_event(o);
         t.pass = pass;
         t.is_frame = is_frame;
-        cudaEventRecord(t.start, o->stream);
+        cudaEventRecord(t.start, st);
     }
     ~ScopedKernelTimer() {
         if (!on) return;
-        cudaEventRecord(t.stop, o->stream);
+        cudaEventRecord(t.stop, st);
         o->timed.push_back(t);
     }
 };
 
+// Orders the handle's stream after everything queued on the way streams.  run_call leaves the ways un-joined when it can, so
+// that consecutive calls pipeline (no GPU-wide barrier per call); every entry point that exposes results joins first.
+static int join_ways(Ofdm* o) {
+    if (!o->ways_pending) return DAB_OK;
+    for (int w = 0; w < o->ways; w++) {
+        DAB_CUDA_CHECK(cudaEventRecord(o->way_done[w], o->way_stream[w]));
+        DAB_CUDA_CHECK(cudaStreamWaitEvent(o->stream, o->way_done[w], 0));
+    }
+    o->ways_pending = false;
+    return DAB_OK;
+}
+
 static int collect_times(Ofdm* o) {
-    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
+    {
+        int rc = join_ways(o);
+        if (rc != DAB_OK) return rc;
+    }
+    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));  // run_call joins the way streams into o->stream
     for (auto& t : o->timed) {
         float ms = 0.0f;
         DAB_CUDA_CHECK(cudaEventElapsedTime(&ms, t.start, t.stop));
@@ -174,7 +201,7 @@ static FrameGeom frame_geom(const Ofdm* o) {
 }
 
 template <int NFFT, bool RAW>
-static int launch_frame_t(Ofdm* o, const FrameDesc* d_descs, int n_frames) {
+static int launch_frame_t(Ofdm* o, cudaStream_t st, const FrameDesc* d_descs, int n_frames) {
     const FrameGeom g = frame_geom(o);
     if (DabGeom<NFFT>::matches(g.symbol_period, g.cyclic_prefix, g.n_carriers) && !o->force_generic_kernel && o->frame_kernel_version >= 3) {
         // the four DAB transmission modes, TMA-fed kernel with the separable PLL (ofdm_frame_v3.cuh)
@@ -184,10 +211,10 @@ static int launch_frame_t(Ofdm* o, const FrameDesc* d_descs, int n_frames) {
         const int grid = (n_items + GROUPS - 1) / GROUPS;
         if (o->debug_taps) {
             DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_v3_kernel<NFFT, RAW, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            ofdm_frame_v3_kernel<NFFT, RAW, true, 3><<<grid, FRAME_CTA_THREADS, smem, o->stream>>>(g, d_descs, n_frames);
+            ofdm_frame_v3_kernel<NFFT, RAW, true, 3><<<grid, FRAME_CTA_THREADS, smem, st>>>(g, d_descs, n_frames);
         } else {
             DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_v3_kernel<NFFT, RAW, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            ofdm_frame_v3_kernel<NFFT, RAW, false, 3><<<grid, FRAME_CTA_THREADS, smem, o->stream>>>(g, d_descs, n_frames);
+            ofdm_frame_v3_kernel<NFFT, RAW, false, 3><<<grid, FRAME_CTA_THREADS, smem, st>>>(g, d_descs, n_frames);
         }
         o->launches++;
         DAB_CUDA_CHECK(cudaGetLastError());
@@ -201,13 +228,13 @@ static int launch_frame_t(Ofdm* o, const FrameDesc* d_descs, int n_frames) {
         const int grid = (n_items + GROUPS - 1) / GROUPS;
         if (o->frame_min_blocks == 3) {
             DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_dab_kernel<NFFT, RAW, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            ofdm_frame_dab_kernel<NFFT, RAW, 3><<<grid, FRAME_CTA_THREADS, smem, o->stream>>>(g, d_descs, n_frames);
+            ofdm_frame_dab_kernel<NFFT, RAW, 3><<<grid, FRAME_CTA_THREADS, smem, st>>>(g, d_descs, n_frames);
         } else if (o->frame_min_blocks == 2) {
             DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_dab_kernel<NFFT, RAW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            ofdm_frame_dab_kernel<NFFT, RAW, 2><<<grid, FRAME_CTA_THREADS, smem, o->stream>>>(g, d_descs, n_frames);
+            ofdm_frame_dab_kernel<NFFT, RAW, 2><<<grid, FRAME_CTA_THREADS, smem, st>>>(g, d_descs, n_frames);
         } else {
             DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_dab_kernel<NFFT, RAW, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            ofdm_frame_dab_kernel<NFFT, RAW, 4><<<grid, FRAME_CTA_THREADS, smem, o->stream>>>(g, d_descs, n_frames);
+            ofdm_frame_dab_kernel<NFFT, RAW, 4><<<grid, FRAME_CTA_THREADS, smem, st>>>(g, d_descs, n_frames);
         }
         o->launches++;
         DAB_CUDA_CHECK(cudaGetLastError());
@@ -218,19 +245,19 @@ static int launch_frame_t(Ofdm* o, const FrameDesc* d_descs, int n_frames) {
     constexpr int GROUPS = FrameSmem<NFFT>::GROUPS;
     const int n_items = n_frames * g.n_chunks;
     const int grid = (n_items + GROUPS - 1) / GROUPS;
-    ofdm_frame_kernel<NFFT, RAW><<<grid, FRAME_CTA_THREADS, smem, o->stream>>>(g, d_descs, n_frames);
+    ofdm_frame_kernel<NFFT, RAW><<<grid, FRAME_CTA_THREADS, smem, st>>>(g, d_descs, n_frames);
     o->launches++;
     DAB_CUDA_CHECK(cudaGetLastError());
     return DAB_OK;
 }
 
-static int launch_frame(Ofdm* o, const FrameDesc* d_descs, int n_frames, bool raw) {
+static int launch_frame(Ofdm* o, cudaStream_t st, const FrameDesc* d_descs, int n_frames, bool raw) {
     if (n_frames <= 0) return DAB_OK;
     switch (o->nfft) {
-    case 2048: return raw ? launch_frame_t<2048, true>(o, d_descs, n_frames) : launch_frame_t<2048, false>(o, d_descs, n_frames);
-    case 1024: return raw ? launch_frame_t<1024, true>(o, d_descs, n_frames) : launch_frame_t<1024, false>(o, d_descs, n_frames);
-    case 512: return raw ? launch_frame_t<512, true>(o, d_descs, n_frames) : launch_frame_t<512, false>(o, d_descs, n_frames);
-    case 256: return raw ? launch_frame_t<256, true>(o, d_descs, n_frames) : launch_frame_t<256, false>(o, d_descs, n_frames);
+    case 2048: return raw ? launch_frame_t<2048, true>(o, st, d_descs, n_frames) : launch_frame_t<2048, false>(o, st, d_descs, n_frames);
+    case 1024: return raw ? launch_frame_t<1024, true>(o, st, d_descs, n_frames) : launch_frame_t<1024, false>(o, st, d_descs, n_frames);
+    case 512: return raw ? launch_frame_t<512, true>(o, st, d_descs, n_frames) : launch_frame_t<512, false>(o, st, d_descs, n_frames);
+    case 256: return raw ? launch_frame_t<256, true>(o, st, d_descs, n_frames) : launch_frame_t<256, false>(o, st, d_descs, n_frames);
     }
     return set_error(DAB_ERR_INVALID, "unsupported FFT size %d", o->nfft);
 }
@@ -243,6 +270,8 @@ static ControlGeom control_geom(const Ofdm* o) {
     g.cyclic_prefix = int(o->p.nb_cyclic_prefix);
     g.n_carriers = int(o->p.nb_data_carriers);
     g.slots = o->slots;
+    g.n_streams = o->n_streams;
+    g.stream0 = 0;
     g.frame_bits = o->frame_bits;
     if (o->ext_base) {
         g.mask = ~uint64_t(0);
@@ -276,23 +305,24 @@ static ControlGeom control_geom(const Ofdm* o) {
 }
 
 template <int NFFT, bool RAW>
-static int launch_control_t(Ofdm* o, int pass) {
-    const ControlGeom g = control_geom(o);
+static int launch_control_t(Ofdm* o, cudaStream_t st, int stream0, int count, int pass) {
+    ControlGeom g = control_geom(o);
+    g.stream0 = stream0;
     const size_t smem = ControlSmem<NFFT>::bytes();
     DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_control_kernel<NFFT, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    ofdm_control_kernel<NFFT, RAW><<<o->n_streams, ControlSmem<NFFT>::THREADS, smem, o->stream>>>(g, pass);
+    ofdm_control_kernel<NFFT, RAW><<<count, ControlSmem<NFFT>::THREADS, smem, st>>>(g, pass);
     o->launches++;
     DAB_CUDA_CHECK(cudaGetLastError());
     return DAB_OK;
 }
 
-static int launch_control(Ofdm* o, int pass) {
+static int launch_control(Ofdm* o, cudaStream_t st, int stream0, int count, int pass) {
     const bool raw = o->raw_u8;
     switch (o->nfft) {
-    case 2048: return raw ? launch_control_t<2048, true>(o, pass) : launch_control_t<2048, false>(o, pass);
-    case 1024: return raw ? launch_control_t<1024, true>(o, pass) : launch_control_t<1024, false>(o, pass);
-    case 512: return raw ? launch_control_t<512, true>(o, pass) : launch_control_t<512, false>(o, pass);
-    case 256: return raw ? launch_control_t<256, true>(o, pass) : launch_control_t<256, false>(o, pass);
+    case 2048: return raw ? launch_control_t<2048, true>(o, st, stream0, count, pass) : launch_control_t<2048, false>(o, st, stream0, count, pass);
+    case 1024: return raw ? launch_control_t<1024, true>(o, st, stream0, count, pass) : launch_control_t<1024, false>(o, st, stream0, count, pass);
+    case 512: return raw ? launch_control_t<512, true>(o, st, stream0, count, pass) : launch_control_t<512, false>(o, st, stream0, count, pass);
+    case 256: return raw ? launch_control_t<256, true>(o, st, stream0, count, pass) : launch_control_t<256, false>(o, st, stream0, count, pass);
     }
     return set_error(DAB_ERR_INVALID, "unsupported FFT size %d", o->nfft);
 }
@@ -306,8 +336,68 @@ static int passes_for(const Ofdm* o, uint64_t n_max) {
     return 1 + int((n_max - 1) / (frame_cap - o->p.nb_cyclic_prefix));
 }
 
-// one Process() call for every stream: n_call[s] new samples are already visible at [fed[s], fed[s] + n_call[s])
-static int run_call(Ofdm* o, bool uniform, uint64_t n_uniform) {
+struct WayRange {
+    int lo, hi;
+    cudaStream_t st;
+};
+static int n_ways(const Ofdm* o) { return (o->n_streams >= 64 * o->ways) ? o->ways : 1; }
+static WayRange way_range(const Ofdm* o, int w, int ways) {
+    WayRange r;
+    r.lo = int(int64_t(o->n_streams) * w / ways);
+    r.hi = int(int64_t(o->n_streams) * (w + 1) / ways);
+    r.st = (ways > 1) ? o->way_stream[w] : o->stream;
+    return r;
+}
+
+// begin -> L1 windows -> (control -> frame)* -> control  for the streams of one way, in order on the way's CUDA stream
+static int issue_way_kernels(Ofdm* o, const WayRange& r, bool uniform, uint64_t n_uniform, uint64_t n_max, int passes) {
+    const int count = r.hi - r.lo;
+    cudaStream_t st = r.st;
+    const int threads = 128;
+    ofdm_begin_call_kernel<<<(count + threads - 1) / threads, threads, 0, st>>>(o->states.ptr + r.lo, uniform ? nullptr : o->d_n.ptr + r.lo, n_uniform, count);
+    o->launches++;
+    DAB_CUDA_CHECK(cudaGetLastError());
+    // UpdateSignalAverage's window averages for this call (default config: one 100-sample window every 500 samples): every slot
+    // of the window buffer that the current call can reach under ANY config (the kernel skips windows past the call's end);
+    // update_signal_average falls back to in-kernel evaluation beyond the buffer
+    {
+        const int max_windows = (n_max >= 1) ? o->l1_windows_stride : 0;
+        const int64_t tasks = int64_t(count) * ((max_windows + L1_WB - 1) / L1_WB);
+        const int grid = int(std::min<int64_t>((tasks + 7) / 8, 148 * 8));
+        ControlGeom g = control_geom(o);
+        g.stream0 = r.lo;
+        if (grid > 0) {
+            ScopedKernelTimer timer(o, st, DAB_OFDM_TIMING_PASSES - 1, false);
+            if (o->raw_u8) ofdm_l1_windows_kernel<true><<<grid, 256, 0, st>>>(g, count, max_windows);
+            else ofdm_l1_windows_kernel<false><<<grid, 256, 0, st>>>(g, count, max_windows);
+            o->launches++;
+            DAB_CUDA_CHECK(cudaGetLastError());
+        }
+    }
+    for (int p = 0; p <= passes; p++) {
+        int rc;
+        {
+            ScopedKernelTimer timer(o, st, p, false);
+            rc = launch_control(o, st, r.lo, count, p);
+        }
+        if (rc != DAB_OK) return rc;
+        if (p < passes) {
+            ScopedKernelTimer timer(o, st, p, true);
+            rc = launch_frame(o, st, o->descs.ptr + size_t(p) * size_t(o->n_streams) + r.lo, count, o->raw_u8);
+            if (rc != DAB_OK) return rc;
+        }
+    }
+    return DAB_OK;
+}
+
+// One Process() call for every stream.  iq == nullptr: the n_call[s] new samples are already visible at [fed[s], fed[s] +
+// n_call[s]) (attached device streams).  Otherwise iq[s] is the caller's host block, copied into the stream ring first.
+//
+// The streams are split into pipeline ways.  Every way runs  upload -> begin -> L1 windows -> (control -> frame)* -> control ->
+// download of the frame counts  in order on its own CUDA stream (per-stream ordering is the reference's real-time order,
+// ofdm_control.cuh); different ways only share the GPU and the PCIe link, so one way's control passes (latency bound, ~1/4 of a
+// step when serialised) hide behind another way's frame kernel, and uploads, kernels and downloads of different ways overlap.
+static int run_call(Ofdm* o, bool uniform, uint64_t n_uniform, const void* const* iq) {
     uint64_t n_max = 0;
     if (uniform) {
         n_max = n_uniform;
@@ -317,39 +407,46 @@ static int run_call(Ofdm* o, bool uniform, uint64_t n_uniform) {
         memcpy(o->h_n.ptr, o->n_call.data(), sizeof(uint64_t) * size_t(o->n_streams));
         DAB_CUDA_CHECK(cudaMemcpyAsync(o->d_n.ptr, o->h_n.ptr, sizeof(uint64_t) * size_t(o->n_streams), cudaMemcpyHostToDevice, o->stream));
     }
-    const int threads = 128;
-    ofdm_begin_call_kernel<<<(o->n_streams + threads - 1) / threads, threads, 0, o->stream>>>(o->states.ptr, uniform ? nullptr : o->d_n.ptr,
-                                                                                            n_uniform, o->n_streams);
-    o->launches++;
-    DAB_CUDA_CHECK(cudaGetLastError());
-    // UpdateSignalAverage's window averages for this call (default config: one 100-sample window every 500 samples)
-    {
-        // every slot of the window buffer that the current call can reach under ANY config (the kernel skips windows past
-        // the call's end); update_signal_average falls back to in-kernel evaluation beyond the buffer
-        const int max_windows = (n_max >= 1) ? o->l1_windows_stride : 0;
-        const int64_t tasks = int64_t(o->n_streams) * max_windows;
-        const int grid = int(std::min<int64_t>((tasks + 7) / 8, 148 * 8));
-        const ControlGeom g = control_geom(o);
-        if (grid > 0) {
-            ScopedKernelTimer timer(o, DAB_OFDM_TIMING_PASSES - 1, false);
-            if (o->raw_u8) ofdm_l1_windows_kernel<true><<<grid, 256, 0, o->stream>>>(g, o->n_streams, max_windows);
-            else ofdm_l1_windows_kernel<false><<<grid, 256, 0, o->stream>>>(g, o->n_streams, max_windows);
-            o->launches++;
-            DAB_CUDA_CHECK(cudaGetLastError());
-        }
-    }
     const int passes = passes_for(o, n_max);
     if (passes > o->slots) return set_error(DAB_ERR_CAPACITY, "call of %llu samples exceeds max_block_samples", (unsigned long long)n_max);
-    for (int p = 0; p <= passes; p++) {
-        int rc;
-        {
-            ScopedKernelTimer timer(o, p, false);
-            rc = launch_control(o, p);
+    const int ways = n_ways(o);
+    const size_t sb = sample_bytes(o), ns = size_t(o->n_streams), slots = size_t(o->slots);
+    if (o->cb) {
+        DAB_CUDA_CHECK(o->h_frames.reserve(ns));
+        DAB_CUDA_CHECK(o->h_infos.reserve(ns * slots));
+    }
+    if (ways > 1) DAB_CUDA_CHECK(cudaEventRecord(o->fork_event, o->stream));
+    for (int w = 0; w < ways; w++) {
+        const WayRange r = way_range(o, w, ways);
+        if (ways > 1) DAB_CUDA_CHECK(cudaStreamWaitEvent(r.st, o->fork_event, 0));
+        if (iq) {
+            // the caller's span is only valid during the call (ofdm_demodulator.cpp:235): copy into the stream ring now
+            for (int s = r.lo; s < r.hi; s++) {
+                const size_t n = size_t(o->n_call[size_t(s)]);
+                if (n == 0) continue;
+                const size_t pos = size_t(o->fed[size_t(s)] & (o->ring_samples - 1));
+                const size_t first = std::min(n, o->ring_samples - pos);
+                unsigned char* base = o->ring_iq.ptr + size_t(s) * o->ring_samples * sb;
+                DAB_CUDA_CHECK(cudaMemcpyAsync(base + pos * sb, iq[s], first * sb, cudaMemcpyHostToDevice, r.st));
+                if (first < n)
+                    DAB_CUDA_CHECK(cudaMemcpyAsync(base, static_cast<const unsigned char*>(iq[s]) + first * sb, (n - first) * sb, cudaMemcpyHostToDevice, r.st));
+            }
         }
+        int rc = issue_way_kernels(o, r, uniform, n_uniform, n_max, passes);
         if (rc != DAB_OK) return rc;
-        if (p < passes) {
-            ScopedKernelTimer timer(o, p, true);
-            rc = launch_frame(o, o->descs.ptr + size_t(p) * size_t(o->n_streams), o->n_streams, o->raw_u8);
+        if (o->cb) {
+            const size_t cnt = size_t(r.hi - r.lo);
+            DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_frames.ptr + r.lo, o->frames_in_call.ptr + r.lo, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, r.st));
+            DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_infos.ptr + size_t(r.lo) * slots, o->infos.ptr + size_t(r.lo) * slots, cnt * slots * sizeof(dab_ofdm_frame_info),
+                                           cudaMemcpyDeviceToHost, r.st));
+        }
+        DAB_CUDA_CHECK(cudaEventRecord(o->counts_ready[w], r.st));
+    }
+    if (ways > 1) {
+        o->ways_pending = true;
+        // per-stream sample counts live in one device buffer that the next call overwrites from the handle's stream
+        if (!uniform) {
+            int rc = join_ways(o);
             if (rc != DAB_OK) return rc;
         }
     }
@@ -361,30 +458,52 @@ static int run_call(Ofdm* o, bool uniform, uint64_t n_uniform) {
     return DAB_OK;
 }
 
-// soft-bit callback delivery (CoordinatorThread's Notify, ofdm_demodulator.cpp:635), in stream then frame order
+// soft-bit callback delivery (CoordinatorThread's Notify, ofdm_demodulator.cpp:635), in stream then frame order.  Way by way:
+// as soon as a way's frame counts are on the host its soft bits are fetched (consecutive frames as one copy), and its
+// callbacks run while the later ways are still uploading / computing.
 static int deliver(Ofdm* o) {
     if (!o->cb) return DAB_OK;
-    const size_t ns = size_t(o->n_streams), slots = size_t(o->slots);
-    DAB_CUDA_CHECK(o->h_frames.reserve(ns));
-    DAB_CUDA_CHECK(o->h_infos.reserve(ns * slots));
-    DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_frames.ptr, o->frames_in_call.ptr, ns * sizeof(int32_t), cudaMemcpyDeviceToHost, o->stream));
-    DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_infos.ptr, o->infos.ptr, ns * slots * sizeof(dab_ofdm_frame_info), cudaMemcpyDeviceToHost, o->stream));
-    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
-    size_t total = 0;
-    for (size_t s = 0; s < ns; s++) total += size_t(std::max(0, o->h_frames.ptr[s]));
-    if (total == 0) return DAB_OK;
-    DAB_CUDA_CHECK(o->h_bits.reserve(total * o->frame_bits));
-    size_t k = 0;
-    for (size_t s = 0; s < ns; s++)
-        for (int f = 0; f < o->h_frames.ptr[s]; f++, k++)
-            DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_bits.ptr + k * o->frame_bits, o->bits.ptr + (s * slots + size_t(f)) * o->frame_bits, o->frame_bits,
-                                           cudaMemcpyDeviceToHost, o->stream));
-    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
-    k = 0;
-    for (size_t s = 0; s < ns; s++)
-        for (int f = 0; f < o->h_frames.ptr[s]; f++, k++)
-            o->cb(o->cb_user, int(s), o->h_bits.ptr + k * o->frame_bits, o->frame_bits, &o->h_infos.ptr[s * slots + size_t(f)]);
-    return DAB_OK;
+    const int ways = n_ways(o);
+    const size_t slots = size_t(o->slots), fb = o->frame_bits;
+    DAB_CUDA_CHECK(o->h_bits.reserve(size_t(o->n_streams) * slots * fb));
+    std::vector<size_t> first_k(size_t(ways) + 1, 0);
+    for (int w = 0; w < ways; w++) {
+        const WayRange r = way_range(o, w, ways);
+        DAB_CUDA_CHECK(cudaEventSynchronize(o->counts_ready[w]));
+        size_t k = first_k[size_t(w)];
+        // device source of frame (s, f) is (s * slots + f) * fb: frames of consecutive streams are contiguous when every
+        // stream filled all of its slots, which is the steady state with one-frame blocks
+        size_t run_src = 0, run_dst = 0, run_len = 0;
+        auto flush = [&]() -> int {
+            if (run_len) DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_bits.ptr + run_dst, o->bits.ptr + run_src, run_len, cudaMemcpyDeviceToHost, r.st));
+            run_len = 0;
+            return DAB_OK;
+        };
+        for (int s = r.lo; s < r.hi; s++)
+            for (int f = 0; f < o->h_frames.ptr[s]; f++, k++) {
+                const size_t src = (size_t(s) * slots + size_t(f)) * fb, dst = k * fb;
+                if (run_len && src == run_src + run_len && dst == run_dst + run_len) {
+                    run_len += fb;
+                } else {
+                    int rc = flush();
+                    if (rc != DAB_OK) return rc;
+                    run_src = src; run_dst = dst; run_len = fb;
+                }
+            }
+        int rc = flush();
+        if (rc != DAB_OK) return rc;
+        first_k[size_t(w) + 1] = k;
+        DAB_CUDA_CHECK(cudaEventRecord(o->bits_ready[w], r.st));
+    }
+    for (int w = 0; w < ways; w++) {
+        const WayRange r = way_range(o, w, ways);
+        DAB_CUDA_CHECK(cudaEventSynchronize(o->bits_ready[w]));
+        size_t k = first_k[size_t(w)];
+        for (int s = r.lo; s < r.hi; s++)
+            for (int f = 0; f < o->h_frames.ptr[s]; f++, k++)
+                o->cb(o->cb_user, s, o->h_bits.ptr + k * fb, fb, &o->h_infos.ptr[size_t(s) * slots + size_t(f)]);
+    }
+    return join_ways(o);
 }
 
 static int init_states(Ofdm* o) {
@@ -438,6 +557,13 @@ static int create_impl(Ofdm* o, const dab_c32* prs, const int* mapper) {
 
     DAB_CUDA_CHECK(cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking));
     o->stream = o->own_stream;
+    for (int w = 0; w < Ofdm::MAX_WAYS; w++) {
+        DAB_CUDA_CHECK(cudaStreamCreateWithFlags(&o->way_stream[w], cudaStreamNonBlocking));
+        DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->way_done[w], cudaEventDisableTiming));
+        DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->counts_ready[w], cudaEventDisableTiming));
+        DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->bits_ready[w], cudaEventDisableTiming));
+    }
+    DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->fork_event, cudaEventDisableTiming));
     DAB_CUDA_CHECK(o->ring_iq.reserve(ns * o->ring_samples * sample_bytes(o)));
     DAB_CUDA_CHECK(cudaMemset(o->ring_iq.ptr, 0, ns * o->ring_samples * sample_bytes(o)));
     DAB_CUDA_CHECK(o->null_ring.reserve(ns * o->p.nb_null_period));
@@ -532,6 +658,7 @@ dab_ofdm* dab_ofdm_create(const dab_ofdm_params* params, const dab_c32* prs_fft_
     o->debug_taps = options->keep_debug_taps != 0;
     o->max_block = options->max_block_samples ? options->max_block_samples : 262144;
     if (const char* e = getenv("DAB_B200_GENERIC_FRAME_KERNEL")) o->force_generic_kernel = (e[0] == '1');
+    if (const char* e = getenv("DAB_B200_PIPELINE_WAYS")) { const int w = atoi(e); if (w >= 1 && w <= Ofdm::MAX_WAYS) o->ways = w; }
     if (const char* e = getenv("DAB_B200_FRAME_KERNEL")) o->frame_kernel_version = atoi(e);
     if (const char* e = getenv("DAB_B200_FRAME_MIN_BLOCKS")) { const int b = atoi(e); o->frame_min_blocks = (b >= 2 && b <= 4) ? b : 3; }
     if (const char* e = getenv("DAB_B200_SYMS_PER_CHUNK")) { const int c = atoi(e); if (c >= 1 && c <= 1024) o->syms_per_chunk = c; }
@@ -548,6 +675,13 @@ void dab_ofdm_destroy(dab_ofdm* h) {
     cudaStreamSynchronize(o->stream);
     for (auto& t : o->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
     for (auto e : o->event_pool) cudaEventDestroy(e);
+    for (int w = 0; w < Ofdm::MAX_WAYS; w++) {
+        if (o->way_stream[w]) { cudaStreamSynchronize(o->way_stream[w]); cudaStreamDestroy(o->way_stream[w]); }
+        if (o->way_done[w]) cudaEventDestroy(o->way_done[w]);
+        if (o->counts_ready[w]) cudaEventDestroy(o->counts_ready[w]);
+        if (o->bits_ready[w]) cudaEventDestroy(o->bits_ready[w]);
+    }
+    if (o->fork_event) cudaEventDestroy(o->fork_event);
     if (o->own_stream) cudaStreamDestroy(o->own_stream);
     delete o;
 }
@@ -560,6 +694,7 @@ void dab_ofdm_destroy(dab_ofdm* h) {
 
 int dab_ofdm_set_cuda_stream(dab_ofdm* h, void* cuda_stream) {
     OFDM_HANDLE(h);
+    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
     o->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : o->own_stream;
     return DAB_OK;
@@ -574,6 +709,7 @@ int dab_ofdm_set_frame_callback(dab_ofdm* h, dab_ofdm_frame_cb cb, void* user) {
 
 int dab_ofdm_set_config(dab_ofdm* h, int stream, const dab_ofdm_config* cfg) {
     OFDM_HANDLE(h);
+    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     if (!cfg || stream < -1 || stream >= o->n_streams) return set_error(DAB_ERR_INVALID, "bad stream / config");
     DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
     const int lo = (stream < 0) ? 0 : stream, hi = (stream < 0) ? o->n_streams : stream + 1;
@@ -584,6 +720,7 @@ int dab_ofdm_set_config(dab_ofdm* h, int stream, const dab_ofdm_config* cfg) {
 
 int dab_ofdm_get_config(dab_ofdm* h, int stream, dab_ofdm_config* cfg) {
     OFDM_HANDLE(h);
+    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     if (!cfg || stream < 0 || stream >= o->n_streams) return set_error(DAB_ERR_INVALID, "bad stream / config");
     DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
     DAB_CUDA_CHECK(cudaMemcpy(cfg, reinterpret_cast<char*>(o->states.ptr + stream) + offsetof(StreamState, cfg), sizeof(*cfg), cudaMemcpyDeviceToHost));
@@ -593,25 +730,17 @@ int dab_ofdm_get_config(dab_ofdm* h, int stream, dab_ofdm_config* cfg) {
 static int ingest_and_run(Ofdm* o, const void* const* iq, const size_t* n, bool raw) {
     if (o->ext_base) return set_error(DAB_ERR_INVALID, "handle is attached to device-resident streams; use dab_ofdm_advance");
     if (raw != o->raw_u8) return set_error(DAB_ERR_INVALID, "handle was created with raw_u8_ingest = %d", int(o->raw_u8));
-    const size_t sb = sample_bytes(o);
     for (int s = 0; s < o->n_streams; s++) {
         const size_t ns = n[s];
         if (ns > o->max_block) return set_error(DAB_ERR_CAPACITY, "stream %d: block of %zu samples exceeds max_block_samples %zu", s, ns, o->max_block);
         if (ns > 0 && !iq[s]) return set_error(DAB_ERR_INVALID, "stream %d: null sample pointer", s);
         o->n_call[size_t(s)] = ns;
-        if (ns == 0) continue;
-        // the caller's span is only valid during the call (ofdm_demodulator.cpp:235): copy into the stream ring now
-        const size_t pos = size_t(o->fed[size_t(s)] & (o->ring_samples - 1));
-        const size_t first = std::min(ns, o->ring_samples - pos);
-        unsigned char* base = o->ring_iq.ptr + size_t(s) * o->ring_samples * sb;
-        DAB_CUDA_CHECK(cudaMemcpyAsync(base + pos * sb, iq[s], first * sb, cudaMemcpyHostToDevice, o->stream));
-        if (first < ns)
-            DAB_CUDA_CHECK(cudaMemcpyAsync(base, static_cast<const unsigned char*>(iq[s]) + first * sb, (ns - first) * sb, cudaMemcpyHostToDevice, o->stream));
     }
-    int rc = run_call(o, false, 0);
+    int rc = run_call(o, false, 0, iq);
     if (rc != DAB_OK) return rc;
-    // pageable source memory may still be in flight in a staging copy: the call must not return before it has left the span
-    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
+    // the caller's span (possibly pageable memory, staged by the driver) must have been consumed before the call returns
+    const int ways = n_ways(o);
+    for (int w = 0; w < ways; w++) DAB_CUDA_CHECK(cudaEventSynchronize(o->counts_ready[w]));
     return deliver(o);
 }
 
@@ -639,6 +768,7 @@ int dab_ofdm_process(dab_ofdm* h, int stream, const dab_c32* iq, size_t n) {
 
 int dab_ofdm_attach_device_streams(dab_ofdm* h, const dab_c32* d_iq, size_t stride_samples, size_t total_samples) {
     OFDM_HANDLE(h);
+    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     if (!d_iq || stride_samples < total_samples) return set_error(DAB_ERR_INVALID, "bad device stream geometry");
     DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
     o->ext_base = d_iq;
@@ -655,8 +785,9 @@ static int advance_impl(Ofdm* o, const size_t* n, size_t n_uniform) {
         if (o->fed[size_t(s)] + ns > o->ext_total) return set_error(DAB_ERR_CAPACITY, "stream %d: advance past the end of the attached buffer", s);
         o->n_call[size_t(s)] = ns;
     }
-    int rc = run_call(o, n == nullptr, n_uniform);
+    int rc = run_call(o, n == nullptr, n_uniform, nullptr);
     if (rc != DAB_OK) return rc;
+    if (n != nullptr) DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));  // the pinned staging copy of n[] is reused by the next call
     return deliver(o);
 }
 
@@ -673,6 +804,7 @@ int dab_ofdm_advance_uniform(dab_ofdm* h, size_t n) {
 
 int dab_ofdm_device_bits(dab_ofdm* h, const int8_t** d_bits, size_t* n_bits, int* slots_per_stream, const int32_t** d_frames_in_call) {
     OFDM_HANDLE(h);
+    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     if (d_bits) *d_bits = o->bits.ptr;
     if (n_bits) *n_bits = o->frame_bits;
     if (slots_per_stream) *slots_per_stream = o->slots;
@@ -682,6 +814,7 @@ int dab_ofdm_device_bits(dab_ofdm* h, const int8_t** d_bits, size_t* n_bits, int
 
 int dab_ofdm_reset(dab_ofdm* h, int stream) {
     OFDM_HANDLE(h);
+    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     if (stream < 0 || stream >= o->n_streams) return set_error(DAB_ERR_INVALID, "stream %d out of range", stream);
     ofdm_reset_stream_kernel<<<1, 1, 0, o->stream>>>(o->states.ptr, stream);
     o->launches++;
@@ -691,6 +824,7 @@ int dab_ofdm_reset(dab_ofdm* h, int stream) {
 
 int dab_ofdm_get_state(dab_ofdm* h, int stream, dab_ofdm_state* out) {
     OFDM_HANDLE(h);
+    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     if (!out || stream < 0 || stream >= o->n_streams) return set_error(DAB_ERR_INVALID, "bad stream / output");
     StreamState st;
     DAB_CUDA_CHECK(cudaMemcpyAsync(&st, o->states.ptr + stream, sizeof(st), cudaMemcpyDeviceToHost, o->stream));
@@ -706,8 +840,14 @@ int dab_ofdm_get_state(dab_ofdm* h, int stream, dab_ofdm_state* out) {
     return DAB_OK;
 }
 
+int dab_ofdm_join(dab_ofdm* h) {
+    OFDM_HANDLE(h);
+    return join_ways(o);
+}
+
 int dab_ofdm_sync(dab_ofdm* h) {
     OFDM_HANDLE(h);
+    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
     return DAB_OK;
 }
@@ -732,18 +872,21 @@ static int copy_out(Ofdm* o, void* dst, const void* d_src, size_t bytes) {
 
 int dab_ofdm_get_impulse_response(dab_ofdm* h, int stream, float* out, size_t nb_fft) {
     OFDM_HANDLE(h);
+    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     if (!out || stream < 0 || stream >= o->n_streams || nb_fft != size_t(o->nfft)) return set_error(DAB_ERR_INVALID, "bad argument");
     return copy_out(o, out, o->impulse.ptr + size_t(stream) * nb_fft, nb_fft * sizeof(float));
 }
 
 int dab_ofdm_get_coarse_frequency_response(dab_ofdm* h, int stream, float* out, size_t nb_fft) {
     OFDM_HANDLE(h);
+    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     if (!out || stream < 0 || stream >= o->n_streams || nb_fft != size_t(o->nfft)) return set_error(DAB_ERR_INVALID, "bad argument");
     return copy_out(o, out, o->freq_resp.ptr + size_t(stream) * nb_fft, nb_fft * sizeof(float));
 }
 
 int dab_ofdm_get_frame_data_bits(dab_ofdm* h, int stream, int8_t* out, size_t n_bits) {
     OFDM_HANDLE(h);
+    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     if (!out || stream < 0 || stream >= o->n_streams || n_bits != o->frame_bits) return set_error(DAB_ERR_INVALID, "bad argument");
     StreamState st;
     int rc = copy_out(o, &st, o->states.ptr + stream, sizeof(st));
@@ -753,6 +896,7 @@ int dab_ofdm_get_frame_data_bits(dab_ofdm* h, int stream, int8_t* out, size_t n_
 
 int dab_ofdm_get_correlation_time_buffer(dab_ofdm* h, int stream, dab_c32* out, size_t n) {
     OFDM_HANDLE(h);
+    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     const size_t cap = o->p.nb_null_period + o->p.nb_symbol_period;
     if (!out || stream < 0 || stream >= o->n_streams || n != cap) return set_error(DAB_ERR_INVALID, "bad argument (n must be nb_null_period + nb_symbol_period)");
     if (o->raw_u8) return set_error(DAB_ERR_INVALID, "not available with raw_u8_ingest");
@@ -786,6 +930,7 @@ int dab_ofdm_get_correlation_time_buffer(dab_ofdm* h, int stream, dab_c32* out, 
 
 int dab_ofdm_get_frame_fft(dab_ofdm* h, int stream, dab_c32* out, size_t n) {
     OFDM_HANDLE(h);
+    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     const size_t want = o->p.nb_frame_symbols * size_t(o->nfft);
     if (!o->debug_taps) return set_error(DAB_ERR_INVALID, "handle was created without keep_debug_taps");
     if (!out || stream < 0 || stream >= o->n_streams || n != want) return set_error(DAB_ERR_INVALID, "bad argument (n must be nb_frame_symbols * nb_fft)");
@@ -794,6 +939,7 @@ int dab_ofdm_get_frame_fft(dab_ofdm* h, int stream, dab_c32* out, size_t n) {
 
 int dab_ofdm_get_frame_data_vec(dab_ofdm* h, int stream, dab_c32* out, size_t n) {
     OFDM_HANDLE(h);
+    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     const size_t want = (o->p.nb_frame_symbols - 1) * o->p.nb_data_carriers;
     if (!o->debug_taps) return set_error(DAB_ERR_INVALID, "handle was created without keep_debug_taps");
     if (!out || stream < 0 || stream >= o->n_streams || n != want) return set_error(DAB_ERR_INVALID, "bad argument (n must be (nb_frame_symbols-1) * nb_data_carriers)");
@@ -845,7 +991,7 @@ int dab_ofdm_demod_frames_device(dab_ofdm* h, const dab_c32* d_frames, size_t fr
     }
     DAB_CUDA_CHECK(o->stage_descs.reserve(size_t(n_frames)));
     DAB_CUDA_CHECK(cudaMemcpyAsync(o->stage_descs.ptr, descs.data(), descs.size() * sizeof(FrameDesc), cudaMemcpyHostToDevice, o->stream));
-    int rc = launch_frame(o, o->stage_descs.ptr, n_frames, false);
+    int rc = launch_frame(o, o->stream, o->stage_descs.ptr, n_frames, false);
     // `descs` is a local: the upload must have left it before we return
     DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
     return rc;

@@ -82,10 +82,11 @@ template <int NFFT>
 struct ControlSmem {
     using G = FftGeom<NFFT>;
     static constexpr int THREADS = (G::T < 32) ? 32 : G::T;
-    static constexpr size_t bytes() {
-        return size_t(G::TW1_SIZE + G::TW2_SIZE + G::E1_SIZE + G::E2_SIZE + NFFT) * sizeof(float2) + size_t(CTRL_L1_BATCH) * sizeof(float) +
-               32 * sizeof(float2) + 64;
-    }
+    // `nat` (natural-order spectrum between two transforms) aliases exchange 1 and the L1 window batch aliases the (contiguous) exchanges: both
+    // are only alive while no transform is in flight (every hand-over is separated by a CTA barrier)
+    static_assert(G::E1_SIZE >= NFFT, "nat must fit into exchange 1");
+    static_assert(size_t(G::E1_SIZE + G::E2_SIZE) * sizeof(float2) >= size_t(CTRL_L1_BATCH) * sizeof(float), "L1 batch must fit into the exchanges");
+    static constexpr size_t bytes() { return size_t(G::TW1_SIZE + G::TW2_SIZE + G::E1_SIZE + G::E2_SIZE) * sizeof(float2) + 32 * sizeof(float2) + 64; }
 };
 
 struct ArgMax {
@@ -450,10 +451,14 @@ struct Control {
     }
 
     // ---- the fine-frequency half of CoordinatorThread (ofdm_demodulator.cpp:606-618, 632) for the frame dispatched before
-    __device__ void finish_pipeline_thread0() {
+    __device__ void finish_pipeline() {
+        // the per-symbol phase errors arrive with one parallel load; the sum keeps the reference's symbol order
         const float* pe = geo.phase_err + (size_t(stream) * geo.slots + st.pending_slot) * geo.n_symbols;
+        for (int s = tid; s < geo.n_symbols; s += THREADS) l1buf[s] = pe[s];
+        __syncthreads();
+        if (tid != 0) return;
         float total = 0.0f;
-        for (int s = 0; s < geo.n_symbols; s++) total += pe[s];
+        for (int s = 0; s < geo.n_symbols; s++) total += l1buf[s];
         const float avg = total / float(geo.n_symbols);
         const float two_pi = 3.14159265358979323846f * 2.0f;
         const float fine_error = (1.0f / float(NFFT)) * avg / two_pi;  // CalculateFineFrequencyError :821-823
@@ -555,7 +560,7 @@ __global__ void __launch_bounds__(256) ofdm_l1_windows_kernel(ControlGeom geo, i
 
 // pass: index of this control pass within the call (0 = first).  Frame slot `pass` is the one a dispatch in this pass fills.
 template <int NFFT, bool RAW_U8>
-__global__ void __launch_bounds__(ControlSmem<NFFT>::THREADS)
+__global__ void __launch_bounds__(ControlSmem<NFFT>::THREADS, 4)
 ofdm_control_kernel(ControlGeom geo, int pass) {
     using G = FftGeom<NFFT>;
     using C = Control<NFFT, RAW_U8>;
@@ -568,9 +573,9 @@ ofdm_control_kernel(ControlGeom geo, int pass) {
     float2* tw2 = tw1 + G::TW1_SIZE;
     float2* e1 = tw2 + G::TW2_SIZE;
     float2* e2 = e1 + G::E1_SIZE;
-    float2* nat = e2 + G::E2_SIZE;
-    float* l1buf = reinterpret_cast<float*>(nat + NFFT);
-    float2* red = reinterpret_cast<float2*>(l1buf + CTRL_L1_BATCH);
+    float2* nat = e1;
+    float* l1buf = reinterpret_cast<float*>(e1);
+    float2* red = e2 + G::E2_SIZE;
 
     if (tid == 0) {
         st = geo.states[stream];
@@ -582,12 +587,13 @@ ofdm_control_kernel(ControlGeom geo, int pass) {
     // nothing to do: no frame waiting for its fine update and no unread samples
     if (!st.pipeline_pending && st.consumed >= st.call_end) return;
 
-    fft_load_twiddles<NFFT>(tw1, geo.twiddles, tid, C::THREADS);
+    __shared__ int tw_loaded;  // the twiddle tables are only staged when a synchronisation stage actually runs
+    if (tid == 0) tw_loaded = 0;
     const void* src = RAW_U8 ? static_cast<const void*>(reinterpret_cast<const uchar2*>(geo.samples) + size_t(stream) * geo.stream_stride)
                              : static_cast<const void*>(reinterpret_cast<const float2*>(geo.samples) + size_t(stream) * geo.stream_stride);
     C ctl{geo, st, stream, tid, tw1, tw2, e1, e2, nat, l1buf, red, src};
 
-    if (tid == 0 && st.pipeline_pending) ctl.finish_pipeline_thread0();
+    if (st.pipeline_pending) ctl.finish_pipeline();
     __syncthreads();
     if (st.call_needs_average) ctl.update_signal_average();
 
@@ -608,10 +614,15 @@ ofdm_control_kernel(ControlGeom geo, int pass) {
             __syncthreads();
             break;
         case DAB_OFDM_RUNNING_COARSE_FREQ_SYNC:
-            ctl.run_coarse_freq_sync();
-            break;
         case DAB_OFDM_RUNNING_FINE_TIME_SYNC:
-            ctl.run_fine_time_sync();
+            if (!tw_loaded) {
+                fft_load_twiddles<NFFT>(tw1, geo.twiddles, tid, C::THREADS);
+                __syncthreads();
+                if (tid == 0) tw_loaded = 1;
+                __syncthreads();
+            }
+            if (st.state == DAB_OFDM_RUNNING_COARSE_FREQ_SYNC) ctl.run_coarse_freq_sync();
+            else ctl.run_fine_time_sync();
             break;
         case DAB_OFDM_READING_SYMBOLS:
             if (tid == 0) {

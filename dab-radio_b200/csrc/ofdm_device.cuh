@@ -174,6 +174,38 @@ __device__ __forceinline__ void fft_pass2(float2 (&v)[16], int t, const float2* 
     }
 }
 
+// fft_pass2 with the twiddle loads issued one batch of four ahead of the exchange-2 stores (see ofdm_frame_v3.cuh, pass 1)
+template <int NFFT>
+__device__ __forceinline__ void fft_pass2_pipelined(float2 (&v)[16], int t, const float2* e1, float2* e2, const float2* tw2) {
+    using G = FftGeom<NFFT>;
+    const int k1p = t / G::R3, n3p = t % G::R3;
+#pragma unroll
+    for (int n2 = 0; n2 < 16; n2++) v[n2] = e1[k1p * G::E1_STRIDE + n2 * G::R3 + n3p];
+    if (G::R3 == 1) {
+        dft16(v);
+        return;
+    }
+    float2 wn[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) wn[q] = tw2[q * G::R3 + n3p];
+    dft16(v);
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        float2 wc[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) wc[q] = wn[q];
+        if (b < 3) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) wn[q] = tw2[(4 * (b + 1) + q) * G::R3 + n3p];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k2 = 4 * b + q;
+            e2[G::e2(k1p, k2, n3p)] = (k2 == 0) ? v[0] : cmul(v[k2], wc[q]);
+        }
+    }
+}
+
 template <int NFFT>
 __device__ __forceinline__ void fft_pass3(float2 (&v)[16], int t, const float2* e2) {
     using G = FftGeom<NFFT>;

@@ -295,10 +295,27 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_f
         corr = group_reduce_sum<RED_WIDTH>(corr);
         if (WARPS_PER_GROUP > 1 && (t & 31) == 0) red[t >> 5] = corr;
 
-        // pass 1: DFT16 over n1, twiddle W_N^{t k1} B_t, scatter A[k1][t]
-        dft16(v);
+        // pass 1: DFT16 over n1, twiddle W_N^{t k1} B_t, scatter A[k1][t].  The twiddle loads are issued a batch of four ahead of
+        // the stores that consume the previous batch: the compiler cannot move a shared-memory load above a shared-memory store
+        // by itself, and a load placed right before its use costs the full LDS latency sixteen times over.
+        {
+            float2 wn[4];
 #pragma unroll
-        for (int k1 = 0; k1 < 16; k1++) e1[k1 * G::E1_STRIDE + t] = cmul(v[k1], tw1[k1 * T + t]);
+            for (int q = 0; q < 4; q++) wn[q] = tw1[q * T + t];
+            dft16(v);
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                float2 wc[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) wc[q] = wn[q];
+                if (b < 3) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) wn[q] = tw1[(4 * (b + 1) + q) * T + t];
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) e1[(4 * b + q) * G::E1_STRIDE + t] = cmul(v[4 * b + q], wc[q]);
+            }
+        }
         __syncthreads();  // ---- barrier A: every thread has consumed the input buffer and the D table
 
         const bool has_next = active && (s + 1 <= s_out_end) && si < n_iter;
@@ -321,7 +338,7 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_f
             staged = -1;
         }
 
-        fft_pass2<NFFT>(v, t, e1, e2, tw2);
+        fft_pass2_pipelined<NFFT>(v, t, e1, e2, tw2);
         __syncthreads();  // ---- barrier B
         fft_pass3<NFFT>(v, t, e2);
 

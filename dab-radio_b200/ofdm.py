@@ -124,6 +124,10 @@ class OfdmDemodBatch:
     def sync(self):
         capi.check(self.L.dab_ofdm_sync(self.h))
 
+    def join(self):
+        """order the handle's CUDA stream after all queued work (device side, the host does not block)"""
+        capi.check(self.L.dab_ofdm_join(self.h))
+
     def impulse_response(self, stream):
         out = np.zeros(self.params.nb_fft, np.float32)
         capi.check(self.L.dab_ofdm_get_impulse_response(self.h, stream, capi.ptr(out), out.size))

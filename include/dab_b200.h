@@ -155,6 +155,11 @@ DAB_API int dab_ofdm_process_batch_u8(dab_ofdm* h, const uint8_t* const* iq_u8, 
  * HBM.  The demodulator then reads the rows in place -- no ring copy.  dab_ofdm_advance(h, n) is one Process() call of n[s]
  * further samples per stream.  Soft bits stay on the device (dab_ofdm_device_bits) unless a callback is attached. */
 DAB_API int dab_ofdm_attach_device_streams(dab_ofdm* h, const dab_c32* d_iq, size_t stride_samples, size_t total_samples);
+/* dab_ofdm_advance* only queue work: internally the streams are split into pipeline ways on CUDA streams of their own, so that
+ * consecutive calls overlap (no GPU-wide barrier per call).  dab_ofdm_join orders the handle's CUDA stream after everything
+ * queued so far without blocking the host; dab_ofdm_device_bits, dab_ofdm_sync, the getters and the frame callback join
+ * implicitly.  Work the caller queues on the handle's stream BEFORE a call is always ordered before that call. */
+DAB_API int dab_ofdm_join(dab_ofdm* h);
 DAB_API int dab_ofdm_advance(dab_ofdm* h, const size_t* n);
 DAB_API int dab_ofdm_advance_uniform(dab_ofdm* h, size_t n);
 /* device pointer / geometry of the soft-bit output of the most recent process/advance call:
