@@ -280,43 +280,60 @@ def run_ours(args):
     del d
 
     # ------------------------------------------------------------------ e2e: host buffers through dab_ofdm_process_batch
-    e2e = None
-    if not args.no_e2e:
-        n_e2e = n_streams
-        # one frame period of every (periodic) stream in pinned host memory; fed repeatedly it is a continuous stream
-        host = torch.empty((n_e2e, FRAME_LEN), dtype=torch.complex64).pin_memory()
-        host.copy_(iq[:n_e2e, :FRAME_LEN])
-        # make the block periodic: same pool frame everywhere is not needed -- the demodulator is differential per symbol and
-        # re-synchronises on every PRS; the CFO phase is continuous across the block boundary by construction
+    def e2e_leg(u8):
+        """K calls of the reference-facing batch entry point with pinned HOST blocks (one frame period per stream; fed repeatedly
+        it is a continuous stream: the demodulator is differential per symbol and re-synchronises on every PRS, and the CFO
+        phase is continuous across the block boundary by construction).  Every call uploads the blocks, demodulates and hands
+        each completed frame's soft bits to the frame callback in host memory before it returns."""
+        if u8:
+            # examples/app_helpers/app_iq_readers.h:17-69 in reverse: what an 8-bit SDR front end delivers
+            src = torch.view_as_real(iq[:, :FRAME_LEN])
+            q = torch.clamp(src * 127.5 + 127.5, 0.0, 255.0).to(torch.uint8)
+            host = torch.empty((n_streams, FRAME_LEN, 2), dtype=torch.uint8).pin_memory()
+            host.copy_(q)
+            del q, src
+            bytes_per_sample = 2
+        else:
+            host = torch.empty((n_streams, FRAME_LEN), dtype=torch.complex64).pin_memory()
+            host.copy_(iq[:, :FRAME_LEN])
+            bytes_per_sample = 8
         torch.cuda.synchronize()
-        d = ofdm.OfdmDemodBatch(MODE, n_streams=n_e2e, device=local_rank, max_block_samples=FRAME_LEN)
+        d = ofdm.OfdmDemodBatch(MODE, n_streams=n_streams, device=local_rank, max_block_samples=FRAME_LEN, raw_u8=u8)
         d.set_cuda_stream(work_stream.cuda_stream)
-        d.collect = False
-        counter = {"frames": 0, "bytes": 0}
-
-        def on_frame(user, stream, bits, n_bits, info):
-            counter["frames"] += 1
-            counter["bytes"] += n_bits
-        cb = pkg.capi.FRAME_CB(on_frame)
-        pkg.capi.check(d.L.dab_ofdm_set_frame_callback(d.h, cb, None))
-        ptrs = [host[s].data_ptr() for s in range(n_e2e)]
-        ns = [FRAME_LEN] * n_e2e
+        counter = d.use_counting_callback()     # the library's own C callback: Python stays out of the delivery loop
+        p, n = d.pointer_arrays([host[s].data_ptr() for s in range(n_streams)], [FRAME_LEN] * n_streams)
         for _ in range(max(W, 3)):
-            d.process_batch_ptrs(ptrs, ns)
+            d.process_batch_prepared(p, n, u8)
         barrier()
-        counter["frames"] = 0
-        counter["bytes"] = 0
+        f0, b0 = int(counter.frames), int(counter.bits)
         t0 = time.perf_counter()
         for _ in range(K):
-            d.process_batch_ptrs(ptrs, ns)   # returns after the soft bits of every completed frame were delivered
+            d.process_batch_prepared(p, n, u8)   # returns after the soft bits of every completed frame were delivered
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         dt_max = aggregate(dt * 1e3, 0, world, dist)[0] * 1e-3
-        e2e = {"value": round(world * n_e2e * FRAME_LEN * K / dt_max / 1e6, 1), "unit": "MSamples/s",
-               "h2d_bytes_per_step": int(n_e2e * FRAME_LEN * 8), "d2h_bytes_per_step": int(counter["bytes"] / K),
-               "frames_delivered_per_step": counter["frames"] / K, "api": "dab_ofdm_process_batch (pinned host complex64) + frame callback",
-               "realtime_streams": round(world * n_e2e * FRAME_LEN * K / dt_max / FS, 1)}
+        frames, bits = int(counter.frames) - f0, int(counter.bits) - b0
+        out = {"value": round(world * n_streams * FRAME_LEN * K / dt_max / 1e6, 1), "unit": "MSamples/s",
+               "h2d_bytes_per_step": int(n_streams * FRAME_LEN * bytes_per_sample), "d2h_bytes_per_step": int(bits / K),
+               "frames_delivered_per_step": frames / K, "ms_per_step": round(dt_max / K * 1e3, 3),
+               "api": ("dab_ofdm_process_batch_u8 (pinned host uint8 IQ)" if u8 else "dab_ofdm_process_batch (pinned host complex64)") +
+                      " + frame callback (dab_ofdm_count_frames_cb)",
+               "realtime_streams": round(world * n_streams * FRAME_LEN * K / dt_max / FS, 1)}
         d.close()
+        del host
+        return out
+
+    e2e = None
+    if not args.no_e2e:
+        e2e = e2e_leg(False)
+        e2e["raw_u8_ingest"] = e2e_leg(True)   # SURVEY 8(f) rank 1: raw 8-bit IQ uploaded and dequantised on the device
+
+    # ------------------------------------------------------------------ Viterbi (secondary line; rank 0, N = 1 only)
+    viterbi = None
+    if rank == 0 and world == 1 and not args.no_viterbi:
+        del iq
+        torch.cuda.empty_cache()
+        viterbi = viterbi_leg(torch, pkg, n_streams, 5, not args.no_cpu)
 
     # ------------------------------------------------------------------ cpu baseline (rank 0, N = 1 only)
     cpu = None
@@ -334,13 +351,107 @@ def run_ours(args):
                        "l2": "inputs (1.6 GB per step) are larger than L2 and read once; no flush needed",
                        "snr_db": 25, "cfo": "+-50 kHz per stream", "parallelism": f"streams sharded, {world} rank(s), no data-path collective"},
             "realtime_streams": round(value * 1e6 / FS, 1), "realtime_streams_per_gpu": round(value * 1e6 / FS / world, 1),
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "viterbi": viterbi,
             "frames_per_stream_in_timed_region": frames_per_stream, "locked_streams": locked,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def viterbi_leg(torch, pkg, n_streams, reps, with_cpu):
+    """Secondary line (BASELINE.json configs[3]): full-ensemble Viterbi decode.  Per stream and transmission frame: the FIC
+    (4 groups: PI_16 x 21 blocks, PI_15 x 3, PI_X; fic_decoder.cpp:74-87) plus the whole MSC as 18 DAB+ sub-channels of 48 CU at
+    EEP 3-A (PI_8 x 45 blocks, PI_7 x 3, PI_X; subchannel_protection_tables.h:121-126) x 4 CIFs = 76 trellises over exactly the
+    230 400 soft bits one demodulated frame holds.  Soft bits, jobs and outputs are device resident; CUDA-event timing."""
+    from oracle import pyoracle as po
+    vit = importlib.import_module("dab-radio_b200.viterbi")
+    rng = np.random.default_rng(99)
+    fic = [(po.puncture_code(16), 128 * 21), (po.puncture_code(15), 128 * 3), (po.PI_X, 24)]
+    eep = [(po.puncture_code(8), 128 * 45), (po.puncture_code(7), 128 * 3), (po.PI_X, 24)]
+    layout = [(fic, 96, 2304)] * 4 + [(eep, 192, 3072)] * 72
+    base = []
+    for segs, nbytes, nsoft in layout:
+        tx = po.puncture(po.conv_encode(rng.integers(0, 256, nbytes, dtype=np.uint8)), segs)
+        assert tx.size == nsoft
+        base.append(np.clip(np.rint(tx + 60.0 * rng.standard_normal(tx.size)), -128, 127).astype(np.int8))
+    base = np.concatenate(base)
+    frame_soft, frame_out = base.size, sum(nb for _, nb, _ in layout)
+    vb = vit.ViterbiBatch(torch.cuda.current_device())
+    vb.set_cuda_stream(torch.cuda.current_stream().cuda_stream)
+    sid_fic = vb.add_schedule(vit.make_schedule(fic, 96))
+    sid_eep = vb.add_schedule(vit.make_schedule(eep, 192))
+    jobs = np.zeros(n_streams * len(layout), pkg.capi.VIT_JOB_DTYPE)
+    k = 0
+    for s in range(n_streams):
+        so, oo = s * frame_soft, s * frame_out
+        for segs, nbytes, nsoft in layout:
+            jobs[k] = (sid_fic if nbytes == 96 else sid_eep, nsoft, so, oo)
+            so += nsoft
+            oo += nbytes
+            k += 1
+    d_base = torch.from_numpy(base).cuda()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    # every stream: the same code words under its own extra noise; stream 0 keeps the CPU-generated soft bits for the check
+    d_soft = (d_base.view(1, -1).to(torch.int16) + torch.randint(-24, 25, (n_streams, frame_soft), device="cuda", generator=g, dtype=torch.int16))
+    d_soft = d_soft.clamp_(-128, 127).to(torch.int8).contiguous()
+    d_soft[0] = d_base
+    d_jobs = torch.from_numpy(jobs.view(np.uint8)).cuda()
+    d_out = torch.zeros(n_streams * frame_out, dtype=torch.uint8, device="cuda")
+    d_err = torch.zeros(jobs.size, dtype=torch.int64, device="cuda")
+    d_st = torch.zeros(jobs.size, dtype=torch.int32, device="cuda")
+    max_steps = 1542
+    run = lambda: vb.decode_jobs_device(d_soft.data_ptr(), d_soft.numel(), d_jobs.data_ptr(), jobs.size, max_steps, d_out.data_ptr(), d_out.numel(),
+                                        d_err.data_ptr(), d_st.data_ptr())
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    assert int(d_st.abs().max().item()) == 0
+    # stream 0 against the oracle: bit-exact bytes and path error for all 76 trellises
+    out0 = d_out[:frame_out].cpu().numpy()
+    err0 = d_err[:len(layout)].cpu().numpy()
+    ov = po.OracleViterbi()
+    so = oo = 0
+    for i, (segs, nbytes, nsoft) in enumerate(layout):
+        ov.set_traceback_length(nbytes * 8)
+        ref_out, ref_err, _ = ov.decode_job(base[so:so + nsoft], segs, nbytes)
+        assert np.array_equal(out0[oo:oo + nbytes], ref_out) and int(err0[i]) == ref_err, f"viterbi job {i} differs from the oracle"
+        so += nsoft
+        oo += nbytes
+    steps = n_streams * (4 * 774 + 72 * 1542)
+    bits = n_streams * frame_out * 8
+    res = {"metric": "full-ensemble Viterbi decode (FIC + 18 x EEP 3-A 48 CU x 4 CIF per Mode I frame)", "value": round(bits / ms / 1e3, 1),
+           "unit": "decoded Mbit/s", "ms_per_launch": round(ms, 4), "trellises": int(jobs.size), "streams": n_streams,
+           "trellis_steps_per_s": round(steps / ms * 1e3, 0), "ensemble_frames_per_s": round(n_streams / ms * 1e3, 1),
+           "realtime_ensembles": round(n_streams / ms * 1e3 * 0.096, 1), "bit_exact_vs_oracle": f"{len(layout)} trellises of stream 0",
+           "bound": "integer ALU (ACS); HBM traffic = soft bits in + bits/8 out, negligible"}
+    if with_cpu:
+        try:
+            from oracle import pyref
+            import ctypes as C
+            L = pyref.fast_lib()
+            cores = os.cpu_count() or 1
+            n_jobs = cores * 400
+            soft = np.tile(base[4 * 2304:4 * 2304 + 3072], n_jobs)
+            codes, lens, nout = po.pack_segments(eep)
+            out = np.zeros(n_jobs * 192, np.uint8)
+            P = lambda a: a.ctypes.data_as(C.c_void_p)
+            dt = float(L.ref_vit_bench(cores, P(soft), 3072, n_jobs, P(codes), P(lens), P(nout), len(eep), 1536, P(out), 192))
+            res["cpu_baseline"] = {"value": round(n_jobs * 1536 / dt / 1e6, 1), "unit": "decoded Mbit/s", "cores": cores, "kind": "reference",
+                                   "sample": f"{n_jobs} EEP 3-A 48 CU trellises, DAB_Viterbi_Decoder (AVX2 u16), one decoder per core, {dt:.2f} s"}
+        except (FileNotFoundError, OSError, AttributeError) as e:  # noqa: PERF203
+            res["cpu_baseline"] = {"unavailable": repr(e)}
+    vb.close()
+    return res
 
 
 def cpu_baseline(args, sample_frames):
@@ -428,6 +539,7 @@ def main():
     ap.add_argument("--streams", type=int, default=N_STREAMS)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-viterbi", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=2000, help="frames per instance in the cpu_baseline sample")
     ap.add_argument("--ref-frames", type=int, default=25, help="frames per instance per step for --impl reference")
     args = ap.parse_args()

@@ -47,6 +47,10 @@ class OfdmConfig(C.Structure):
     ]
 
 
+class FrameCounter(C.Structure):
+    _fields_ = [("frames", C.c_uint64), ("bits", C.c_uint64), ("checksum", C.c_uint64)]
+
+
 class OfdmState(C.Structure):
     _fields_ = [
         ("state", C.c_int32), ("fine_time_offset", C.c_int32), ("total_frames_read", C.c_int32),
@@ -100,7 +104,7 @@ EXPORTED_SYMBOLS = (
     "dab_ofdm_create", "dab_ofdm_destroy", "dab_ofdm_set_cuda_stream", "dab_ofdm_set_frame_callback", "dab_ofdm_set_config",
     "dab_ofdm_get_config", "dab_ofdm_default_config", "dab_ofdm_process", "dab_ofdm_process_batch", "dab_ofdm_process_batch_u8",
     "dab_ofdm_attach_device_streams", "dab_ofdm_advance", "dab_ofdm_advance_uniform", "dab_ofdm_device_bits", "dab_ofdm_reset",
-    "dab_ofdm_get_state", "dab_ofdm_sync", "dab_ofdm_join", "dab_ofdm_frame_bits", "dab_ofdm_get_params", "dab_ofdm_get_impulse_response",
+    "dab_ofdm_get_state", "dab_ofdm_sync", "dab_ofdm_join", "dab_ofdm_count_frames_cb", "dab_ofdm_frame_bits", "dab_ofdm_get_params", "dab_ofdm_get_impulse_response",
     "dab_ofdm_get_coarse_frequency_response", "dab_ofdm_get_correlation_time_buffer", "dab_ofdm_get_frame_data_bits", "dab_ofdm_get_frame_fft", "dab_ofdm_get_frame_data_vec",
     "dab_ofdm_kernel_launches", "dab_ofdm_set_kernel_timing", "dab_ofdm_get_kernel_times", "dab_ofdm_demod_frames_device",
     "dab_viterbi_create", "dab_viterbi_destroy", "dab_viterbi_set_cuda_stream", "dab_viterbi_add_schedule",

@@ -59,13 +59,17 @@ struct Ofdm {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     // pipeline ways: the streams of a handle are split into `ways` contiguous groups, each sequenced on its own CUDA stream, so
-    // that the latency-bound control passes of one group overlap the frame kernel of another (DAB_B200_PIPELINE_WAYS, default 2)
-    static constexpr int MAX_WAYS = 4;
-    int ways = 2;
-    cudaStream_t way_stream[MAX_WAYS] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t way_done[MAX_WAYS] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t counts_ready[MAX_WAYS] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t bits_ready[MAX_WAYS] = {nullptr, nullptr, nullptr, nullptr};
+    // that the latency-bound control passes of one group overlap the frame kernel of another (DAB_B200_PIPELINE_WAYS, default 4)
+    static constexpr int MAX_WAYS = 8;
+    int ways = 4;
+    cudaStream_t way_stream[MAX_WAYS] = {};
+    cudaEvent_t way_done[MAX_WAYS] = {};
+    cudaEvent_t counts_ready[MAX_WAYS] = {};
+    cudaEvent_t bits_ready[MAX_WAYS] = {};
+    cudaEvent_t up_done[MAX_WAYS] = {};
+    // host-buffer path: all uploads on one stream and all soft-bit downloads on another, each in way order, so that the PCIe
+    // link serves the ways first-in first-out (copies queued on the way streams themselves share the link and all finish last)
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;
     cudaEvent_t fork_event = nullptr;
     bool ways_pending = false;          // way streams carry work the handle's stream has not been ordered after yet
     // device memory
@@ -421,15 +425,21 @@ static int run_call(Ofdm* o, bool uniform, uint64_t n_uniform, const void* const
         if (ways > 1) DAB_CUDA_CHECK(cudaStreamWaitEvent(r.st, o->fork_event, 0));
         if (iq) {
             // the caller's span is only valid during the call (ofdm_demodulator.cpp:235): copy into the stream ring now
+            cudaStream_t up = (ways > 1) ? o->up_stream : r.st;
+            if (ways > 1 && w == 0) DAB_CUDA_CHECK(cudaStreamWaitEvent(up, o->fork_event, 0));
             for (int s = r.lo; s < r.hi; s++) {
                 const size_t n = size_t(o->n_call[size_t(s)]);
                 if (n == 0) continue;
                 const size_t pos = size_t(o->fed[size_t(s)] & (o->ring_samples - 1));
                 const size_t first = std::min(n, o->ring_samples - pos);
                 unsigned char* base = o->ring_iq.ptr + size_t(s) * o->ring_samples * sb;
-                DAB_CUDA_CHECK(cudaMemcpyAsync(base + pos * sb, iq[s], first * sb, cudaMemcpyHostToDevice, r.st));
+                DAB_CUDA_CHECK(cudaMemcpyAsync(base + pos * sb, iq[s], first * sb, cudaMemcpyHostToDevice, up));
                 if (first < n)
-                    DAB_CUDA_CHECK(cudaMemcpyAsync(base, static_cast<const unsigned char*>(iq[s]) + first * sb, (n - first) * sb, cudaMemcpyHostToDevice, r.st));
+                    DAB_CUDA_CHECK(cudaMemcpyAsync(base, static_cast<const unsigned char*>(iq[s]) + first * sb, (n - first) * sb, cudaMemcpyHostToDevice, up));
+            }
+            if (ways > 1) {
+                DAB_CUDA_CHECK(cudaEventRecord(o->up_done[w], up));
+                DAB_CUDA_CHECK(cudaStreamWaitEvent(r.st, o->up_done[w], 0));
             }
         }
         int rc = issue_way_kernels(o, r, uniform, n_uniform, n_max, passes);
@@ -474,8 +484,9 @@ static int deliver(Ofdm* o) {
         // device source of frame (s, f) is (s * slots + f) * fb: frames of consecutive streams are contiguous when every
         // stream filled all of its slots, which is the steady state with one-frame blocks
         size_t run_src = 0, run_dst = 0, run_len = 0;
+        cudaStream_t down = (ways > 1) ? o->down_stream : r.st;  // counts_ready[w] (synchronised above) follows the way's kernels
         auto flush = [&]() -> int {
-            if (run_len) DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_bits.ptr + run_dst, o->bits.ptr + run_src, run_len, cudaMemcpyDeviceToHost, r.st));
+            if (run_len) DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_bits.ptr + run_dst, o->bits.ptr + run_src, run_len, cudaMemcpyDeviceToHost, down));
             run_len = 0;
             return DAB_OK;
         };
@@ -493,7 +504,7 @@ static int deliver(Ofdm* o) {
         int rc = flush();
         if (rc != DAB_OK) return rc;
         first_k[size_t(w) + 1] = k;
-        DAB_CUDA_CHECK(cudaEventRecord(o->bits_ready[w], r.st));
+        DAB_CUDA_CHECK(cudaEventRecord(o->bits_ready[w], down));
     }
     for (int w = 0; w < ways; w++) {
         const WayRange r = way_range(o, w, ways);
@@ -562,7 +573,10 @@ static int create_impl(Ofdm* o, const dab_c32* prs, const int* mapper) {
         DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->way_done[w], cudaEventDisableTiming));
         DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->counts_ready[w], cudaEventDisableTiming));
         DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->bits_ready[w], cudaEventDisableTiming));
+        DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->up_done[w], cudaEventDisableTiming));
     }
+    DAB_CUDA_CHECK(cudaStreamCreateWithFlags(&o->up_stream, cudaStreamNonBlocking));
+    DAB_CUDA_CHECK(cudaStreamCreateWithFlags(&o->down_stream, cudaStreamNonBlocking));
     DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->fork_event, cudaEventDisableTiming));
     DAB_CUDA_CHECK(o->ring_iq.reserve(ns * o->ring_samples * sample_bytes(o)));
     DAB_CUDA_CHECK(cudaMemset(o->ring_iq.ptr, 0, ns * o->ring_samples * sample_bytes(o)));
@@ -680,7 +694,10 @@ void dab_ofdm_destroy(dab_ofdm* h) {
         if (o->way_done[w]) cudaEventDestroy(o->way_done[w]);
         if (o->counts_ready[w]) cudaEventDestroy(o->counts_ready[w]);
         if (o->bits_ready[w]) cudaEventDestroy(o->bits_ready[w]);
+        if (o->up_done[w]) cudaEventDestroy(o->up_done[w]);
     }
+    if (o->up_stream) { cudaStreamSynchronize(o->up_stream); cudaStreamDestroy(o->up_stream); }
+    if (o->down_stream) { cudaStreamSynchronize(o->down_stream); cudaStreamDestroy(o->down_stream); }
     if (o->fork_event) cudaEventDestroy(o->fork_event);
     if (o->own_stream) cudaStreamDestroy(o->own_stream);
     delete o;
@@ -698,6 +715,17 @@ int dab_ofdm_set_cuda_stream(dab_ofdm* h, void* cuda_stream) {
     DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
     o->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : o->own_stream;
     return DAB_OK;
+}
+
+void dab_ofdm_count_frames_cb(void* user, int stream, const int8_t* bits, size_t n_bits, const dab_ofdm_frame_info* info) {
+    auto* c = static_cast<dab_ofdm_frame_counter*>(user);
+    if (!c) return;
+    uint64_t sum = uint64_t(stream) + uint64_t(info ? info->frame_start : 0);
+    const size_t edge = n_bits < 64 ? n_bits : 64;
+    for (size_t i = 0; i < edge; i++) sum = sum * 31u + uint8_t(bits[i]) + uint8_t(bits[n_bits - 1 - i]);
+    c->frames++;
+    c->bits += n_bits;
+    c->checksum += sum;
 }
 
 int dab_ofdm_set_frame_callback(dab_ofdm* h, dab_ofdm_frame_cb cb, void* user) {

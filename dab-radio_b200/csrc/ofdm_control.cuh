@@ -11,6 +11,7 @@
 #pragma once
 #include "ofdm_device.cuh"
 #include "ofdm_frame.cuh"
+#include "ofdm_frame_dab.cuh"
 
 namespace dabb200 {
 
@@ -252,7 +253,10 @@ struct Control {
     }
 
     // forward FFT of v (input layout v[n1] = x[n1 T + t]); result in registers, bin of slot r = fft_out_bin(t, r)
-    __device__ void fft_forward(float2 (&v)[16]) {
+    // One copy of the transform in the instruction stream: the five transforms of a synchronisation used to be inlined one
+    // after the other (19 000 straight-line instructions, ~300 KB) and the kernel spent a third of its cycles waiting for
+    // instruction fetches (profiles/r01d_control_kernel_ncu.md).  The 16 points travel through local memory at the call.
+    __device__ __noinline__ void fft_forward(float2 (&v)[16]) {
         if (tid < T) fft_pass1<NFFT>(v, tid, e1, tw1);
         __syncthreads();
         if (tid < T) fft_pass2<NFFT>(v, tid, e1, e2, tw2);
@@ -515,33 +519,42 @@ __global__ void __launch_bounds__(256) ofdm_l1_windows_kernel(ControlGeom geo, i
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int groups = (max_windows + L1_WB - 1) / L1_WB;
-    const int64_t total = int64_t(n_streams) * groups;
-    for (int64_t task = int64_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); task < total; task += int64_t(gridDim.x) * warps_per_block) {
-        const int stream = geo.stream0 + int(task / groups), w0 = int(task % groups) * L1_WB;
-        const StreamState& st = geo.states[stream];
-        const int K = st.cfg.signal_l1_nb_samples;
-        const int L = K * st.cfg.signal_l1_nb_decimate;
-        const int64_t N = st.call_end - st.call_begin;
+    const int total = n_streams * groups;
+    for (int task = blockIdx.x * warps_per_block + (threadIdx.x >> 5); task < total; task += gridDim.x * warps_per_block) {
+        const int stream = geo.stream0 + task / groups, w0 = (task % groups) * L1_WB;
+        const StreamState* st = geo.states + stream;
+        const int K = st->cfg.signal_l1_nb_samples;
+        const int L = K * st->cfg.signal_l1_nb_decimate;
+        const int64_t call_begin = st->call_begin;
+        const int64_t N = st->call_end - call_begin;
         if (K <= 0 || L <= 0 || N < K) continue;
-        const void* src = RAW_U8 ? static_cast<const void*>(reinterpret_cast<const uchar2*>(geo.samples) + size_t(stream) * geo.stream_stride)
-                                 : static_cast<const void*>(reinterpret_cast<const float2*>(geo.samples) + size_t(stream) * geo.stream_stride);
-        bool live[L1_WB];
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(geo.samples) + size_t(stream) * geo.stream_stride * (RAW_U8 ? 2 : 8);
+        // window b: samples [first, first + K) of the stream; `flat` when it does not wrap around the ring
+        bool live[L1_WB], flat[L1_WB];
+        uint64_t first[L1_WB];
         float acc[L1_WB];
 #pragma unroll
         for (int b = 0; b < L1_WB; b++) {
             live[b] = (w0 + b < max_windows) && (int64_t(w0 + b) * L < N - K);  // loop condition i < M of the reference
+            first[b] = uint64_t(call_begin + int64_t(w0 + b) * L) & geo.mask;
+            flat[b] = (geo.mask == ~uint64_t(0)) || (first[b] + uint64_t(K) <= geo.mask + 1);
             acc[b] = 0.0f;
         }
         for (int i0 = 0; i0 < K; i0 += 128) {
             float2 v[L1_WB][4];
 #pragma unroll
-            for (int b = 0; b < L1_WB; b++)
+            for (int b = 0; b < L1_WB; b++) {
+                const unsigned char* p = src + first[b] * (RAW_U8 ? 2 : 8);
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const int i = i0 + lane + 32 * q;
-                    v[b][q] = (live[b] && i < K) ? load_sample<RAW_U8>(src, uint64_t(st.call_begin + int64_t(w0 + b) * L + i) & geo.mask)
-                                                 : make_float2(0.0f, 0.0f);
+                    v[b][q] = make_float2(0.0f, 0.0f);
+                    if (live[b] && i < K) {
+                        if (flat[b]) v[b][q] = load_sample_ptr<RAW_U8>(p + i * (RAW_U8 ? 2 : 8));
+                        else v[b][q] = load_sample<RAW_U8>(src, (first[b] + uint64_t(i)) & geo.mask);
+                    }
                 }
+            }
 #pragma unroll
             for (int b = 0; b < L1_WB; b++)
 #pragma unroll

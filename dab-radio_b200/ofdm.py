@@ -86,6 +86,20 @@ class OfdmDemodBatch:
         n = (C.c_size_t * self.n_streams)(*ns)
         capi.check(self.L.dab_ofdm_process_batch(self.h, p, n))
 
+    def pointer_arrays(self, ptrs, ns):
+        """ctypes argument arrays for process_batch_prepared, built once and reused every step"""
+        return (C.c_void_p * self.n_streams)(*ptrs), (C.c_size_t * self.n_streams)(*ns)
+
+    def process_batch_prepared(self, p, n, u8=False):
+        capi.check((self.L.dab_ofdm_process_batch_u8 if u8 else self.L.dab_ofdm_process_batch)(self.h, p, n))
+
+    def use_counting_callback(self):
+        """deliver frames to the library's own dab_ofdm_count_frames_cb (no Python in the delivery loop); returns the counter"""
+        self.counter = capi.FrameCounter()
+        cb = C.cast(self.L.dab_ofdm_count_frames_cb, capi.FRAME_CB)
+        capi.check(self.L.dab_ofdm_set_frame_callback(self.h, cb, C.cast(C.pointer(self.counter), C.c_void_p)))
+        return self.counter
+
     def attach_device_streams(self, d_ptr, stride_samples, total_samples):
         capi.check(self.L.dab_ofdm_attach_device_streams(self.h, d_ptr, stride_samples, total_samples))
 

@@ -131,6 +131,16 @@ typedef struct {
  * invoked the process/sync entry point, in frame order per stream. */
 typedef void (*dab_ofdm_frame_cb)(void* user, int stream, const int8_t* bits, size_t n_bits, const dab_ofdm_frame_info* info);
 
+/* A ready-made dab_ofdm_frame_cb for throughput measurements from languages whose own callbacks are slow (bench.py's e2e leg
+ * delivers 1024 frames per step): `user` points at a dab_ofdm_frame_counter that accumulates the frames and soft bits
+ * delivered and a checksum over the first and last 64 soft bits of every frame. */
+typedef struct {
+    uint64_t frames;
+    uint64_t bits;
+    uint64_t checksum;
+} dab_ofdm_frame_counter;
+DAB_API void dab_ofdm_count_frames_cb(void* user, int stream, const int8_t* bits, size_t n_bits, const dab_ofdm_frame_info* info);
+
 /* OFDM_Demod::OFDM_Demod(params, prs_fft_ref, carrier_mapper, nb_desired_threads) -- the thread count has no meaning here */
 DAB_API dab_ofdm* dab_ofdm_create(const dab_ofdm_params* params, const dab_c32* prs_fft_ref, const int* carrier_mapper,
                                   const dab_ofdm_options* options, int* status);
