@@ -211,3 +211,85 @@ def test_reset_and_config_are_honoured(ofdm, oracle):
     assert d.state(0)["total_frames_desync"] >= 1
     d.close()
     o.close()
+
+
+# config 3: carrier frequency offset x sample-rate drift x multipath x AWGN.  The drift / multipath / AWGN
+# generators are ours (tests/dabgen.py, seeded); the acceptance is north_star's: identical frame starts and Reset events,
+# frequency estimates within 1e-3 bin, >= 99.9 % of the soft bits within +-1 LSB.
+IMPAIRMENT_CASES = [
+    # mode, block, cfo_hz, drift_ppm, snr_db, multipath [(delay samples, gain dB, phase rad)]
+    (1, 65536, 333.0, 10.0, 30.0, [(0, 0.0, 0.0), (40, -6.0, 1.0)]),
+    (1, 65536, -2500.0, -50.0, 20.0, [(0, 0.0, 0.0), (100, -3.0, 2.0), (230, -9.0, -1.0)]),
+    (1, 4096, 50000.0, 100.0, 10.0, [(0, 0.0, 0.0), (17, -12.0, 0.5), (120, -6.0, 2.5), (250, -9.0, -2.0)]),
+    (1, 65536, -50000.0, -100.0, 10.0, None),
+    (2, 4096, 2500.0, 50.0, 20.0, [(0, 0.0, 0.0), (30, -3.0, -2.0), (60, -12.0, 0.3)]),
+    (4, 4096, -333.0, -10.0, 30.0, [(0, 0.0, 0.0), (100, -9.0, 1.5)]),
+]
+
+
+@pytest.mark.parametrize("mode,block,cfo_hz,drift_ppm,snr_db,multipath", IMPAIRMENT_CASES)
+def test_impairments_match_oracle(ofdm, oracle, mode, block, cfo_hz, drift_ppm, snr_db, multipath):
+    x = dabgen.make_stream(mode, 6, seed=100 + mode, cfo_hz=cfo_hz, start=12345, snr_db=snr_db, multipath=multipath,
+                           drift_ppm=drift_ppm)
+    o, d = _run_both(ofdm, oracle, mode, x, block)
+    _assert_stream_parity(oracle, mode, o, d, min_frames=3)
+    d.close()
+    o.close()
+
+
+def test_mixed_mode_batch(ofdm, oracle):
+    """config 5: streams of transmission modes I-IV live on the GPU at the same time (one handle per mode, calls interleaved),
+    4096-sample blocks so that the reference itself locks in modes II / III"""
+    block, per_mode = 4096, 3
+    handles, streams = {}, {}
+    for mode in (1, 2, 3, 4):
+        handles[mode] = ofdm.OfdmDemodBatch(mode, n_streams=per_mode, max_block_samples=block)
+        # Mode III only locks when the stream starts inside a NULL symbol (STREAM_CASES above)
+        streams[mode] = [dabgen.make_stream(mode, 4, seed=200 + 10 * mode + s, cfo_hz=[0.0, 2500.0, -333.0][s],
+                                            start=0 if mode == 3 else 7000 * s + 11, snr_db=25.0) for s in range(per_mode)]
+    longest = max(x.size for xs in streams.values() for x in xs)
+    for off in range(0, longest, block):
+        for mode in (1, 2, 3, 4):
+            if off < streams[mode][0].size:
+                handles[mode].process_batch([x[off:off + block] for x in streams[mode]])
+    locked = 0
+    for mode in (1, 2, 3, 4):
+        for s in range(per_mode):
+            o = oracle.OracleOfdmDemod(mode)
+            o.process_blocks(streams[mode][s], block)
+            # Mode II streams that start well outside the NULL symbol never lock in the reference either (as Mode III above):
+            # there the vector pins equal desync counts and zero frames
+            _assert_stream_parity(oracle, mode, o, handles[mode], stream=s, min_frames=0)
+            locked += o.frames_done() >= 2
+            o.close()
+        handles[mode].close()
+    assert locked >= 10
+
+
+def test_full_size_batch_of_1024_streams(ofdm, oracle):
+    """config 2 at BASELINE.json's size: 1024 streams in one handle (the pipeline-way split, FIFO upload / download streams and
+    the strided bulk upload are only active at this size).  8 distinct streams are each fed to 128 slots: every replica must
+    deliver exactly the frames of its base stream (size-independent property), and the base streams match the oracle."""
+    mode, block, n_base, n_streams = 1, 100000, 8, 1024
+    base = [dabgen.make_stream(mode, 3, seed=300 + b, cfo_hz=[0.0, 333.0, -2500.0, 50000.0, -333.0, 2500.0, -50000.0, 1000.0][b],
+                               start=b * 23456 + 5, snr_db=25.0) for b in range(n_base)]
+    d = ofdm.OfdmDemodBatch(mode, n_streams=n_streams, max_block_samples=block)
+    stack = np.stack(base)
+    for k, off in enumerate(range(0, base[0].size, block)):
+        if k % 2 == 0:   # rows of one [n_streams][block] array: equal pointer stride -> the pitched bulk upload
+            rows = np.ascontiguousarray(np.tile(stack[:, off:off + block], (n_streams // n_base, 1)))
+            d.process_batch([rows[s] for s in range(n_streams)])
+        else:            # scattered host blocks -> one copy per stream
+            d.process_batch([base[s % n_base][off:off + block] for s in range(n_streams)])
+    for b in range(n_base):
+        o = oracle.OracleOfdmDemod(mode)
+        o.process_blocks(base[b], block)
+        _assert_stream_parity(oracle, mode, o, d, stream=b, min_frames=1)
+        o.close()
+    for s in range(n_base, n_streams):
+        got, want = d.frames[s], d.frames[s % n_base]
+        assert len(got) == len(want) >= 1
+        for (gi, gb), (wi, wb) in zip(got, want):
+            assert gi["frame_start"] == wi["frame_start"] and gi["fine_offset_after"] == wi["fine_offset_after"]
+            assert np.array_equal(gb, wb), f"stream {s} differs from its base stream {s % n_base}"
+    d.close()
