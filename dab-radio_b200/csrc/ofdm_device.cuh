@@ -10,11 +10,20 @@
 
 namespace dabb200 {
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x)); }
+// Complex arithmetic on the packed FP32x2 pipe of sm_100 (FADD2 / FMUL2 / FFMA2): one instruction per complex add, two per
+// complex multiply.  ptxas folds the operand shapes used below into the instruction's own operand modifiers -- scalar
+// broadcast (R.F32), half swap (R.F32x2.LO_HI) and per-half negation (.NP / .PN) -- so multiplying by +-j or by a conjugate
+// costs nothing (probe: tools/f32x2_probe.cu; the packed forms issue at half the rate of the scalar ones, so the FP pipe
+// time is the same and the issue slots halve).  Rounding is identical to the scalar fmaf forms these replace.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return __ffma2_rn(a, make_float2(b.x, b.x), __fmul2_rn(make_float2(-a.y, a.x), make_float2(b.y, b.y)));
+}
 // a * conj(b)
-__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) { return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y)); }
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {
+    return __ffma2_rn(a, make_float2(b.x, b.x), __fmul2_rn(make_float2(a.y, -a.x), make_float2(b.y, b.y)));
+}
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 // multiply by -j
 __device__ __forceinline__ float2 mul_mj(float2 a) { return make_float2(a.y, -a.x); }
@@ -39,8 +48,8 @@ constexpr float kC16 = 0.92387953251128675613f;  // cos(pi/8)
 constexpr float kS16 = 0.38268343236508977173f;  // sin(pi/8)
 
 // multiply by W_8^1 = (1 - j)/sqrt(2) and W_8^3 = (-1 - j)/sqrt(2)
-__device__ __forceinline__ float2 mul_w8_1(float2 a) { return make_float2((a.x + a.y) * kC8, (a.y - a.x) * kC8); }
-__device__ __forceinline__ float2 mul_w8_3(float2 a) { return make_float2((a.y - a.x) * kC8, -(a.x + a.y) * kC8); }
+__device__ __forceinline__ float2 mul_w8_1(float2 a) { return __fmul2_rn(__fadd2_rn(a, make_float2(a.y, -a.x)), make_float2(kC8, kC8)); }
+__device__ __forceinline__ float2 mul_w8_3(float2 a) { return __fmul2_rn(__fadd2_rn(a, make_float2(-a.y, a.x)), make_float2(-kC8, -kC8)); }
 
 // forward DFT of 8 points, natural order in and out
 __device__ __forceinline__ void dft8(float2 (&v)[8]) {
