@@ -252,17 +252,6 @@ struct Control {
         st.freq_fine = fmodf(st.freq_fine, wrap);
     }
 
-    // forward FFT of v (input layout v[n1] = x[n1 T + t]); result in registers, bin of slot r = fft_out_bin(t, r)
-    // One copy of the transform in the instruction stream: the five transforms of a synchronisation used to be inlined one
-    // after the other (19 000 straight-line instructions, ~300 KB) and the kernel spent a third of its cycles waiting for
-    // instruction fetches (profiles/r01d_control_kernel_ncu.md).  The 16 points travel through local memory at the call.
-    __device__ __noinline__ void fft_forward(float2 (&v)[16]) {
-        if (tid < T) fft_pass1<NFFT>(v, tid, e1, tw1);
-        __syncthreads();
-        if (tid < T) fft_pass2<NFFT>(v, tid, e1, e2, tw2);
-        __syncthreads();
-        if (tid < T) fft_pass3<NFFT>(v, tid, e2);
-    }
     __device__ void store_natural(const float2 (&v)[16], bool conjugate) {
         if (tid < T) {
 #pragma unroll
@@ -290,46 +279,93 @@ struct Control {
         return r;
     }
 
-    // ---- RunCoarseFreqSync (ofdm_demodulator.cpp:360-471)
-    __device__ void run_coarse_freq_sync() {
-        if (!st.cfg.sync_is_coarse_freq_correction) {
-            if (tid == 0) { st.freq_coarse = 0.0f; st.state = DAB_OFDM_RUNNING_FINE_TIME_SYNC; }
-            __syncthreads();
-            return;
+    // ---- RunCoarseFreqSync (ofdm_demodulator.cpp:360-471) followed by RunFineTimeSync (:473-548).
+    // The reference runs the two back to back inside one Process() call (neither consumes samples, :256-262), so they are one
+    // five-transform sequence here:  stage 0-2 = coarse frequency (FFT, IFFT, FFT), stage 3-4 = fine time (FFT, IFFT).  The
+    // transform is inlined ONCE, inside the stage loop, with its 16 points per thread in registers: five inlined copies made
+    // the kernel wait on instruction fetches for a third of its cycles (profiles/r01d), and one out-of-line copy sent the
+    // points through local memory, which thrashes the 22 KB of L1 left beside four CTAs' shared memory (profiles/r01f:
+    // 176 us per pass against 80 us).
+    __device__ void run_sync() {
+        int stage = 3;
+        if (st.state == DAB_OFDM_RUNNING_COARSE_FREQ_SYNC) {
+            if (st.cfg.sync_is_coarse_freq_correction) {
+                stage = 0;
+            } else {
+                if (tid == 0) { st.freq_coarse = 0.0f; st.state = DAB_OFDM_RUNNING_FINE_TIME_SYNC; }
+                __syncthreads();
+            }
         }
+        const int cp = geo.cyclic_prefix, sp = geo.symbol_period, np = geo.null_period;
         float2 v[16];
-        // step 1: FFT of the first NFFT samples of the received PRS symbol window
-        if (tid < T) {
+#pragma unroll 1
+        for (; stage < 5; stage++) {
+            // ---- input of the transform, v[n1] = x[n1 T + t]
+            if (tid < T) {
+                if (stage == 0) {
+                    // FFT of the first NFFT samples of the received PRS symbol window (:383-387)
 #pragma unroll
-            for (int n1 = 0; n1 < 16; n1++) v[n1] = corr_at(geo.null_period + n1 * T + tid);
-        }
-        fft_forward(v);
-        store_natural(v, false);
-        // step 2: relative phase conj(X[i]) X[i+1], last bin zero (:901-909); step 3: IFFT = conj(FFT(conj(.)))
-        if (tid < T) {
+                    for (int n1 = 0; n1 < 16; n1++) v[n1] = corr_at(np + n1 * T + tid);
+                } else if (stage == 1) {
+                    // relative phase conj(X[i]) X[i+1], last bin zero (:901-909); IFFT = conj(FFT(conj(.)))
 #pragma unroll
-            for (int n1 = 0; n1 < 16; n1++) {
-                const int i = n1 * T + tid;
-                const float2 rel = (i < NFFT - 1) ? cmul(cconj(nat[i]), nat[i + 1]) : make_float2(0.0f, 0.0f);
-                v[n1] = cconj(rel);
+                    for (int n1 = 0; n1 < 16; n1++) {
+                        const int i = n1 * T + tid;
+                        const float2 rel = (i < NFFT - 1) ? cmul(cconj(nat[i]), nat[i + 1]) : make_float2(0.0f, 0.0f);
+                        v[n1] = cconj(rel);
+                    }
+                } else if (stage == 2) {
+                    // multiply by conj(IFFT(relative phase of the reference)), then FFT (:402-414)
+#pragma unroll
+                    for (int n1 = 0; n1 < 16; n1++) {
+                        const int i = n1 * T + tid;
+                        v[n1] = cmul(nat[i], geo.prs_time_ref_conj[i]);
+                    }
+                } else if (stage == 3) {
+                    // fine time: PRS window with the PLL at the (just updated) net frequency offset (:482-489)
+                    const PllSymbol pll = pll_symbol(st.freq_coarse + st.freq_fine, 0, NFFT);
+#pragma unroll
+                    for (int n1 = 0; n1 < 16; n1++) {
+                        const int i = n1 * T + tid;
+                        v[n1] = pll_rotate(pll, corr_at(np + i), i);
+                    }
+                } else {
+#pragma unroll
+                    for (int n1 = 0; n1 < 16; n1++) v[n1] = nat[n1 * T + tid];
+                }
+            }
+            __syncthreads();  // `nat` aliases exchange 1
+            if (tid < T) fft_pass1<NFFT>(v, tid, e1, tw1);
+            __syncthreads();
+            if (tid < T) fft_pass2<NFFT>(v, tid, e1, e2, tw2);
+            __syncthreads();
+            if (tid < T) fft_pass3<NFFT>(v, tid, e2);
+            // ---- what becomes of the spectrum (bin of register slot r = fft_out_bin(t, r))
+            if (stage == 0) {
+                store_natural(v, false);
+            } else if (stage == 1) {
+                store_natural(v, true);
+            } else if (stage == 2) {
+                coarse_freq_decide(v);
+            } else if (stage == 3) {
+                // correlation in time = conjugate product in frequency; then IFFT through conj(FFT(conj(.)))
+                if (tid < T) {
+#pragma unroll
+                    for (int r = 0; r < 16; r++) v[r] = cmul(v[r], geo.prs_fft_ref_conj[fft_out_bin<NFFT>(tid, r)]);
+                }
+                store_natural(v, true);
+            } else {
+                fine_time_decide(v, cp, sp, np);
             }
         }
-        __syncthreads();
-        fft_forward(v);
-        store_natural(v, true);
-        // step 4: multiply by conj(IFFT(relative phase of the reference)); step 5: FFT
-        if (tid < T) {
-#pragma unroll
-            for (int n1 = 0; n1 < 16; n1++) {
-                const int i = n1 * T + tid;
-                v[n1] = cmul(nat[i], geo.prs_time_ref_conj[i]);
-            }
-        }
-        __syncthreads();
-        fft_forward(v);
+    }
+
+    // steps 6-11 of RunCoarseFreqSync (:416-470) on the spectrum of the third transform
+    __device__ __forceinline__ void coarse_freq_decide(const float2 (&v)[16]) {
         // step 6: magnitude in dB, fft-shifted (:911-920)
         float* resp = geo.freq_response + size_t(stream) * NFFT;
         float* mag = reinterpret_cast<float*>(nat);
+        __syncthreads();  // every thread is past its exchange-2 reads before `nat` (exchange 1) is overwritten
         if (tid < T) {
 #pragma unroll
             for (int r = 0; r < 16; r++) {
@@ -379,38 +415,12 @@ struct Control {
         __syncthreads();
     }
 
-    // ---- RunFineTimeSync (ofdm_demodulator.cpp:473-548)
-    __device__ void run_fine_time_sync() {
-        const int cp = geo.cyclic_prefix, sp = geo.symbol_period, np = geo.null_period;
-        const float freq_offset = st.freq_coarse + st.freq_fine;
-        float2 v[16];
-        if (tid < T) {
-            const PllSymbol pll = pll_symbol(freq_offset, 0, NFFT);
-#pragma unroll
-            for (int n1 = 0; n1 < 16; n1++) {
-                const int i = n1 * T + tid;
-                v[n1] = pll_rotate(pll, corr_at(np + i), i);
-            }
-        }
-        fft_forward(v);
-        // correlation in time = conjugate product in frequency; then IFFT through conj(FFT(conj(.)))
-        if (tid < T) {
-#pragma unroll
-            for (int r = 0; r < 16; r++) {
-                const int k = fft_out_bin<NFFT>(tid, r);
-                v[r] = cmul(v[r], geo.prs_fft_ref_conj[k]);
-            }
-        }
-        store_natural(v, true);
-        if (tid < T) {
-#pragma unroll
-            for (int n1 = 0; n1 < 16; n1++) v[n1] = nat[n1 * T + tid];
-        }
-        __syncthreads();
-        fft_forward(v);
+    // the impulse-response half of RunFineTimeSync (:497-547) on the spectrum of the fifth transform
+    __device__ __forceinline__ void fine_time_decide(const float2 (&v)[16], int cp, int sp, int np) {
         float* resp = geo.impulse_response + size_t(stream) * NFFT;
         float* imp = reinterpret_cast<float*>(nat);
         float partial = 0.0f;
+        __syncthreads();  // see coarse_freq_decide
         if (tid < T) {
 #pragma unroll
             for (int r = 0; r < 16; r++) {
@@ -634,8 +644,7 @@ ofdm_control_kernel(ControlGeom geo, int pass) {
                 if (tid == 0) tw_loaded = 1;
                 __syncthreads();
             }
-            if (st.state == DAB_OFDM_RUNNING_COARSE_FREQ_SYNC) ctl.run_coarse_freq_sync();
-            else ctl.run_fine_time_sync();
+            ctl.run_sync();
             break;
         case DAB_OFDM_READING_SYMBOLS:
             if (tid == 0) {
