@@ -95,6 +95,32 @@ class VitSchedule(C.Structure):
                 ("start_state", C.c_uint32), ("end_state", C.c_uint32)]
 
 
+class DabParameters(C.Structure):
+    """DAB_Parameters (reference src/dab/constants/dab_parameters.h:5-21)."""
+    _fields_ = [(k, C.c_int) for k in
+                ("nb_frame_bits", "nb_symbols", "nb_fic_symbols", "nb_msc_symbols", "nb_fibs", "nb_cifs", "nb_fibs_per_cif",
+                 "nb_sym_bits", "nb_fic_bits", "nb_msc_bits", "nb_fib_bits", "nb_fib_cif_bits", "nb_cif_bits")]
+
+    def asdict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class Subchannel(C.Structure):
+    """The fields of Subchannel (reference src/dab/database/dab_database_entities.h:179-190) the decoder reads."""
+    _fields_ = [(k, C.c_int32) for k in
+                ("id", "start_address", "length", "is_uep", "uep_prot_index", "eep_prot_level", "eep_type_b", "reserved")]
+
+
+class EnsembleOptions(C.Structure):
+    _fields_ = [("n_streams", C.c_int), ("device", C.c_int), ("max_subchannels", C.c_int)]
+
+
+class EnsembleResults(C.Structure):
+    _fields_ = [("fib_bytes", C.c_void_p), ("fib_valid", C.c_void_p), ("fic_error", C.c_void_p), ("msc_bytes", C.c_void_p),
+                ("msc_nbytes", C.c_void_p), ("msc_error", C.c_void_p), ("decoded", C.c_void_p), ("fib_group_bytes", C.c_size_t),
+                ("msc_cif_bytes", C.c_size_t), ("nb_cifs", C.c_int), ("nb_fibs_per_cif", C.c_int), ("max_subchannels", C.c_int)]
+
+
 VIT_JOB_DTYPE = np.dtype([("schedule", np.uint32), ("n_soft", np.uint32), ("soft_offset", np.uint64), ("out_offset", np.uint64)])
 
 # every symbol include/dab_b200.h declares (tests/test_capi_symbols.py checks the library exports each of them)
@@ -110,6 +136,10 @@ EXPORTED_SYMBOLS = (
     "dab_viterbi_create", "dab_viterbi_destroy", "dab_viterbi_set_cuda_stream", "dab_viterbi_add_schedule",
     "dab_viterbi_schedule_soft_symbols", "dab_viterbi_decode_batch", "dab_viterbi_decode_batch_device",
     "dab_viterbi_decode_jobs_device", "dab_viterbi_decode_one", "dab_viterbi_sync", "dab_viterbi_kernel_launches",
+    "dab_get_dab_parameters", "dab_ensemble_create", "dab_ensemble_destroy", "dab_ensemble_set_cuda_stream",
+    "dab_ensemble_set_subchannels", "dab_ensemble_subchannel_schedule", "dab_ensemble_decode_frames_device",
+    "dab_ensemble_decode_frames", "dab_ensemble_device_results", "dab_ensemble_read_fic", "dab_ensemble_read_msc",
+    "dab_ensemble_sync", "dab_ensemble_kernel_launches", "dab_ensemble_last_work",
 )
 
 _lib = None
@@ -169,6 +199,7 @@ def load():
     L.dab_ofdm_get_kernel_times.argtypes = [vp, C.POINTER(OfdmKernelTimes)]
     L.dab_ofdm_demod_frames_device.argtypes = [vp, vp, sz, i32, vp, vp, vp]
     _bind_viterbi(L)
+    _bind_ensemble(L)
     _lib = L
     return L
 
@@ -191,6 +222,29 @@ def _bind_viterbi(L):
     L.dab_viterbi_sync.argtypes = [vp]
     L.dab_viterbi_kernel_launches.argtypes = [vp]
     L.dab_viterbi_kernel_launches.restype = u64
+    return L
+
+
+def _bind_ensemble(L):
+    vp, sz, i32, u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
+    ip = C.POINTER(C.c_int)
+    L.dab_get_dab_parameters.argtypes = [i32, C.POINTER(DabParameters)]
+    L.dab_ensemble_create.argtypes = [C.POINTER(DabParameters), C.POINTER(EnsembleOptions), ip]
+    L.dab_ensemble_create.restype = vp
+    L.dab_ensemble_destroy.argtypes = [vp]
+    L.dab_ensemble_destroy.restype = None
+    L.dab_ensemble_set_cuda_stream.argtypes = [vp, vp]
+    L.dab_ensemble_set_subchannels.argtypes = [vp, i32, vp, i32]
+    L.dab_ensemble_subchannel_schedule.argtypes = [C.POINTER(Subchannel), C.POINTER(VitSchedule), C.POINTER(C.c_uint32)]
+    L.dab_ensemble_decode_frames_device.argtypes = [vp, vp, sz, vp, i32]
+    L.dab_ensemble_decode_frames.argtypes = [vp, vp, vp]
+    L.dab_ensemble_device_results.argtypes = [vp, C.POINTER(EnsembleResults)]
+    L.dab_ensemble_read_fic.argtypes = [vp, i32, vp, vp, vp]
+    L.dab_ensemble_read_msc.argtypes = [vp, i32, i32, i32, vp, sz, C.POINTER(C.c_int32), C.POINTER(u64)]
+    L.dab_ensemble_sync.argtypes = [vp]
+    L.dab_ensemble_kernel_launches.argtypes = [vp]
+    L.dab_ensemble_kernel_launches.restype = u64
+    L.dab_ensemble_last_work.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     return L
 
 

@@ -1,8 +1,11 @@
 /* dab_b200.h -- C ABI of the B200-native DAB receive hot path (libdab_b200.so).
  *
- * This is the drop-in boundary for exactly two reference components and nothing else:
+ * This is the drop-in boundary for the receive hot path and the callers either side of its Viterbi stage, nothing else:
  *   1. OFDM_Demod            /root/reference/src/ofdm/ofdm_demodulator.h:47-168   (IQ -> int8 soft bits)
  *   2. DAB_Viterbi_Decoder   /root/reference/src/dab/algorithms/dab_viterbi_decoder.h:12-45 (punctured soft bits -> bytes)
+ *   3. FIC_Decoder / MSC_Decoder + CIF_Deinterleaver
+ *                            /root/reference/src/dab/fic/fic_decoder.h:17-40, src/dab/msc/msc_decoder.h:18-43,
+ *                            src/dab/msc/cif_deinterleaver.h:10-24   (frame soft bits -> FIBs + sub-channel bytes)
  * Plain pointers and sizes only; no C++ or torch types cross this boundary.  The C++ mirror classes that keep the
  * reference's own signatures on top of these calls live in dab-radio_b200/cpp/ (see INTEGRATION.md).
  *
@@ -263,6 +266,90 @@ DAB_API int dab_viterbi_decode_one(dab_viterbi* h, const dab_vit_schedule* s, co
                                    uint64_t* path_error);
 DAB_API int dab_viterbi_sync(dab_viterbi* h);
 DAB_API uint64_t dab_viterbi_kernel_launches(const dab_viterbi* h);
+/* ------------------------------------------------------------------------------------------------------------------
+ * Ensemble decoder: everything between one OFDM frame of soft bits and the decoded bytes, batched over streams.
+ * Replaces, per stream, BasicRadio::Process's split of the frame (src/basic_radio/basic_radio.cpp:42-63), one FIC_Decoder
+ * (src/dab/fic/fic_decoder.cpp:53-116: Viterbi PI_16 x21 + PI_15 x3 + PI_X, energy dispersal, CRC16 per FIB) and one
+ * MSC_Decoder per sub-channel (src/dab/msc/msc_decoder.cpp:46-170: CIF_Deinterleaver over 16 CIFs
+ * (cif_deinterleaver.cpp:21-70), EEP / UEP puncturing schedule (subchannel_protection_tables.h), Viterbi, energy dispersal).
+ * The soft bits never leave HBM between the demodulator and the decoded bytes.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* same fields and order as DAB_Parameters (src/dab/constants/dab_parameters.h:5-21) */
+typedef struct {
+    int nb_frame_bits, nb_symbols, nb_fic_symbols, nb_msc_symbols, nb_fibs, nb_cifs, nb_fibs_per_cif;
+    int nb_sym_bits, nb_fic_bits, nb_msc_bits, nb_fib_bits, nb_fib_cif_bits, nb_cif_bits;
+} dab_parameters;
+DAB_API int dab_get_dab_parameters(int transmission_mode, dab_parameters* out); /* get_dab_parameters, dab_parameters.h:26-93 */
+
+/* the fields of Subchannel (src/dab/database/dab_database_entities.h:179-190) the decoder reads */
+typedef struct {
+    int32_t id;
+    int32_t start_address;   /* capacity units (64 soft bits) from the start of the CIF */
+    int32_t length;          /* capacity units */
+    int32_t is_uep;
+    int32_t uep_prot_index;  /* row of UEP_PROTECTION_TABLE, 0..63 */
+    int32_t eep_prot_level;  /* 0..3 = level 1..4 */
+    int32_t eep_type_b;      /* 0 = EEP_Type::TYPE_A, 1 = TYPE_B */
+    int32_t reserved;
+} dab_subchannel;
+
+#define DAB_ENSEMBLE_MAX_SUBCHANNELS 64
+typedef struct {
+    int n_streams;
+    int device;
+    int max_subchannels;  /* per stream, 0 => 64 */
+} dab_ensemble_options;
+
+typedef struct dab_ensemble dab_ensemble;
+DAB_API dab_ensemble* dab_ensemble_create(const dab_parameters* params, const dab_ensemble_options* options, int* status);
+DAB_API void dab_ensemble_destroy(dab_ensemble* h);
+DAB_API int dab_ensemble_set_cuda_stream(dab_ensemble* h, void* cuda_stream);
+/* The sub-channel set of one stream (stream = -1: every stream), i.e. which MSC_Decoder objects exist
+ * (basic_radio.cpp:100-153).  A sub-channel whose descriptor is unchanged keeps its de-interleaver history, a new one starts
+ * empty and yields no bytes until 16 CIFs have been consumed (cif_deinterleaver.cpp:40-43). */
+DAB_API int dab_ensemble_set_subchannels(dab_ensemble* h, int stream, const dab_subchannel* subs, int n_subs);
+/* MSC_Decoder's update() schedule for a sub-channel as a dab_vit_schedule (msc_decoder.cpp:88-99,136-146); n_soft receives
+ * length * 64.  A segment that would underrun is dropped exactly as the reference's release build does
+ * (dab_viterbi_decoder.cpp:158-162). */
+DAB_API int dab_ensemble_subchannel_schedule(const dab_subchannel* sub, dab_vit_schedule* out, uint32_t* n_soft);
+
+/* One OFDM frame (nb_frame_bits soft bits: FIC then MSC) per stream, already on the device: stream s's frame starts at
+ * d_bits + s * stream_stride.  d_frames_in_call (optional, dab_ofdm_device_bits) selects the streams that have a frame:
+ * stream s is decoded iff d_frames_in_call == NULL or d_frames_in_call[s] > slot.  Asynchronous on the handle's stream. */
+DAB_API int dab_ensemble_decode_frames_device(dab_ensemble* h, const int8_t* d_bits, size_t stream_stride,
+                                              const int32_t* d_frames_in_call, int slot);
+/* The same from host memory: bits[n_streams][nb_frame_bits]; present[n_streams] (optional) = 0 skips a stream. */
+DAB_API int dab_ensemble_decode_frames(dab_ensemble* h, const int8_t* bits, const uint8_t* present);
+
+/* Device-resident results of the most recent decode call (valid until the next one):
+ *   fib_bytes [n_streams][nb_cifs][nb_fib_cif_bits/24]   descrambled FIB groups (FIC_Decoder::m_decoded_bytes)
+ *   fib_valid [n_streams][nb_cifs][nb_fibs_per_cif]      1 = CRC16 matches (the FIB would be passed to OnFIB)
+ *   fic_error [n_streams][nb_cifs]                       Viterbi path error
+ *   msc_bytes [n_streams][nb_cifs][nb_cif_bits/8]        sub-channel k's bytes start at start_address * 8
+ *   msc_nbytes[n_streams][nb_cifs][max_subchannels]      decoded bytes (0 while the de-interleaver fills, -1 = overflows the CIF)
+ *   msc_error [n_streams][nb_cifs][max_subchannels]
+ *   decoded   [n_streams]                                1 = the stream had a frame in this call */
+typedef struct {
+    const uint8_t* fib_bytes;
+    const uint8_t* fib_valid;
+    const uint64_t* fic_error;
+    const uint8_t* msc_bytes;
+    const int32_t* msc_nbytes;
+    const uint64_t* msc_error;
+    const int32_t* decoded;
+    size_t fib_group_bytes, msc_cif_bytes;
+    int nb_cifs, nb_fibs_per_cif, max_subchannels;
+} dab_ensemble_results;
+DAB_API int dab_ensemble_device_results(dab_ensemble* h, dab_ensemble_results* out);
+/* host copies (synchronise, then copy): FIC of one stream / one sub-channel of one CIF */
+DAB_API int dab_ensemble_read_fic(dab_ensemble* h, int stream, uint8_t* fib_bytes, uint8_t* fib_valid, uint64_t* path_error);
+DAB_API int dab_ensemble_read_msc(dab_ensemble* h, int stream, int cif, int sub_index, uint8_t* out, size_t capacity,
+                                  int32_t* n_bytes, uint64_t* path_error);
+DAB_API int dab_ensemble_sync(dab_ensemble* h);
+DAB_API uint64_t dab_ensemble_kernel_launches(const dab_ensemble* h);
+/* trellises decoded / trellis steps run by the most recent decode call (host-side count from the sub-channel tables; upper
+ * bound when d_frames_in_call masks streams) */
+DAB_API int dab_ensemble_last_work(const dab_ensemble* h, uint64_t* trellises, uint64_t* trellis_steps);
 
 #ifdef __cplusplus
 }

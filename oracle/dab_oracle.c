@@ -872,6 +872,164 @@ size_t orc_puncture(const int8_t* mother, size_t n_mother, const uint8_t* seg_co
     return io;
 }
 
+/* ------------------------------------------------------------------------------------------------ FIC / MSC decode
+ * what sits between the OFDM soft bits and the decoded bytes, either side of the Viterbi decoder. */
+
+/* src/dab/algorithms/additive_scrambler.h:10-35: G(x) = 1 + x^-5 + x^-9, register reloaded with the syncword on Reset() */
+void orc_scrambler_bytes(uint16_t syncword, uint8_t* out, size_t n) {
+    uint16_t reg = syncword;
+    for (size_t k = 0; k < n; k++) {
+        uint8_t b = 0;
+        for (int i = 0; i < 8; i++) {
+            const uint8_t v = (uint8_t)(((reg >> 8) ^ (reg >> 4)) & 1u);
+            b |= (uint8_t)(v << (7 - i));
+            reg = (uint16_t)((reg << 1) | v);
+        }
+        out[k] = b;
+    }
+}
+
+/* src/dab/algorithms/crc.h:24-33 with the FIB parameters of fic_decoder.cpp:20-33: poly 0x1021, init 0xFFFF, final xor 0xFFFF */
+uint16_t orc_crc16_fib(const uint8_t* x, size_t n) {
+    uint16_t crc = 0xFFFF;
+    for (size_t i = 0; i < n; i++) {
+        crc ^= (uint16_t)((uint16_t)x[i] << 8);
+        for (int j = 0; j < 8; j++) crc = (uint16_t)((crc & 0x8000u) ? (((unsigned)crc << 1) ^ 0x1021u) : ((unsigned)crc << 1));
+    }
+    return (uint16_t)(crc ^ 0xFFFFu);
+}
+
+/* src/dab/fic/fic_decoder.cpp:53-116.  bits: nb_encoded_bits soft bits of one FIB group; out: nb_encoded_bits/24 descrambled
+ * bytes; valid[nb_fibs]: CRC16 match per FIB.  Returns the Viterbi path error, or UINT64_MAX when the group size is not the
+ * Mode I size the reference accepts (:70-75; nothing is decoded then). */
+uint64_t orc_fic_decode_group(orc_viterbi* v, const int8_t* bits, size_t nb_encoded_bits, size_t nb_fibs, uint8_t* out, uint8_t* valid) {
+    const size_t nb_decoded_bits = nb_encoded_bits / 3, nb_decoded_bytes = nb_encoded_bits / 24;
+    for (size_t i = 0; i < nb_fibs; i++) valid[i] = 0;
+    if (nb_decoded_bits != (128u * 21u + 128u * 3u + 24u) / 4u - 6u) return UINT64_MAX;
+    if (orc_vit_get_traceback_length(v) != nb_decoded_bits) orc_vit_set_traceback_length(v, nb_decoded_bits);
+    orc_vit_reset(v, 0);
+    size_t used = 0;
+    used += orc_vit_update(v, bits + used, nb_encoded_bits - used, orc_puncture_code(16), 8, 128 * 21);
+    used += orc_vit_update(v, bits + used, nb_encoded_bits - used, orc_puncture_code(15), 8, 128 * 3);
+    used += orc_vit_update(v, bits + used, nb_encoded_bits - used, PI_TAIL, 6, 24);
+    const uint64_t err = orc_vit_chainback(v, out, nb_decoded_bytes, 0);
+    uint8_t prbs[1024];
+    orc_scrambler_bytes(0xFFFF, prbs, nb_decoded_bytes);
+    for (size_t i = 0; i < nb_decoded_bytes; i++) out[i] ^= prbs[i];
+    const size_t fib_bytes = nb_decoded_bytes / nb_fibs;
+    for (size_t i = 0; i < nb_fibs; i++) {
+        const uint8_t* fib = out + i * fib_bytes;
+        const uint16_t rx = (uint16_t)((fib[fib_bytes - 2] << 8) | fib[fib_bytes - 1]);
+        valid[i] = (uint8_t)(rx == orc_crc16_fib(fib, fib_bytes - 2));
+    }
+    return err;
+}
+
+/* src/dab/msc/cif_deinterleaver.cpp:9-70 */
+static const int CIF_OFFSETS[16] = { 0, 8, 4, 12, 2, 10, 6, 14, 1, 9, 5, 13, 3, 11, 7, 15 };
+struct orc_deint { int8_t* ring; size_t nb_bits; int curr; int stored; };
+orc_deint* orc_deint_create(size_t nb_bits) {
+    orc_deint* d = (orc_deint*)calloc(1, sizeof(orc_deint));
+    d->ring = (int8_t*)calloc(nb_bits * 16u, 1);
+    d->nb_bits = nb_bits;
+    return d;
+}
+void orc_deint_destroy(orc_deint* d) { if (d) { free(d->ring); free(d); } }
+int orc_deint_push(orc_deint* d, const int8_t* bits, int8_t* out) {
+    memcpy(d->ring + d->nb_bits * (size_t)d->curr, bits, d->nb_bits);    /* Consume :21-35 */
+    d->curr = (d->curr + 1) % 16;
+    if (d->stored < 16) d->stored++;
+    if (d->stored < 16) return 0;                                        /* Deinterleave :37-70 */
+    for (size_t i = 0; i < d->nb_bits; i++) {
+        const int age = 15 - CIF_OFFSETS[i % 16];                        /* BUFFER_LOOKUP index: 0 = newest */
+        const int row = ((d->curr - 1) - age + 32) % 16;
+        out[i] = d->ring[d->nb_bits * (size_t)row + i];
+    }
+    return 1;
+}
+
+/* src/dab/constants/subchannel_protection_tables.h:21-86 (UEP rows: Lx[4], PIx[4]; the two 128 kbit/s rows are kept in the
+ * reference's order), :121-140 (EEP A/B as Lx = m*n + b), :145-154 (2-A special when the sub-channel has 8 CU) */
+static const uint8_t UEP_TABLE[64][8] = {
+    {3,4,17,0, 5,3,2,0}, {3,3,18,0, 11,6,5,0}, {3,4,14,3, 15,9,6,8}, {3,4,14,3, 22,13,8,13}, {3,5,13,3, 24,17,12,17},
+    {4,3,26,3, 5,4,2,3}, {3,4,26,3, 9,6,4,6}, {3,4,26,3, 15,10,6,9}, {3,4,26,3, 24,14,8,15}, {3,5,25,3, 24,18,13,18},
+    {6,10,23,3, 5,4,2,3}, {6,10,23,3, 9,6,4,5}, {6,12,21,3, 16,7,6,9}, {6,10,23,3, 23,13,8,13},
+    {6,9,31,2, 5,3,2,3}, {6,9,33,0, 11,6,5,0}, {6,12,27,3, 16,8,6,9}, {6,10,29,3, 23,13,8,13}, {6,11,28,3, 24,18,12,18},
+    {6,10,41,3, 6,3,2,3}, {6,10,41,3, 11,6,5,6}, {6,11,40,3, 16,8,6,7}, {6,10,41,3, 23,13,8,13}, {6,10,41,3, 24,17,12,18},
+    {7,9,53,3, 5,4,2,4}, {7,10,52,3, 9,6,4,6}, {6,12,51,3, 16,9,6,10}, {6,10,53,3, 22,12,9,12}, {6,13,50,3, 24,18,13,19},
+    {14,17,50,3, 5,4,2,5}, {11,21,49,3, 9,6,4,8}, {11,23,47,3, 16,8,6,9}, {11,21,49,3, 23,12,9,14},
+    {12,19,62,3, 5,3,2,4}, {11,21,61,3, 11,6,5,7}, {11,22,60,3, 16,9,6,10}, {11,21,61,3, 22,12,9,14}, {11,20,62,3, 24,17,13,19},
+    {11,19,87,3, 5,4,2,4}, {11,23,83,3, 11,6,5,9}, {11,24,82,3, 16,8,6,11}, {11,21,85,3, 22,11,9,13}, {11,22,84,3, 24,18,12,19},
+    {11,20,110,3, 6,4,2,5}, {11,22,108,3, 10,6,4,9}, {11,24,106,3, 16,10,6,11}, {11,20,110,3, 22,13,9,13}, {11,21,109,3, 24,20,13,24},
+    {12,22,131,3, 8,6,2,6}, {12,26,127,3, 12,8,4,11}, {11,20,134,3, 16,10,7,9}, {11,22,132,3, 24,16,10,15}, {11,24,130,3, 24,20,12,20},
+    {11,24,154,3, 6,5,2,5}, {11,24,154,3, 12,9,5,10}, {11,27,151,3, 16,10,7,10}, {11,22,156,3, 24,14,10,13}, {11,26,152,3, 24,19,14,18},
+    {11,26,200,3, 8,5,2,6}, {11,25,201,3, 13,9,5,10}, {11,26,200,3, 24,17,9,17},
+    {11,27,247,3, 8,6,2,7}, {11,24,250,3, 16,9,7,10}, {12,28,245,3, 24,20,14,23},
+};
+static const uint16_t UEP_SIZE[64] = {
+    16,21,24,29,35, 24,29,35,42,52, 29,35,42,52, 32,42,48,58,70, 40,52,58,70,84, 48,58,70,84,104, 58,70,84,104,
+    84,64,96,116,140, 80,104,116,140,168, 96,116,140,168,208, 116,140,168,208,232, 128,168,192,232,280, 160,208,280, 192,280,416,
+};
+int orc_uep_subchannel_size(int index) { return (index >= 0 && index < 64) ? (int)UEP_SIZE[index] : -1; }
+typedef struct { int cu_multiple; int m[2], b[2]; int pi[2]; } eep_desc;
+static const eep_desc EEP_A[4] = { {12, {6, 0}, {-3, 3}, {24, 23}}, {8, {2, 4}, {-3, 3}, {14, 13}}, {6, {6, 0}, {-3, 3}, {8, 7}}, {4, {4, 2}, {-3, 3}, {3, 2}} };
+static const eep_desc EEP_2A_SPECIAL = {8, {0, 0}, {5, 1}, {13, 12}};
+static const eep_desc EEP_B[4] = { {27, {24, 0}, {-3, 3}, {10, 9}}, {21, {24, 0}, {-3, 3}, {6, 5}}, {18, {24, 0}, {-3, 3}, {4, 3}}, {15, {24, 0}, {-3, 3}, {2, 1}} };
+
+/* The update() sequence of MSC_Decoder::DecodeEEP / DecodeUEP (msc_decoder.cpp:88-99, 136-146) for one sub-channel, as
+ * (puncture index, requested output symbols) pairs; the PI_X tail (24 symbols) is pi = 0.  Returns the number of entries. */
+int orc_msc_segments(const orc_subchannel* sc, int pi_out[5], uint32_t n_out[5]) {
+    int k = 0;
+    if (!sc->is_uep) {
+        const eep_desc* d = sc->eep_type_b ? &EEP_B[sc->eep_prot_level & 3] : (sc->length == 8 ? &EEP_2A_SPECIAL : &EEP_A[sc->eep_prot_level & 3]);
+        const int n = sc->length / d->cu_multiple;
+        for (int i = 0; i < 2; i++) { pi_out[k] = d->pi[i]; n_out[k] = (uint32_t)(128 * (d->m[i] * n + d->b[i])); k++; }
+    } else {
+        const uint8_t* row = UEP_TABLE[sc->uep_prot_index & 63];
+        for (int i = 0; i < 4; i++) { pi_out[k] = row[4 + i]; n_out[k] = 128u * row[i]; k++; }
+    }
+    pi_out[k] = 0; n_out[k] = 24; k++;
+    return k;
+}
+
+/* src/dab/msc/msc_decoder.cpp:27-170 */
+struct orc_msc { orc_subchannel sc; size_t nb_bits; orc_deint* deint; orc_viterbi* vit; int8_t* enc; uint8_t* dec; uint8_t* prbs; };
+orc_msc* orc_msc_create(const orc_subchannel* sc) {
+    orc_msc* m = (orc_msc*)calloc(1, sizeof(orc_msc));
+    m->sc = *sc;
+    m->nb_bits = (size_t)sc->length * 64u;
+    m->deint = orc_deint_create(m->nb_bits);
+    m->vit = orc_vit_create();
+    orc_vit_set_traceback_length(m->vit, m->nb_bits);      /* :38 */
+    m->enc = (int8_t*)calloc(m->nb_bits + 1, 1);
+    m->dec = (uint8_t*)calloc(m->nb_bits / 8u + 1, 1);
+    m->prbs = (uint8_t*)calloc(m->nb_bits / 8u + 1, 1);
+    orc_scrambler_bytes(0xFFFF, m->prbs, m->nb_bits / 8u);
+    return m;
+}
+void orc_msc_destroy(orc_msc* m) { if (m) { orc_deint_destroy(m->deint); orc_vit_destroy(m->vit); free(m->enc); free(m->dec); free(m->prbs); free(m); } }
+/* DecodeCIF: returns the number of bytes written to out (0 while the de-interleaver fills, -1 when the sub-channel overflows
+ * the CIF, :49-54); *path_error receives the Viterbi error when bytes were produced */
+int64_t orc_msc_decode_cif(orc_msc* m, const int8_t* cif_bits, size_t n_bits, uint8_t* out, uint64_t* path_error) {
+    const size_t start_bit = (size_t)m->sc.start_address * 64u;
+    if (start_bit + m->nb_bits > n_bits) return -1;
+    if (!orc_deint_push(m->deint, cif_bits + start_bit, m->enc)) return 0;
+    int pi[5]; uint32_t n_out[5];
+    const int n_seg = orc_msc_segments(&m->sc, pi, n_out);
+    orc_vit_reset(m->vit, 0);
+    size_t used = 0;
+    for (int i = 0; i < n_seg; i++) {
+        const uint8_t* code = pi[i] ? orc_puncture_code(pi[i]) : PI_TAIL;
+        used += orc_vit_update(m->vit, m->enc + used, m->nb_bits - used, code, pi[i] ? 8 : 6, n_out[i]);
+    }
+    const size_t decoded_bits = orc_vit_get_current_decoded_bit(m->vit) - 6u;   /* :105-108 (24 tail symbols / code rate 4) */
+    const size_t nbytes = decoded_bits / 8u;
+    const uint64_t err = orc_vit_chainback(m->vit, m->dec, nbytes, 0);
+    if (path_error) *path_error = err;
+    for (size_t i = 0; i < nbytes; i++) out[i] = (uint8_t)(m->dec[i] ^ m->prbs[i]);   /* :112-117 */
+    return (int64_t)nbytes;
+}
+
 /* ------------------------------------------------------------------------------------------------ CPU baselines */
 
 static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }

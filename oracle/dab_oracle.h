@@ -119,6 +119,27 @@ const uint8_t* orc_puncture_code_tail(void); /* PI_X, 6 entries */
 size_t orc_conv_encode(const uint8_t* bytes, size_t nbytes, int8_t* soft_out /* (8*nbytes+6)*4 */);
 size_t orc_puncture(const int8_t* mother, size_t n_mother, const uint8_t* seg_codes, const uint32_t* seg_code_len, const uint32_t* seg_n_out,
                     uint32_t n_seg, int8_t* out);
+/* FIC / MSC decode around the Viterbi decoder:
+ * additive_scrambler.h:10-35, crc.h:24-33 + fic_decoder.cpp:20-33, fic_decoder.cpp:53-116, cif_deinterleaver.cpp:9-70,
+ * subchannel_protection_tables.h:21-154, msc_decoder.cpp:27-170 */
+void orc_scrambler_bytes(uint16_t syncword, uint8_t* out, size_t n);
+uint16_t orc_crc16_fib(const uint8_t* x, size_t n);
+uint64_t orc_fic_decode_group(orc_viterbi* v, const int8_t* bits, size_t nb_encoded_bits, size_t nb_fibs, uint8_t* out, uint8_t* valid);
+typedef struct orc_deint orc_deint;
+orc_deint* orc_deint_create(size_t nb_bits);
+void orc_deint_destroy(orc_deint* d);
+int orc_deint_push(orc_deint* d, const int8_t* bits, int8_t* out); /* Consume + Deinterleave; 1 when out was written */
+/* Subchannel (src/dab/database/dab_database_entities.h:179-190), the fields the decoder reads */
+typedef struct {
+    int32_t start_address, length, is_uep, uep_prot_index, eep_prot_level, eep_type_b;
+} orc_subchannel;
+int orc_uep_subchannel_size(int index);
+int orc_msc_segments(const orc_subchannel* sc, int pi_out[5], uint32_t n_out[5]);
+typedef struct orc_msc orc_msc;
+orc_msc* orc_msc_create(const orc_subchannel* sc);
+void orc_msc_destroy(orc_msc* m);
+int64_t orc_msc_decode_cif(orc_msc* m, const int8_t* cif_bits, size_t n_bits, uint8_t* out, uint64_t* path_error);
+
 /* CPU baselines for bench.py (port kind): wall seconds */
 double orc_ofdm_bench(int mode, int n_threads, const orc_c32* iq, size_t n, size_t block, int repeats, uint64_t* frames_out);
 double orc_vit_bench(int n_threads, const int8_t* soft, size_t soft_per_job, size_t n_jobs, const uint8_t* seg_codes,

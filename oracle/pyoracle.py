@@ -46,6 +46,11 @@ class OfdmState(C.Structure):
     ]
 
 
+class Subchannel(C.Structure):
+    """Subchannel (src/dab/database/dab_database_entities.h:179-190), the fields the MSC decoder reads."""
+    _fields_ = [(k, C.c_int32) for k in ("start_address", "length", "is_uep", "uep_prot_index", "eep_prot_level", "eep_type_b")]
+
+
 class C32(C.Structure):
     _fields_ = [("re", C.c_float), ("im", C.c_float)]
 
@@ -115,6 +120,22 @@ def lib():
     L.orc_conv_encode.restype = sz
     L.orc_puncture.argtypes = [vp, sz, vp, vp, vp, u32, vp]
     L.orc_puncture.restype = sz
+    L.orc_scrambler_bytes.argtypes = [C.c_uint16, vp, sz]
+    L.orc_crc16_fib.argtypes = [vp, sz]
+    L.orc_crc16_fib.restype = C.c_uint16
+    L.orc_fic_decode_group.argtypes = [vp, vp, sz, sz, vp, vp]
+    L.orc_fic_decode_group.restype = C.c_uint64
+    L.orc_deint_create.argtypes = [sz]
+    L.orc_deint_create.restype = vp
+    L.orc_deint_destroy.argtypes = [vp]
+    L.orc_deint_push.argtypes = [vp, vp, vp]
+    L.orc_uep_subchannel_size.argtypes = [i32]
+    L.orc_msc_segments.argtypes = [C.POINTER(Subchannel), vp, vp]
+    L.orc_msc_create.argtypes = [C.POINTER(Subchannel)]
+    L.orc_msc_create.restype = vp
+    L.orc_msc_destroy.argtypes = [vp]
+    L.orc_msc_decode_cif.argtypes = [vp, vp, sz, vp, C.POINTER(C.c_uint64)]
+    L.orc_msc_decode_cif.restype = C.c_int64
     L.orc_ofdm_bench.argtypes = [i32, i32, vp, sz, sz, i32, C.POINTER(C.c_uint64)]
     L.orc_ofdm_bench.restype = C.c_double
     L.orc_vit_bench.argtypes = [i32, vp, sz, sz, vp, vp, vp, u32, sz, vp, sz]
@@ -347,5 +368,93 @@ class OracleViterbi:
     def __del__(self):
         try:
             self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------- FIC / MSC decode
+def scrambler_bytes(n, syncword=0xFFFF):
+    out = np.zeros(n, np.uint8)
+    lib().orc_scrambler_bytes(syncword, _p(out), n)
+    return out
+
+
+def crc16_fib(data):
+    data = np.ascontiguousarray(data, np.uint8)
+    return int(lib().orc_crc16_fib(_p(data), data.size))
+
+
+def subchannel(start_address, length, is_uep=False, uep_prot_index=0, eep_prot_level=0, eep_type_b=False):
+    return Subchannel(int(start_address), int(length), int(bool(is_uep)), int(uep_prot_index), int(eep_prot_level), int(bool(eep_type_b)))
+
+
+def uep_subchannel_size(index):
+    return int(lib().orc_uep_subchannel_size(index))
+
+
+def msc_segments(sc):
+    """The update() schedule of MSC_Decoder for a sub-channel as [(puncture code, n_out)], tail included."""
+    pi = np.zeros(5, np.int32)
+    n_out = np.zeros(5, np.uint32)
+    n = lib().orc_msc_segments(C.byref(sc), _p(pi), _p(n_out))
+    return [(puncture_code(int(pi[i])) if pi[i] else PI_X, int(n_out[i])) for i in range(n)]
+
+
+def fic_decode_group(bits, nb_fibs=3):
+    """FIC_Decoder::DecodeFIBGroup -> (descrambled bytes, crc-valid flags, path error or None when the size is rejected)."""
+    bits = np.ascontiguousarray(bits, np.int8)
+    v = OracleViterbi()
+    out = np.zeros(bits.size // 24, np.uint8)
+    valid = np.zeros(nb_fibs, np.uint8)
+    err = int(lib().orc_fic_decode_group(v.h, _p(bits), bits.size, nb_fibs, _p(out), _p(valid)))
+    v.close()
+    return out, valid, (None if err == 0xFFFFFFFFFFFFFFFF else err)
+
+
+class OracleDeinterleaver:
+    def __init__(self, nb_bits):
+        self.L = lib()
+        self.n = nb_bits
+        self.h = self.L.orc_deint_create(nb_bits)
+
+    def push(self, bits):
+        bits = np.ascontiguousarray(bits, np.int8)
+        assert bits.size == self.n
+        out = np.zeros(self.n, np.int8)
+        ok = self.L.orc_deint_push(self.h, _p(bits), _p(out))
+        return out if ok else None
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.orc_deint_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class OracleMscDecoder:
+    """MSC_Decoder for one sub-channel (msc_decoder.cpp:27-170)."""
+
+    def __init__(self, sc):
+        self.L = lib()
+        self.sc = sc
+        self.h = self.L.orc_msc_create(C.byref(sc))
+
+    def decode_cif(self, cif_bits):
+        """-> (bytes ndarray (empty while the de-interleaver fills), path error or None)."""
+        cif_bits = np.ascontiguousarray(cif_bits, np.int8)
+        out = np.zeros(self.sc.length * 8 + 8, np.uint8)
+        err = C.c_uint64(0)
+        n = int(self.L.orc_msc_decode_cif(self.h, _p(cif_bits), cif_bits.size, _p(out), C.byref(err)))
+        if n <= 0:
+            return np.zeros(0, np.uint8), None
+        return out[:n].copy(), int(err.value)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.orc_msc_destroy(self.h)
+                self.h = None
         except Exception:
             pass

@@ -117,6 +117,20 @@ def _bind(L):
     L.ref_vit_bench.argtypes = [i32, vp, u64, u64, vp, vp, vp, C.c_uint32, u64, vp, u64]
     L.ref_vit_bench.restype = C.c_double
     L.ref_build_info.restype = C.c_char_p
+    L.ref_fic_create.argtypes = [u64, u64]
+    L.ref_fic_create.restype = vp
+    L.ref_fic_destroy.argtypes = [vp]
+    L.ref_fic_decode_group.argtypes = [vp, vp, u64, u64, vp, vp]
+    L.ref_msc_create.argtypes = [i32] * 6
+    L.ref_msc_create.restype = vp
+    L.ref_msc_destroy.argtypes = [vp]
+    L.ref_msc_decode_cif.argtypes = [vp, vp, u64, vp, u64]
+    L.ref_msc_decode_cif.restype = C.c_int64
+    L.ref_deint_create.argtypes = [i32]
+    L.ref_deint_create.restype = vp
+    L.ref_deint_destroy.argtypes = [vp]
+    L.ref_deint_push.argtypes = [vp, vp, vp, u64]
+    L.ref_scrambler_bytes.argtypes = [C.c_uint16, vp, u64]
     return L
 
 
@@ -281,3 +295,81 @@ class RefOfdmPool:
         if self.h:
             self.L.ref_ofdm_pool_destroy(self.h)
             self.h = None
+
+
+# ---------------------------------------------------------------------------------------------- FIC / MSC decoders
+def scrambler_bytes(n, syncword=0xFFFF):
+    out = np.zeros(n, np.uint8)
+    lib().ref_scrambler_bytes(syncword, _p(out), n)
+    return out
+
+
+class RefFicDecoder:
+    """The reference FIC_Decoder (src/dab/fic/fic_decoder.cpp:53-116)."""
+
+    def __init__(self, nb_encoded_bits=2304, nb_fibs=3):
+        self.L = lib()
+        self.n, self.fibs = nb_encoded_bits, nb_fibs
+        self.h = self.L.ref_fic_create(nb_encoded_bits, nb_fibs)
+
+    def decode_group(self, bits, cif_index=0):
+        bits = np.ascontiguousarray(bits, np.int8)
+        out = np.zeros(self.n // 24, np.uint8)
+        valid = np.zeros(self.fibs, np.uint8)
+        self.L.ref_fic_decode_group(self.h, _p(bits), bits.size, cif_index, _p(out), _p(valid))
+        return out, valid
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.ref_fic_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class RefDeinterleaver:
+    """The reference CIF_Deinterleaver (src/dab/msc/cif_deinterleaver.cpp:21-70)."""
+
+    def __init__(self, nb_bits):
+        self.L = lib()
+        self.n = nb_bits
+        self.h = self.L.ref_deint_create(nb_bits // 8)
+
+    def push(self, bits):
+        bits = np.ascontiguousarray(bits, np.int8)
+        out = np.zeros(self.n, np.int8)
+        ok = self.L.ref_deint_push(self.h, _p(bits), _p(out), self.n)
+        return out if ok else None
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.ref_deint_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class RefMscDecoder:
+    """The reference MSC_Decoder (src/dab/msc/msc_decoder.cpp:27-170) for one sub-channel."""
+
+    def __init__(self, start_address, length, is_uep=False, uep_prot_index=0, eep_prot_level=0, eep_type_b=False):
+        self.L = lib()
+        self.length = length
+        self.h = self.L.ref_msc_create(int(start_address), int(length), int(bool(is_uep)), int(uep_prot_index), int(eep_prot_level),
+                                       int(bool(eep_type_b)))
+
+    def decode_cif(self, cif_bits):
+        cif_bits = np.ascontiguousarray(cif_bits, np.int8)
+        out = np.zeros(self.length * 8 + 8, np.uint8)
+        n = int(self.L.ref_msc_decode_cif(self.h, _p(cif_bits), cif_bits.size, _p(out), out.size))
+        return out[:max(n, 0)].copy()
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.ref_msc_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass

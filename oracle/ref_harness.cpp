@@ -10,6 +10,8 @@
 //   tables                    src/ofdm/dab_ofdm_params_ref.cpp:10, dab_prs_ref.cpp:140, dab_mapper_ref.cpp:10
 //   dsp                       src/ofdm/dsp/apply_pll.cpp:121, complex_conj_mul_sum.cpp:104
 //   DAB_Viterbi_Decoder       src/dab/algorithms/dab_viterbi_decoder.h:12-45
+//   FIC_Decoder               src/dab/fic/fic_decoder.h:17-40, fic_decoder.cpp:53-116
+//   MSC_Decoder               src/dab/msc/msc_decoder.h:18-43, msc_decoder.cpp:46-170 (with CIF_Deinterleaver, AdditiveScrambler)
 //
 // Determinism ("real-time order"): the reference's Process() lets the reader thread
 // race the pipeline/coordinator threads on m_freq_fine_offset / m_freq_coarse_offset.  In real-time operation
@@ -46,6 +48,13 @@
 #include "ofdm/ofdm_helpers.h"
 #include "ofdm/ofdm_modulator.h"
 #include "dab/algorithms/dab_viterbi_decoder.h"
+#define private public
+#include "dab/fic/fic_decoder.h"
+#undef private
+#include "dab/msc/msc_decoder.h"
+#include "dab/msc/cif_deinterleaver.h"
+#include "dab/algorithms/additive_scrambler.h"
+#include "dab/database/dab_database_entities.h"
 
 extern "C" {
 
@@ -435,6 +444,71 @@ double ref_vit_bench(int n_threads, const int8_t* soft, uint64_t soft_per_job, u
     for (auto& w : workers) w.join();
     const auto t1 = std::chrono::steady_clock::now();
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---------------------------------------------------------------- FIC / MSC decoders
+// FIC_Decoder::DecodeFIBGroup: `out` receives the descrambled group (m_decoded_bytes, nb_encoded_bits / 24 bytes) whether or not
+// the CRCs match; valid[i] = 1 when FIB i was passed to OnFIB.  Returns the number of valid FIBs.
+struct FicCtx {
+    std::unique_ptr<FIC_Decoder> dec;
+    size_t nb_fibs = 0;
+    std::vector<uint8_t> valid;
+    std::vector<const uint8_t*> seen;
+};
+void* ref_fic_create(uint64_t nb_encoded_bits, uint64_t nb_fibs_per_group) {
+    auto* c = new FicCtx();
+    c->dec = std::make_unique<FIC_Decoder>(size_t(nb_encoded_bits), size_t(nb_fibs_per_group));
+    c->nb_fibs = size_t(nb_fibs_per_group);
+    c->dec->OnFIB().Attach([c](tcb::span<const uint8_t> buf) { c->seen.push_back(buf.data()); });
+    return c;
+}
+void ref_fic_destroy(void* h) { delete static_cast<FicCtx*>(h); }
+int ref_fic_decode_group(void* h, const int8_t* bits, uint64_t n_bits, uint64_t cif_index, uint8_t* out, uint8_t* valid) {
+    auto* c = static_cast<FicCtx*>(h);
+    c->seen.clear();
+    std::fill(c->dec->m_decoded_bytes.begin(), c->dec->m_decoded_bytes.end(), uint8_t(0));
+    c->dec->DecodeFIBGroup({bits, size_t(n_bits)}, size_t(cif_index));
+    const auto& bytes = c->dec->m_decoded_bytes;
+    std::memcpy(out, bytes.data(), bytes.size());
+    const size_t fib_bytes = bytes.size() / c->nb_fibs;
+    for (size_t i = 0; i < c->nb_fibs; i++) valid[i] = 0;
+    for (const uint8_t* p : c->seen) valid[size_t(p - bytes.data()) / fib_bytes] = 1;
+    return int(c->seen.size());
+}
+
+// MSC_Decoder for one sub-channel; DecodeCIF returns the descrambled bytes (0 while the de-interleaver is still filling)
+void* ref_msc_create(int start_address, int length, int is_uep, int uep_prot_index, int eep_prot_level, int eep_type_b) {
+    Subchannel sc(0);
+    sc.start_address = subchannel_addr_t(start_address);
+    sc.length = subchannel_size_t(length);
+    sc.is_uep = is_uep != 0;
+    sc.uep_prot_index = uep_protection_index_t(uep_prot_index);
+    sc.eep_prot_level = eep_protection_level_t(eep_prot_level);
+    sc.eep_type = eep_type_b ? EEP_Type::TYPE_B : EEP_Type::TYPE_A;
+    sc.is_complete = true;
+    return new MSC_Decoder(sc);
+}
+void ref_msc_destroy(void* h) { delete static_cast<MSC_Decoder*>(h); }
+int64_t ref_msc_decode_cif(void* h, const int8_t* cif_bits, uint64_t n_bits, uint8_t* out, uint64_t out_capacity) {
+    auto res = static_cast<MSC_Decoder*>(h)->DecodeCIF({cif_bits, size_t(n_bits)});
+    if (res.size() > out_capacity) return -1;
+    std::memcpy(out, res.data(), res.size());
+    return int64_t(res.size());
+}
+// CIF_Deinterleaver alone (cif_deinterleaver.cpp:21-70): Consume then Deinterleave; returns 1 when output was produced
+void* ref_deint_create(int nb_bytes) { return new CIF_Deinterleaver(nb_bytes); }
+void ref_deint_destroy(void* h) { delete static_cast<CIF_Deinterleaver*>(h); }
+int ref_deint_push(void* h, const int8_t* bits, int8_t* out, uint64_t n_bits) {
+    auto* d = static_cast<CIF_Deinterleaver*>(h);
+    d->Consume({bits, size_t(n_bits)});
+    return d->Deinterleave({out, size_t(n_bits)}) ? 1 : 0;
+}
+// AdditiveScrambler with syncword 0xFFFF (additive_scrambler.h:10-35)
+void ref_scrambler_bytes(uint16_t syncword, uint8_t* out, uint64_t n) {
+    AdditiveScrambler s;
+    s.SetSyncword(syncword);
+    s.Reset();
+    for (uint64_t i = 0; i < n; i++) out[i] = s.Process();
 }
 
 const char* ref_build_info() {

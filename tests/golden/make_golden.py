@@ -126,7 +126,60 @@ def golden_ofdm():
         r.close()
 
 
+ENSEMBLE_SUBS = [
+    # start_address, length, is_uep, uep_prot_index, eep_prot_level, eep_type_b
+    (0, 12, 0, 0, 2, 0),     # EEP 3-A, n = 2
+    (12, 27, 0, 0, 0, 1),    # EEP 1-B, n = 1
+    (40, 16, 1, 0, 0, 0),    # UEP row 0 (32 kbit/s, level 5)
+    (56, 8, 0, 0, 1, 0),     # EEP 2-A with 8 CU: the special row
+    (64, 64, 1, 34, 0, 0),   # UEP row 34: the reference's table gives it 64 CU, its last segments underrun and are dropped
+    (128, 24, 0, 0, 3, 0),   # EEP 4-A, n = 6
+    (860, 8, 0, 0, 2, 0),    # overflows the CIF: never decoded (msc_decoder.cpp:49-54)
+]
+ENSEMBLE_USED_CU = 160
+
+
+def golden_ensemble():
+    """FIC_Decoder + MSC_Decoder (reference sources) over 6 consecutive Mode I frames of a noisy synthetic ensemble."""
+    import ensgen
+    subs = [po.subchannel(*a) for a in ENSEMBLE_SUBS]
+    tx = ensgen.EnsembleTx(1, subs[:-1], seed=321, sigma=75.0)
+    frames = [tx.next_frame(corrupt_fibs=[(1, 2), (3, 0)] if f == 2 else ()) for f in range(6)]
+    nb_cifs, nb_fic_bits, nb_fib_cif_bits, nb_fibs, nb_cif_bits = ensgen.MODE_GEOM[1]
+    used = ENSEMBLE_USED_CU * 64
+    fic = pyref.RefFicDecoder(nb_fib_cif_bits, nb_fibs)
+    mscs = [pyref.RefMscDecoder(*a) for a in ENSEMBLE_SUBS]
+    out = {"subs": np.array(ENSEMBLE_SUBS, np.int32), "used_bits": np.array([used])}
+    fib_bytes, fib_valid, msc_len, msc_bytes = [], [], [], []
+    for f, frame in enumerate(frames):
+        msc = frame[nb_fic_bits:].reshape(nb_cifs, nb_cif_bits)   # a view: the unused capacity units are blanked to keep the fixture small
+        msc[:, used:] = 0
+        out[f"frame{f}_fic"] = frame[:nb_fic_bits]
+        out[f"frame{f}_msc"] = np.ascontiguousarray(msc[:, :used])
+        for c in range(nb_cifs):
+            b, v = fic.decode_group(frame[c * nb_fib_cif_bits:(c + 1) * nb_fib_cif_bits], c)
+            fib_bytes.append(b)
+            fib_valid.append(v)
+            for m in mscs:
+                d = m.decode_cif(msc[c])
+                msc_len.append(d.size)
+                msc_bytes.append(d)
+    out["fib_bytes"] = np.array(fib_bytes, np.uint8).reshape(len(frames), nb_cifs, 96)
+    out["fib_valid"] = np.array(fib_valid, np.uint8).reshape(len(frames), nb_cifs, nb_fibs)
+    out["msc_len"] = np.array(msc_len, np.int32).reshape(len(frames), nb_cifs, len(mscs))
+    out["msc_bytes"] = np.concatenate(msc_bytes)
+    out["scrambler"] = pyref.scrambler_bytes(256)
+    np.savez_compressed(os.path.join(HERE, "ensemble.npz"), **out)
+    print("ensemble: valid FIBs", int(out["fib_valid"].sum()), "of", out["fib_valid"].size, "msc bytes", out["msc_bytes"].size,
+          "lens", out["msc_len"][-1, -1].tolist())
+
+
 if __name__ == "__main__":
+    only = sys.argv[1:]
+    if only == ["ensemble"]:
+        golden_ensemble()
+        sys.exit(0)
+    golden_ensemble()
     golden_tables()
     golden_dsp()
     golden_viterbi()
