@@ -37,6 +37,15 @@ FRAME_LEN = 196608                      # Mode I transmission frame, samples (96
 FRAME_BITS = 230400
 ALGO_BYTES_PER_FRAME = 196608 * 8 + 230400   # complex64 in + int8 out = 9.172 B/sample
 N_STREAMS = 1024
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line, on the real stdout (fd 1 is parked on stderr while the run is in progress)."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
 POOL_FRAMES = 12                        # distinct modulated frames the synthetic streams are drawn from
 
 
@@ -179,6 +188,12 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # NCCL prints its version banner on stdout when NCCL_DEBUG is set; stdout must carry the ONE JSON line only, so fd 1 is
+    # pointed at stderr until the result is printed (see emit()).
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -354,7 +369,7 @@ def run_ours(args):
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "viterbi": viterbi,
             "frames_per_stream_in_timed_region": frames_per_stream, "locked_streams": locked,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
