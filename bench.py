@@ -398,14 +398,13 @@ def viterbi_leg(torch, pkg, n_streams, reps, with_cpu):
     sid_fic = vb.add_schedule(vit.make_schedule(fic, 96))
     sid_eep = vb.add_schedule(vit.make_schedule(eep, 192))
     jobs = np.zeros(n_streams * len(layout), pkg.capi.VIT_JOB_DTYPE)
-    k = 0
-    for s in range(n_streams):
-        so, oo = s * frame_soft, s * frame_out
-        for segs, nbytes, nsoft in layout:
-            jobs[k] = (sid_fic if nbytes == 96 else sid_eep, nsoft, so, oo)
-            so += nsoft
-            oo += nbytes
-            k += 1
+    # job order: trellis slot major, stream minor -- the 32 trellises a warp of the bulk kernel runs in lock step share a
+    # schedule; jobs[slot * n_streams + s] is trellis `slot` of stream s (buffers stay [stream][slot])
+    so_slot = np.concatenate([[0], np.cumsum([ns for _, _, ns in layout])[:-1]])
+    oo_slot = np.concatenate([[0], np.cumsum([nb for _, nb, _ in layout])[:-1]])
+    for i, (segs, nbytes, nsoft) in enumerate(layout):
+        for s in range(n_streams):
+            jobs[i * n_streams + s] = (sid_fic if nbytes == 96 else sid_eep, nsoft, s * frame_soft + int(so_slot[i]), s * frame_out + int(oo_slot[i]))
     d_base = torch.from_numpy(base).cuda()
     g = torch.Generator(device="cuda")
     g.manual_seed(5)
@@ -433,7 +432,7 @@ def viterbi_leg(torch, pkg, n_streams, reps, with_cpu):
     assert int(d_st.abs().max().item()) == 0
     # stream 0 against the oracle: bit-exact bytes and path error for all 76 trellises
     out0 = d_out[:frame_out].cpu().numpy()
-    err0 = d_err[:len(layout)].cpu().numpy()
+    err0 = d_err.view(len(layout), n_streams)[:, 0].cpu().numpy()
     ov = po.OracleViterbi()
     so = oo = 0
     for i, (segs, nbytes, nsoft) in enumerate(layout):

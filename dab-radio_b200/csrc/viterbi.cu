@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "viterbi_core.cuh"
+#include "viterbi_lanes.cuh"
 
 namespace dabb200 {
 
@@ -30,6 +31,7 @@ struct PlainView {
     const int8_t* soft;
     uint8_t* out;
     __device__ __forceinline__ uint32_t fetch(uint32_t idx) const { return uint32_t(uint8_t(soft[idx])); }
+    __device__ __forceinline__ const int8_t* soft_base() const { return soft; }
     __device__ __forceinline__ void store(uint32_t byte, uint32_t value) { out[byte] = uint8_t(value); }
 };
 
@@ -76,6 +78,41 @@ viterbi_kernel(const int8_t* __restrict__ soft, size_t soft_bytes, const dab_vit
     }
 }
 
+// The bulk form: one trellis per thread (viterbi_lanes.cuh).  Thread i decodes job order[i] (order == nullptr: job i); the
+// host sorts `order` by schedule so that the 32 trellises of a warp walk the same puncturing schedule in lock step.
+__global__ void __launch_bounds__(VITL_THREADS)
+viterbi_lanes_kernel(const int8_t* __restrict__ soft, size_t soft_bytes, const dab_vit_job* __restrict__ jobs, int n_jobs,
+                     const int32_t* __restrict__ order, const DevSchedule* __restrict__ schedules, int n_schedules,
+                     uint8_t* __restrict__ out, size_t out_bytes, uint64_t* __restrict__ path_error, int32_t* __restrict__ job_status,
+                     uint2* __restrict__ scratch, uint32_t scratch_steps) {
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * VITL_THREADS + threadIdx.x;
+    const size_t warp_global = size_t(slot) >> 5;
+    int job_index = -1;
+    if (slot < n_jobs) job_index = order ? order[slot] : slot;
+    int status = DAB_OK;
+    dab_vit_job job{};
+    const DevSchedule* sch = schedules;
+    if (job_index >= 0) {
+        job = jobs[job_index];
+        if (job.schedule >= uint32_t(n_schedules)) status = DAB_ERR_INVALID;
+        else {
+            sch = schedules + job.schedule;
+            if (sch->soft_symbols > job.n_soft || job.soft_offset + sch->soft_symbols > soft_bytes) status = DAB_ERR_UNDERRUN;
+            else if (sch->n_out_bits + 6u > sch->total_steps) status = DAB_ERR_TRACEBACK;
+            else if (job.out_offset + sch->n_out_bits / 8u > out_bytes) status = DAB_ERR_CAPACITY;
+            else if (sch->total_steps > scratch_steps) status = DAB_ERR_CAPACITY;
+        }
+    }
+    const bool active = job_index >= 0 && status == DAB_OK;
+    PlainView view{soft + job.soft_offset, out + job.out_offset};
+    const uint64_t err = viterbi_lane_trellis(sch, view, scratch + warp_global * size_t(scratch_steps) * 32u, lane, active);
+    if (job_index >= 0) {
+        if (path_error) path_error[job_index] = active ? err : 0;
+        if (job_status) job_status[job_index] = status;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 
 struct Viterbi {
@@ -91,6 +128,8 @@ struct Viterbi {
     DeviceBuffer<uint64_t> d_error;
     DeviceBuffer<int32_t> d_status;
     DeviceBuffer<uint2> d_scratch;
+    DeviceBuffer<int32_t> d_order;
+    std::vector<int32_t> order;
     int max_smem_optin = 0;
     int oneshot_slot = -1;  // schedule slot reused by dab_viterbi_decode_one
     uint64_t launches = 0;
@@ -118,11 +157,50 @@ static uint32_t pick_window(const Viterbi* v, uint32_t max_steps, size_t* smem_b
     return window;
 }
 
-static int launch(Viterbi* v, const int8_t* d_soft, size_t soft_bytes, const dab_vit_job* d_jobs, int n_jobs, uint32_t max_steps,
-                  uint8_t* d_out, size_t out_bytes, uint64_t* d_error, int32_t* d_status) {
+// Batches of at least this many trellises run one trellis per thread (viterbi_lanes_kernel); smaller ones one per warp
+// (viterbi_kernel), which finishes a handful of trellises sooner.  DAB_B200_VITERBI_LANES=0/1 forces the choice.
+constexpr int VITL_MIN_JOBS = 4096;
+
+static bool use_lanes(int n_jobs) {
+    const char* e = getenv("DAB_B200_VITERBI_LANES");
+    if (e && *e) return atoi(e) != 0;
+    return n_jobs >= VITL_MIN_JOBS;
+}
+
+static int launch_lanes(Viterbi* v, const int8_t* d_soft, size_t soft_bytes, const dab_vit_job* d_jobs, const dab_vit_job* host_jobs,
+                        int n_jobs, uint32_t max_steps, uint8_t* d_out, size_t out_bytes, uint64_t* d_error, int32_t* d_status) {
+    const uint32_t scratch_steps = std::max(8u, (max_steps + 1u) & ~1u);
+    const size_t n_warps = (size_t(n_jobs) + 31) / 32;
+    DAB_CUDA_CHECK(v->d_scratch.reserve(n_warps * size_t(scratch_steps) * 32u));
+    const int32_t* d_order = nullptr;
+    if (host_jobs) {
+        // lanes of a warp should walk the same schedule: order the jobs by schedule (stable, so neighbours stay neighbours)
+        bool mixed = false;
+        for (int i = 1; i < n_jobs && !mixed; i++) mixed = host_jobs[i].schedule != host_jobs[0].schedule;
+        if (mixed) {
+            v->order.resize(size_t(n_jobs));
+            for (int i = 0; i < n_jobs; i++) v->order[size_t(i)] = i;
+            std::stable_sort(v->order.begin(), v->order.end(), [&](int32_t a, int32_t b) { return host_jobs[a].schedule < host_jobs[b].schedule; });
+            DAB_CUDA_CHECK(v->d_order.reserve(size_t(n_jobs)));
+            DAB_CUDA_CHECK(cudaMemcpyAsync(v->d_order.ptr, v->order.data(), size_t(n_jobs) * sizeof(int32_t), cudaMemcpyHostToDevice, v->stream));
+            d_order = v->d_order.ptr;
+        }
+    }
+    const int grid = (n_jobs + VITL_THREADS - 1) / VITL_THREADS;
+    viterbi_lanes_kernel<<<grid, VITL_THREADS, 0, v->stream>>>(d_soft, soft_bytes, d_jobs, n_jobs, d_order, v->d_schedules.ptr,
+                                                              int(v->schedules.size()), d_out, out_bytes, d_error, d_status,
+                                                              v->d_scratch.ptr, scratch_steps);
+    v->launches++;
+    DAB_CUDA_CHECK(cudaGetLastError());
+    return DAB_OK;
+}
+
+static int launch(Viterbi* v, const int8_t* d_soft, size_t soft_bytes, const dab_vit_job* d_jobs, const dab_vit_job* host_jobs, int n_jobs,
+                  uint32_t max_steps, uint8_t* d_out, size_t out_bytes, uint64_t* d_error, int32_t* d_status) {
     if (n_jobs <= 0) return DAB_OK;
     int rc = upload_schedules(v);
     if (rc != DAB_OK) return rc;
+    if (use_lanes(n_jobs)) return launch_lanes(v, d_soft, soft_bytes, d_jobs, host_jobs, n_jobs, max_steps, d_out, out_bytes, d_error, d_status);
     size_t smem = 0;
     const uint32_t window = pick_window(v, max_steps, &smem);
     uint32_t scratch_steps = 0;
@@ -214,7 +292,7 @@ int dab_viterbi_decode_jobs_device(dab_viterbi* h, const int8_t* d_soft, size_t 
     if (n_jobs < 0 || (n_jobs > 0 && (!d_soft || !d_jobs || !d_out))) return set_error(DAB_ERR_INVALID, "null buffer");
     std::lock_guard<std::mutex> lock(v->mtx);
     DAB_CUDA_CHECK(cudaSetDevice(v->device));
-    return launch(v, d_soft, soft_bytes, d_jobs, n_jobs, max_steps, d_out, out_bytes, d_path_error, d_job_status);
+    return launch(v, d_soft, soft_bytes, d_jobs, nullptr, n_jobs, max_steps, d_out, out_bytes, d_path_error, d_job_status);
 }
 
 int dab_viterbi_decode_batch_device(dab_viterbi* h, const int8_t* d_soft, size_t soft_bytes, const dab_vit_job* jobs, int n_jobs,
@@ -230,7 +308,7 @@ int dab_viterbi_decode_batch_device(dab_viterbi* h, const int8_t* d_soft, size_t
     if (bad >= 0) return set_error(DAB_ERR_INVALID, "job %d names unknown schedule %u", bad, jobs[bad].schedule);
     DAB_CUDA_CHECK(v->d_jobs.reserve(size_t(n_jobs)));
     DAB_CUDA_CHECK(cudaMemcpyAsync(v->d_jobs.ptr, jobs, size_t(n_jobs) * sizeof(dab_vit_job), cudaMemcpyHostToDevice, v->stream));
-    int rc = launch(v, d_soft, soft_bytes, v->d_jobs.ptr, n_jobs, max_steps, d_out, out_bytes, d_path_error, d_job_status);
+    int rc = launch(v, d_soft, soft_bytes, v->d_jobs.ptr, jobs, n_jobs, max_steps, d_out, out_bytes, d_path_error, d_job_status);
     // `jobs` is caller memory: make sure the staged copy has left it before returning
     DAB_CUDA_CHECK(cudaStreamSynchronize(v->stream));
     return rc;
@@ -255,7 +333,7 @@ int dab_viterbi_decode_batch(dab_viterbi* h, const int8_t* soft, size_t soft_byt
     DAB_CUDA_CHECK(cudaMemcpyAsync(v->d_jobs.ptr, jobs, size_t(n_jobs) * sizeof(dab_vit_job), cudaMemcpyHostToDevice, v->stream));
     DAB_CUDA_CHECK(cudaMemcpyAsync(v->d_soft.ptr, soft, soft_bytes, cudaMemcpyHostToDevice, v->stream));
     DAB_CUDA_CHECK(cudaMemsetAsync(v->d_out.ptr, 0, out_bytes, v->stream));
-    int rc = launch(v, v->d_soft.ptr, soft_bytes, v->d_jobs.ptr, n_jobs, max_steps, v->d_out.ptr, out_bytes, v->d_error.ptr, v->d_status.ptr);
+    int rc = launch(v, v->d_soft.ptr, soft_bytes, v->d_jobs.ptr, jobs, n_jobs, max_steps, v->d_out.ptr, out_bytes, v->d_error.ptr, v->d_status.ptr);
     if (rc != DAB_OK) return rc;
     DAB_CUDA_CHECK(cudaMemcpyAsync(out, v->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, v->stream));
     if (path_error) DAB_CUDA_CHECK(cudaMemcpyAsync(path_error, v->d_error.ptr, size_t(n_jobs) * sizeof(uint64_t), cudaMemcpyDeviceToHost, v->stream));

@@ -1,0 +1,241 @@
+// Lane-per-trellis form of the DAB Viterbi decoder (sm_100a): the bulk path for batches of thousands of trellises.
+//
+// Same arithmetic as viterbi_core.cuh (the warp-per-trellis form), i.e. ViterbiDecoder_AVX_u16<7,4>
+// (reference vendor/viterbi_decoder/include/viterbi/x86/viterbi_decoder_avx_u16.h:47-170), DAB_Viterbi_Decoder::update /
+// depuncture_symbols (src/dab/algorithms/dab_viterbi_decoder.cpp:114-181) and ViterbiDecoder_Core::chainback
+// (viterbi_decoder_core.h:214-236) -- bit-exact bytes and path error -- but laid out the other way round:
+//
+//   * one THREAD runs one 64-state trellis; a warp runs 32 trellises in lock step.  The 64 path metrics of a trellis live in
+//     32 registers as u16x2 pairs R[k] = (metric[k], metric[k+32]) -- exactly the two predecessors of butterfly k.
+//   * butterflies k and k+16 are done together: two PRMTs build A = (m0_k, m0_k+16), B = (m1_k, m1_k+16); then
+//     (new[2k], new[2k+32]) = min(A + E, B + E') and (new[2k+1], new[2k+33]) = min(A + E', B + E) are 4 VIADD.16x2 + 2
+//     VIMNMX.U16x2, and the results ARE R'[2k] and R'[2k+1]: the layout reproduces itself, no shuffles, no shared memory.
+//   * the 32 butterflies see only 8 distinct branch-metric patterns (G = {109,79,83,109}: polynomials 0 and 3 coincide), and
+//     butterfly k+16 has the pattern of k with the first bit flipped, so a step needs 8 VABSDIFF4 and 8 packs.  When no symbol is
+//     -128, 1016 - e[p] = e[~p], so the complementary pairs E' are the same 8 registers.
+//   * the packed adds wrap where the reference saturates.  All metrics lie within 6 * 1020 of metric[0] (every state is
+//     reachable from the best one in 6 steps), so a lane looks at the other 63 metrics only while metric[0] >= 58000; it then
+//     computes the exact maximum and runs the saturating form of the step when a metric could reach 65535.
+//   * survivor decisions (64 bits per step per trellis) stream to a global scratch as [warp][step][lane] uint2: every warp
+//     store / traceback load is one coalesced 256-byte row.  The traceback is 32 lanes wide (each lane walks its own trellis).
+//   * depuncturing walks the cyclic count table per lane; the punctured symbols are read as aligned 32-bit words and
+//     funnel-shifted to the lane's byte position (L1 holds the lane's 128-byte line between refills).
+//
+// ~7 warp instructions per trellis step instead of ~65 for the warp-per-trellis form, so this is the form used when a batch
+// is large enough to fill the GPU with one trellis per thread (viterbi.cu: launch()).
+#pragma once
+#include "viterbi_core.cuh"
+
+namespace dabb200 {
+
+constexpr int VITL_THREADS = 64;              // 2 warps per CTA
+constexpr uint32_t VITL_CAREFUL = 58000;      // < 65535 - 1020 - 6 * 1020: below this no metric can be near saturation
+
+__host__ __device__ constexpr uint32_t vitl_par(uint32_t v) { return (v ^ (v >> 1) ^ (v >> 2) ^ (v >> 3) ^ (v >> 4) ^ (v >> 5) ^ (v >> 6)) & 1u; }
+// branch pattern of butterfly s: bit 0 = polynomials 0 and 3 (109), bit 1 = polynomial 1 (79), bit 2 = polynomial 2 (83)
+// (ViterbiBranchTable<7,4>, viterbi_branch_table.h:44-52)
+__host__ __device__ constexpr uint32_t vitl_pattern(uint32_t s) {
+    return vitl_par((s << 1) & 109u) | (vitl_par((s << 1) & 79u) << 1) | (vitl_par((s << 1) & 83u) << 2);
+}
+// the 4 table bytes (+127 -> 0x7F, -127 -> 0x81) of pattern p, one byte per polynomial
+__host__ __device__ constexpr uint32_t vitl_table4(uint32_t p) {
+    return ((p & 1u) ? 0x7F00007Fu : 0x81000081u) | ((p & 2u) ? 0x00007F00u : 0x00008100u) | ((p & 4u) ? 0x007F0000u : 0x00810000u);
+}
+static_assert(vitl_pattern(16) == (vitl_pattern(0) ^ 1u) && vitl_pattern(21) == (vitl_pattern(5) ^ 1u), "butterfly k+16 flips pattern bit 0");
+
+__device__ __forceinline__ uint32_t vitl_min_halves(uint32_t x) { return min(x & 0xFFFFu, x >> 16); }
+__device__ __forceinline__ uint32_t vitl_max_halves(uint32_t x) { return max(x & 0xFFFFu, x >> 16); }
+
+// acc |= bit under a predicate, as ONE predicated LOP3 (the compiler's own choice is SEL + IADD3: 1.5 instructions per bit)
+__device__ __forceinline__ void vitl_or_if(uint32_t& acc, bool p, uint32_t bit) {
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q or.b32 %0, %0, %2;\n\t}" : "+r"(acc) : "r"(uint32_t(p)), "r"(bit));
+}
+
+// One trellis step for all 64 states of this lane's trellis: in -> out, decision bits (state k < 32: bit k of dlo, else bit
+// k-32 of dhi; 1 = predecessor k/2+32 survived, ties included: viterbi_decoder_avx_u16.h:114-115).
+template <bool SATURATING>
+__device__ __forceinline__ void vitl_acs(const uint32_t (&in)[32], uint32_t (&out)[32], const uint32_t (&E)[8], const uint32_t (&Ei)[8],
+                                         uint32_t& dlo, uint32_t& dhi) {
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        constexpr uint32_t dummy = 0; (void)dummy;
+        const uint32_t p = vitl_pattern(uint32_t(s));
+        const uint32_t A = __byte_perm(in[s], in[s + 16], 0x5410);   // (metric[s],    metric[s+16])
+        const uint32_t B = __byte_perm(in[s], in[s + 16], 0x7632);   // (metric[s+32], metric[s+48])
+        uint32_t a0, b0, a1, b1;
+        if (SATURATING) {
+            a0 = __vaddus2(A, E[p]);  b0 = __vaddus2(B, Ei[p]);
+            a1 = __vaddus2(A, Ei[p]); b1 = __vaddus2(B, E[p]);
+        } else {
+            a0 = __vadd2(A, E[p]);  b0 = __vadd2(B, Ei[p]);
+            a1 = __vadd2(A, Ei[p]); b1 = __vadd2(B, E[p]);
+        }
+        bool ph, pl;
+        out[2 * s] = __vibmin_u16x2(b0, a0, &ph, &pl);        // pred = (b <= a)
+        vitl_or_if(lo, pl, 1u << (2 * s));
+        vitl_or_if(hi, ph, 1u << (2 * s));
+        out[2 * s + 1] = __vibmin_u16x2(b1, a1, &ph, &pl);
+        vitl_or_if(lo, pl, 1u << (2 * s + 1));
+        vitl_or_if(hi, ph, 1u << (2 * s + 1));
+    }
+    dlo = lo;
+    dhi = hi;
+}
+
+// per-lane reader of the punctured symbols of one job + the depuncture walk (dab_viterbi_decoder.cpp:131-181)
+struct VitlFeed {
+    const uint32_t* words;    // aligned base
+    uint32_t bytepos;         // byte position of the next symbol from `words`
+    uint32_t widx;            // index of w0
+    uint32_t last_word;       // last word that may be read
+    uint32_t w0, w1;
+    // segment walk
+    const DevSegment* segs;
+    uint32_t n_seg, k, seg_end, code_len, counts, r;
+
+    __device__ __forceinline__ void open(const int8_t* soft, uint32_t soft_symbols, const DevSchedule* sch) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(soft);
+        words = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+        bytepos = uint32_t(a & 3u);
+        widx = 0;
+        last_word = (bytepos + max(soft_symbols, 1u) - 1u) >> 2;
+        w0 = __ldg(words);
+        w1 = __ldg(words + min(1u, last_word));
+        segs = sch->seg;
+        n_seg = sch->n_seg;
+        k = 0;
+        load_segment();
+    }
+    __device__ __forceinline__ void load_segment() {
+        const DevSegment& sg = segs[k];
+        seg_end = sg.first_step + sg.n_steps;
+        code_len = sg.code_len;
+        counts = sg.counts;
+        r = 0;
+    }
+    // the 4 depunctured symbols of trellis step t as packed bytes (punctured positions = 0)
+    __device__ __forceinline__ uint32_t next(uint32_t t) {
+        while (t >= seg_end && k + 1 < n_seg) { k++; load_segment(); }
+        const uint32_t cnt = (counts >> (4u * r)) & 0xFu;
+        r = (r + 1u == code_len) ? 0u : r + 1u;
+        const uint32_t raw = __funnelshift_r(w0, w1, (bytepos & 3u) * 8u);
+        const uint32_t sym4 = raw & __funnelshift_rc(0xFFFFFFFFu, 0u, 32u - 8u * cnt);
+        bytepos += cnt;
+        if ((bytepos >> 2) != widx) {
+            widx++;
+            w0 = w1;
+            w1 = __ldg(words + min(widx + 1u, last_word));
+        }
+        return sym4;
+    }
+};
+
+// One trellis per lane.  `active` lanes decode (sch, view); the others idle through the warp's loop.
+//     View::soft_base()                       first punctured symbol of this lane's job
+//     View::store(uint32_t byte, uint32_t v)  decoded byte (MSB first)
+// dec: this warp's decision rows, [step][32] uint2.  Returns the path error (dab_viterbi_decoder.cpp:124-129).
+template <class View>
+__device__ __forceinline__ uint64_t viterbi_lane_trellis(const DevSchedule* sch, View& view, uint2* __restrict__ dec, int lane, bool active) {
+    const uint32_t total_steps = active ? sch->total_steps : 0u;
+    const uint32_t warp_steps = __reduce_max_sync(0xFFFFFFFFu, total_steps);
+
+    uint32_t R[32], Q[32];
+    uint64_t renorm_acc = 0;
+    bool near_sat = false;
+    VitlFeed feed;
+    if (active) {
+        // ViterbiDecoder_Core::reset (viterbi_decoder_core.h:202-211)
+        const uint32_t start_state = sch->start_state & 63u;
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            uint32_t v = VIT_NON_START | (VIT_NON_START << 16);
+            if (start_state == uint32_t(k)) v &= 0xFFFF0000u;
+            if (start_state == uint32_t(k + 32)) v &= 0x0000FFFFu;
+            R[k] = v;
+        }
+        feed.open(view.soft_base(), sch->soft_symbols, sch);
+    }
+
+    auto step = [&](uint32_t t, const uint32_t (&in)[32], uint32_t (&out)[32]) {
+        const uint32_t sym4 = feed.next(t);
+        uint32_t e8[8], E[8], Ei[8];
+#pragma unroll
+        for (int p = 0; p < 8; p++) e8[p] = vabsdiff4_sum(vitl_table4(uint32_t(p)), sym4);   // <= 1020: adds_epu16 never saturates
+#pragma unroll
+        for (int p = 0; p < 8; p++) E[p] = e8[p] | (e8[p ^ 1] << 16);
+        // subs_epu16(1016, e) == e of the complementary pattern unless a symbol is -128 (|127 + 128| + |-127 + 128| = 256)
+        const uint32_t t80 = sym4 ^ 0x80808080u;
+        const bool has_m128 = ((t80 - 0x01010101u) & ~t80 & 0x80808080u) != 0u;
+#pragma unroll
+        for (int p = 0; p < 8; p++) Ei[p] = E[p ^ 7];
+        if (has_m128) {
+#pragma unroll
+            for (int p = 0; p < 8; p++) {
+                const uint32_t i0 = (e8[p] > VIT_MAX_ERROR) ? 0u : VIT_MAX_ERROR - e8[p];
+                const uint32_t i1 = (e8[p ^ 1] > VIT_MAX_ERROR) ? 0u : VIT_MAX_ERROR - e8[p ^ 1];
+                Ei[p] = i0 | (i1 << 16);
+            }
+        }
+        uint32_t dlo, dhi;
+        if (near_sat) vitl_acs<true>(in, out, E, Ei, dlo, dhi);
+        else vitl_acs<false>(in, out, E, Ei, dlo, dhi);
+        __stcs(&dec[size_t(t) * 32u + uint32_t(lane)], make_uint2(dlo, dhi));
+        near_sat = false;
+        const uint32_t new0 = out[0] & 0xFFFFu;
+        if (new0 >= VITL_CAREFUL) {
+            if (new0 >= VIT_RENORM) {   // renormalise (viterbi_decoder_avx_u16.h:138-170)
+                uint32_t m2 = out[0];
+#pragma unroll
+                for (int k = 1; k < 32; k++) m2 = __vminu2(m2, out[k]);
+                const uint32_t mn = vitl_min_halves(m2);
+                const uint32_t mn2 = mn | (mn << 16);
+#pragma unroll
+                for (int k = 0; k < 32; k++) out[k] = __vsub2(out[k], mn2);
+                renorm_acc += mn;
+            }
+            uint32_t x2 = out[0];
+#pragma unroll
+            for (int k = 1; k < 32; k++) x2 = __vmaxu2(x2, out[k]);
+            near_sat = vitl_max_halves(x2) >= VIT_NEAR_SAT;
+        }
+    };
+
+    for (uint32_t t = 0; t < warp_steps; t += 2) {
+        if (t < total_steps) step(t, R, Q);
+        if (t + 1 < total_steps) {
+            step(t + 1, Q, R);
+        } else if (t < total_steps) {
+#pragma unroll
+            for (int k = 0; k < 32; k++) R[k] = Q[k];
+        }
+    }
+
+    // ---- DAB_Viterbi_Decoder::chainback (dab_viterbi_decoder.cpp:124-129): error = sum of renormalisations + metric[0]
+    const uint64_t path_error = active ? renorm_acc + uint64_t(R[0] & 0xFFFFu) : 0;
+
+    // ---- ViterbiDecoder_Core::chainback (viterbi_decoder_core.h:214-236) with ViterbiTracebackBuffer<7>, a byte at a time:
+    // the 8 decision rows of a byte are requested before the serial walk through them
+    const uint32_t n_bytes = active ? sch->n_out_bits / 8u : 0u;
+    const uint32_t warp_bytes = __reduce_max_sync(0xFFFFFFFFu, n_bytes);
+    uint32_t reg = active ? (sch->end_state & 63u) << 2 : 0u;
+    for (int32_t b = int32_t(warp_bytes) - 1; b >= 0; b--) {
+        if (uint32_t(b) < n_bytes) {
+            uint2 w[8];
+            const uint2* row = dec + (size_t(b) * 8u + 6u) * 32u + uint32_t(lane);
+#pragma unroll
+            for (int i = 0; i < 8; i++) w[i] = __ldcs(row + size_t(i) * 32u);
+#pragma unroll
+            for (int i = 7; i >= 0; i--) {
+                const uint32_t state = reg >> 2;
+                const uint32_t word = (state & 32u) ? w[i].y : w[i].x;
+                const uint32_t bit = (word >> (state & 31u)) & 1u;
+                reg = (reg >> 1) | (bit << 7);
+            }
+            view.store(uint32_t(b), reg & 0xFFu);
+        }
+    }
+    return path_error;
+}
+
+}  // namespace dabb200

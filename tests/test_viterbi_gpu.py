@@ -29,8 +29,11 @@ EEP_3A_48CU = [(8, 128 * 45), (7, 128 * 3), (0, 24)]      # 6n-3, 3 blocks with 
 UEP_ROW0 = [(5, 128 * 3), (3, 128 * 4), (2, 128 * 17), (0, 24)]
 
 
-@pytest.fixture(scope="module")
-def vit(pkg):
+@pytest.fixture(params=["warp", "lanes"])
+def vit(pkg, request, monkeypatch):
+    """every parity case runs through both kernel forms: one trellis per warp (viterbi_kernel) and one per thread
+    (viterbi_lanes_kernel, the bulk form) -- DAB_B200_VITERBI_LANES is read at every launch"""
+    monkeypatch.setenv("DAB_B200_VITERBI_LANES", "1" if request.param == "lanes" else "0")
     v = importlib.import_module("dab-radio_b200.viterbi")
     return v
 
@@ -159,4 +162,81 @@ def test_against_reference_golden_vectors(vit, oracle):
     for i, (o, out, err) in enumerate(want):
         assert np.array_equal(got[o:o + out.size], out), keys[i]
         assert int(errs[i]) == err, keys[i]
+    vb.close()
+
+
+def test_unaligned_offsets_and_ragged_warps(vit, oracle):
+    """jobs start at odd byte offsets (the bulk kernel reads aligned words and funnel-shifts), 37 jobs = one full + one
+    ragged warp, three schedules of different length interleaved"""
+    rng = np.random.default_rng(77)
+    vb = vit.ViterbiBatch(0)
+    specs = [(FIC, 96), (EEP_3A_48CU, 192), (UEP_ROW0, 96)]
+    sids = [vb.add_schedule(vit.make_schedule(_segments(oracle, sp), nb)) for sp, nb in specs]
+    n = 37
+    jobs = np.zeros(n, vit.capi.VIT_JOB_DTYPE)
+    chunks, cases, soft_off, out_off = [], [], 0, 0
+    for i in range(n):
+        k = i % 3
+        segs, rx = _make_case(oracle, rng, specs[k][0], specs[k][1], (0, 70, 140)[(i // 3) % 3])
+        pad = int(rng.integers(0, 4)) | 1
+        chunks += [np.full(pad, -128, np.int8), rx]
+        soft_off += pad
+        jobs[i] = (sids[k], rx.size, soft_off, out_off)
+        cases.append((segs, rx, specs[k][1], out_off))
+        soft_off += rx.size
+        out_off += specs[k][1]
+    out, err, st = vb.decode_batch(np.concatenate(chunks), jobs, out_off)
+    assert np.all(st == 0)
+    o = oracle.OracleViterbi()
+    for i, (segs, rx, nb, off) in enumerate(cases):
+        o.set_traceback_length(nb * 8)
+        ref_out, ref_err, _ = o.decode_job(rx, segs, nb)
+        assert np.array_equal(out[off:off + nb], ref_out), i
+        assert int(err[i]) == ref_err, i
+    vb.close()
+
+
+def test_bulk_batch_default_dispatch(pkg, oracle, monkeypatch):
+    """8192 trellises in one call: the default dispatch takes the one-trellis-per-thread form; every job must equal the
+    one-trellis-per-warp form bit for bit, and a sample of them the oracle"""
+    v = importlib.import_module("dab-radio_b200.viterbi")
+    rng = np.random.default_rng(123)
+    specs = [(FIC, 96), (EEP_3A_48CU, 192)]
+    base = [[_make_case(oracle, rng, sp, nb, sigma) for sigma in (0, 60, 110, 160) for _ in range(4)] for sp, nb in specs]
+    n = 8192
+    vb = v.ViterbiBatch(0)
+    sids = [vb.add_schedule(v.make_schedule(_segments(oracle, sp), nb)) for sp, nb in specs]
+    jobs = np.zeros(n, v.capi.VIT_JOB_DTYPE)
+    chunks, meta, soft_off, out_off = [], [], 0, 0
+    for i in range(n):
+        k = int(rng.integers(0, 2))
+        segs, rx = base[k][int(rng.integers(0, len(base[k])))]
+        # perturb a few symbols so that the jobs are not copies of one another
+        rx = rx.copy()
+        idx = rng.integers(0, rx.size, 8)
+        rx[idx] = rng.integers(-128, 128, 8).astype(np.int8)
+        jobs[i] = (sids[k], rx.size, soft_off, out_off)
+        chunks.append(rx)
+        meta.append((segs, rx, specs[k][1], out_off))
+        soft_off += rx.size
+        out_off += specs[k][1]
+    soft = np.concatenate(chunks)
+    results = {}
+    for form in ("", "0", "1"):
+        if form:
+            monkeypatch.setenv("DAB_B200_VITERBI_LANES", form)
+        else:
+            monkeypatch.delenv("DAB_B200_VITERBI_LANES", raising=False)
+        out, err, st = vb.decode_batch(soft, jobs, out_off)
+        assert np.all(st == 0)
+        results[form] = (out.copy(), err.copy())
+    assert np.array_equal(results[""][0], results["0"][0]) and np.array_equal(results[""][1], results["0"][1])
+    assert np.array_equal(results["1"][0], results["0"][0]) and np.array_equal(results["1"][1], results["0"][1])
+    o = oracle.OracleViterbi()
+    for i in range(0, n, 97):
+        segs, rx, nb, off = meta[i]
+        o.set_traceback_length(nb * 8)
+        ref_out, ref_err, _ = o.decode_job(rx, segs, nb)
+        assert np.array_equal(results[""][0][off:off + nb], ref_out), i
+        assert int(results[""][1][i]) == ref_err, i
     vb.close()
