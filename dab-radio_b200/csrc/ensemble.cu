@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "viterbi_core.cuh"
+#include "viterbi_lanes.cuh"
 
 namespace dabb200 {
 
@@ -127,6 +128,7 @@ struct EnsView {
     uint8_t* out;
     const uint8_t* prbs;   // AdditiveScrambler byte sequence for syncword 0xFFFF
     __device__ __forceinline__ uint32_t fetch(uint32_t idx) const { return uint32_t(uint8_t(soft[idx])); }
+    __device__ __forceinline__ const int8_t* soft_base() const { return soft; }
     __device__ __forceinline__ void store(uint32_t byte, uint32_t value) { out[byte] = uint8_t(value ^ prbs[byte]); }
 };
 
@@ -217,6 +219,71 @@ ens_viterbi_kernel(EnsGeom g, const int8_t* __restrict__ bits, size_t stream_str
         if (lane == 0) o.fic_error[size_t(s) * g.nb_cifs + c] = err;
     } else if (lane == 0) {
         o.msc_nbytes[(size_t(s) * g.nb_cifs + c) * size_t(g.max_subs) + k] = int32_t(n_out_bytes);
+        o.msc_error[(size_t(s) * g.nb_cifs + c) * size_t(g.max_subs) + k] = err;
+    }
+}
+
+// The same stage with one trellis per THREAD (viterbi_lanes.cuh), used when a call carries thousands of trellises.  Warps are
+// laid out slot-major: warp w serves slot w / warps_per_slot (0 = FIC when enabled, then the sub-channel slots), and within the
+// slot the 32 consecutive (cif, stream) pairs starting at (w % warps_per_slot) * 32, stream fastest -- streams tuned to the same
+// ensemble walk the same schedule in lock step.  slot_row[k] = first decision row (of 32 uint2) of slot k's warps.
+__global__ void __maxnreg__(VITL_MAX_REGS)
+ens_viterbi_lanes_kernel(EnsGeom g, const int8_t* __restrict__ bits, size_t stream_stride, const int32_t* __restrict__ frames_in_call, int slot,
+                         const int8_t* __restrict__ deint, const SubDesc* __restrict__ subs, const int32_t* __restrict__ stored,
+                         const DevSchedule* __restrict__ schedules, const uint8_t* __restrict__ prbs, EnsOut o, int warps_per_slot,
+                         const unsigned long long* __restrict__ slot_row, const uint32_t* __restrict__ slot_steps, uint2* __restrict__ scratch) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int slot_k = w / warps_per_slot;
+    const int wj = w - slot_k * warps_per_slot;
+    const long long j = (long long)(wj) * 32 + lane;
+    const long long per_slot = (long long)(g.nb_cifs) * g.n_streams;
+    const int s = int(j % g.n_streams);
+    const int c = int(j / g.n_streams);
+    const bool is_fic = g.fic_enabled && slot_k == 0;
+    const int k = slot_k - (g.fic_enabled ? 1 : 0);
+
+    bool active = j < per_slot && stream_has_frame(frames_in_call, slot, s);
+    const DevSchedule* sch = schedules;   // schedule 0 is the FIC schedule
+    const int8_t* soft = bits;
+    uint8_t* out = o.fib_bytes;
+    if (active) {
+        if (is_fic) {
+            soft = bits + size_t(s) * stream_stride + size_t(c) * size_t(g.nb_fib_cif_bits);
+            out = o.fib_bytes + (size_t(s) * g.nb_cifs + c) * size_t(g.fib_group_bytes);
+        } else {
+            active = false;
+            if (k < g.max_subs) {
+                const SubDesc sd = subs[size_t(s) * g.max_subs + k];
+                if (sd.schedule >= 0) {
+                    int32_t* nbytes = o.msc_nbytes + (size_t(s) * g.nb_cifs + c) * size_t(g.max_subs) + k;
+                    if (sd.overflow) *nbytes = -1;
+                    // CIF_Deinterleaver::Deinterleave refuses until 16 CIFs were consumed (cif_deinterleaver.cpp:40-43)
+                    else if (stored[size_t(s) * g.max_subs + k] + c + 1 < ENS_DEINT_DEPTH) *nbytes = 0;
+                    else if (schedules[sd.schedule].total_steps <= slot_steps[slot_k]) {
+                        active = true;
+                        sch = schedules + sd.schedule;
+                        soft = deint + (size_t(s) * g.nb_cifs + c) * size_t(g.cif_pitch) + size_t(sd.start_cu) * 64u;
+                        out = o.msc_bytes + (size_t(s) * g.nb_cifs + c) * size_t(g.msc_cif_bytes) + size_t(sd.start_cu) * 8u;
+                    }
+                }
+            }
+        }
+    }
+    EnsView view{soft, out, prbs};
+    uint2* dec = scratch + (size_t(slot_row[slot_k]) + size_t(wj) * slot_steps[slot_k]) * 32u;
+    const uint64_t err = viterbi_lane_trellis(sch, view, dec, lane, active);
+    if (!active) return;
+    if (is_fic) {
+        const int fib_bytes = g.fib_group_bytes / g.nb_fibs_per_cif;
+        for (int f = 0; f < g.nb_fibs_per_cif; f++) {
+            const uint8_t* fib = out + f * fib_bytes;
+            const uint32_t rx = (uint32_t(fib[fib_bytes - 2]) << 8) | fib[fib_bytes - 1];
+            o.fib_valid[(size_t(s) * g.nb_cifs + c) * size_t(g.nb_fibs_per_cif) + f] = uint8_t(rx == crc16_fib(fib, fib_bytes - 2));
+        }
+        o.fic_error[size_t(s) * g.nb_cifs + c] = err;
+    } else {
+        o.msc_nbytes[(size_t(s) * g.nb_cifs + c) * size_t(g.max_subs) + k] = int32_t(sch->n_out_bits / 8u);
         o.msc_error[(size_t(s) * g.nb_cifs + c) * size_t(g.max_subs) + k] = err;
     }
 }
@@ -328,6 +395,13 @@ struct Ensemble {
     DeviceBuffer<DevSchedule> d_schedules;
     DeviceBuffer<uint8_t> d_prbs, d_fib_bytes, d_fib_valid, d_msc_bytes;
     DeviceBuffer<uint2> d_scratch;
+    // one-trellis-per-thread form (ens_viterbi_lanes_kernel): decision rows per slot
+    int warps_per_slot = 0;
+    std::vector<unsigned long long> lane_slot_row;   // [jobs_per_cif + 1] first row of each slot's warps
+    std::vector<uint32_t> lane_slot_steps;           // [jobs_per_cif] rows per warp
+    DeviceBuffer<unsigned long long> d_slot_row;
+    DeviceBuffer<uint32_t> d_slot_steps;
+    DeviceBuffer<uint2> d_lane_scratch;
     uint64_t launches = 0;
 };
 
@@ -383,6 +457,20 @@ static int upload_tables(Ensemble* e) {
     e->window_steps = std::min(cap_steps, std::max((window + 31u) & ~31u, 32u));
     e->scratch_steps = (longest + 31u) & ~31u;
     if (e->n_long > 0) DAB_CUDA_CHECK(e->d_scratch.reserve(size_t(e->n_long) * g.nb_cifs * g.n_streams * e->scratch_steps));
+    e->warps_per_slot = int((size_t(g.nb_cifs) * size_t(g.n_streams) + 31) / 32);
+    e->lane_slot_steps.assign(size_t(std::max(e->jobs_per_cif, 1)), 0u);
+    e->lane_slot_row.assign(size_t(e->jobs_per_cif) + 1, 0ull);
+    for (int sk = 0; sk < e->jobs_per_cif; sk++) {
+        const bool fic = g.fic_enabled && sk == 0;
+        const uint32_t st = fic ? e->schedules[0].total_steps : slot_steps[size_t(sk - (g.fic_enabled ? 1 : 0))];
+        const uint32_t rows = std::max(8u, (st + 1u) & ~1u);
+        e->lane_slot_steps[size_t(sk)] = rows;
+        e->lane_slot_row[size_t(sk) + 1] = e->lane_slot_row[size_t(sk)] + (unsigned long long)(e->warps_per_slot) * rows;
+    }
+    DAB_CUDA_CHECK(e->d_slot_row.reserve(e->lane_slot_row.size()));
+    DAB_CUDA_CHECK(e->d_slot_steps.reserve(e->lane_slot_steps.size()));
+    DAB_CUDA_CHECK(cudaMemcpyAsync(e->d_slot_row.ptr, e->lane_slot_row.data(), e->lane_slot_row.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, e->stream));
+    DAB_CUDA_CHECK(cudaMemcpyAsync(e->d_slot_steps.ptr, e->lane_slot_steps.data(), e->lane_slot_steps.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
     DAB_CUDA_CHECK(e->d_schedules.reserve(std::max<size_t>(e->schedules.size(), 64)));
     DAB_CUDA_CHECK(cudaMemcpyAsync(e->d_schedules.ptr, e->schedules.data(), e->schedules.size() * sizeof(DevSchedule), cudaMemcpyHostToDevice, e->stream));
     DAB_CUDA_CHECK(cudaMemcpyAsync(e->d_subs.ptr, e->h_subs.data(), e->h_subs.size() * sizeof(SubDesc), cudaMemcpyHostToDevice, e->stream));
@@ -407,7 +495,17 @@ static int decode_device(Ensemble* e, const int8_t* d_bits, size_t stream_stride
         ens_deint_kernel<<<grid, ENS_CHUNK, 0, e->stream>>>(g, d_frames_in_call, slot, e->d_cif_count.ptr, e->d_ring.ptr, e->d_deint.ptr);
         e->launches += 2;
     }
-    if (e->jobs_per_cif > 0) {
+    const long long total_jobs = (long long)(e->jobs_per_cif) * g.nb_cifs * g.n_streams;
+    if (e->jobs_per_cif > 0 && vitl_use_lanes(total_jobs)) {
+        DAB_CUDA_CHECK(e->d_lane_scratch.reserve(size_t(e->lane_slot_row.back()) * 32u));
+        EnsOut o{e->d_fib_bytes.ptr, e->d_fib_valid.ptr, e->d_fic_error.ptr, e->d_msc_bytes.ptr, e->d_msc_nbytes.ptr, e->d_msc_error.ptr};
+        const unsigned grid = unsigned(e->warps_per_slot) * unsigned(e->jobs_per_cif);
+        ens_viterbi_lanes_kernel<<<grid, VITL_THREADS, 0, e->stream>>>(g, d_bits, stream_stride, d_frames_in_call, slot, e->d_deint.ptr,
+                                                                       e->d_subs.ptr, e->d_stored.ptr, e->d_schedules.ptr, e->d_prbs.ptr, o,
+                                                                       e->warps_per_slot, e->d_slot_row.ptr, e->d_slot_steps.ptr,
+                                                                       e->d_lane_scratch.ptr);
+        e->launches++;
+    } else if (e->jobs_per_cif > 0) {
         const size_t smem = size_t(VIT_WARPS_PER_CTA) * (size_t(e->window_steps) * sizeof(uint2) + sizeof(DevSchedule));
         DAB_CUDA_CHECK(cudaFuncSetAttribute(ens_viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
         const long long total = (long long)(e->jobs_per_cif) * g.nb_cifs * g.n_streams;

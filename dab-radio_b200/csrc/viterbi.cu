@@ -80,7 +80,7 @@ viterbi_kernel(const int8_t* __restrict__ soft, size_t soft_bytes, const dab_vit
 
 // The bulk form: one trellis per thread (viterbi_lanes.cuh).  Thread i decodes job order[i] (order == nullptr: job i); the
 // host sorts `order` by schedule so that the 32 trellises of a warp walk the same puncturing schedule in lock step.
-__global__ void __launch_bounds__(VITL_THREADS)
+__global__ void __maxnreg__(VITL_MAX_REGS)
 viterbi_lanes_kernel(const int8_t* __restrict__ soft, size_t soft_bytes, const dab_vit_job* __restrict__ jobs, int n_jobs,
                      const int32_t* __restrict__ order, const DevSchedule* __restrict__ schedules, int n_schedules,
                      uint8_t* __restrict__ out, size_t out_bytes, uint64_t* __restrict__ path_error, int32_t* __restrict__ job_status,
@@ -157,16 +157,6 @@ static uint32_t pick_window(const Viterbi* v, uint32_t max_steps, size_t* smem_b
     return window;
 }
 
-// Batches of at least this many trellises run one trellis per thread (viterbi_lanes_kernel); smaller ones one per warp
-// (viterbi_kernel), which finishes a handful of trellises sooner.  DAB_B200_VITERBI_LANES=0/1 forces the choice.
-constexpr int VITL_MIN_JOBS = 4096;
-
-static bool use_lanes(int n_jobs) {
-    const char* e = getenv("DAB_B200_VITERBI_LANES");
-    if (e && *e) return atoi(e) != 0;
-    return n_jobs >= VITL_MIN_JOBS;
-}
-
 static int launch_lanes(Viterbi* v, const int8_t* d_soft, size_t soft_bytes, const dab_vit_job* d_jobs, const dab_vit_job* host_jobs,
                         int n_jobs, uint32_t max_steps, uint8_t* d_out, size_t out_bytes, uint64_t* d_error, int32_t* d_status) {
     const uint32_t scratch_steps = std::max(8u, (max_steps + 1u) & ~1u);
@@ -200,7 +190,7 @@ static int launch(Viterbi* v, const int8_t* d_soft, size_t soft_bytes, const dab
     if (n_jobs <= 0) return DAB_OK;
     int rc = upload_schedules(v);
     if (rc != DAB_OK) return rc;
-    if (use_lanes(n_jobs)) return launch_lanes(v, d_soft, soft_bytes, d_jobs, host_jobs, n_jobs, max_steps, d_out, out_bytes, d_error, d_status);
+    if (vitl_use_lanes(n_jobs)) return launch_lanes(v, d_soft, soft_bytes, d_jobs, host_jobs, n_jobs, max_steps, d_out, out_bytes, d_error, d_status);
     size_t smem = 0;
     const uint32_t window = pick_window(v, max_steps, &smem);
     uint32_t scratch_steps = 0;

@@ -24,12 +24,24 @@
 // ~7 warp instructions per trellis step instead of ~65 for the warp-per-trellis form, so this is the form used when a batch
 // is large enough to fill the GPU with one trellis per thread (viterbi.cu: launch()).
 #pragma once
+#include <cstdlib>
 #include "viterbi_core.cuh"
 
 namespace dabb200 {
 
-constexpr int VITL_THREADS = 64;              // 2 warps per CTA
+constexpr int VITL_THREADS = 32;              // one warp per CTA: the finest grain the block scheduler can balance
+constexpr int VITL_MAX_REGS = 112;            // 18 warps per SM (registers are granted in 512s per warp): 2432 warps (1024 Mode I ensembles x 76 trellises) fit in one wave
+constexpr int VITL_TB_BYTES = 5;               // traceback: decoded bytes (x 8 decision rows) buffered per lane
 constexpr uint32_t VITL_CAREFUL = 58000;      // < 65535 - 1020 - 6 * 1020: below this no metric can be near saturation
+
+// Batches of at least this many trellises run one trellis per thread; smaller ones one per warp (viterbi_core.cuh), which
+// finishes a handful of trellises sooner.  DAB_B200_VITERBI_LANES=0/1 forces the choice (read at every launch).
+constexpr long long VITL_MIN_JOBS = 4096;
+inline bool vitl_use_lanes(long long n_jobs) {
+    const char* e = getenv("DAB_B200_VITERBI_LANES");
+    if (e && *e) return atoi(e) != 0;
+    return n_jobs >= VITL_MIN_JOBS;
+}
 
 __host__ __device__ constexpr uint32_t vitl_par(uint32_t v) { return (v ^ (v >> 1) ^ (v >> 2) ^ (v >> 3) ^ (v >> 4) ^ (v >> 5) ^ (v >> 6)) & 1u; }
 // branch pattern of butterfly s: bit 0 = polynomials 0 and 3 (109), bit 1 = polynomial 1 (79), bit 2 = polynomial 2 (83)
@@ -46,9 +58,12 @@ static_assert(vitl_pattern(16) == (vitl_pattern(0) ^ 1u) && vitl_pattern(21) == 
 __device__ __forceinline__ uint32_t vitl_min_halves(uint32_t x) { return min(x & 0xFFFFu, x >> 16); }
 __device__ __forceinline__ uint32_t vitl_max_halves(uint32_t x) { return max(x & 0xFFFFu, x >> 16); }
 
-// acc |= bit under a predicate, as ONE predicated LOP3 (the compiler's own choice is SEL + IADD3: 1.5 instructions per bit)
-__device__ __forceinline__ void vitl_or_if(uint32_t& acc, bool p, uint32_t bit) {
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q or.b32 %0, %0, %2;\n\t}" : "+r"(acc) : "r"(uint32_t(p)), "r"(bit));
+// Decision gather on the FP32 pipe: acc += 2^k under a predicate, as ONE predicated FADD.  The integer alternatives (@P
+// VIADD / LOP3) land on the fma-heavy or alu pipe, which the packed adds, PRMTs and min/max already fill; the fma-lite pipe
+// is otherwise idle in this kernel.  acc starts at 2^23, so with k < 16 the sum is exact and the low 16 mantissa bits of the
+// float ARE the gathered bits (no conversion: two PRMTs assemble the 64-bit decision word from four accumulators).
+__device__ __forceinline__ void vitl_fadd_if(float& acc, bool p, float bit) {
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q add.rn.f32 %0, %0, %2;\n\t}" : "+f"(acc) : "r"(uint32_t(p)), "f"(bit));
 }
 
 // One trellis step for all 64 states of this lane's trellis: in -> out, decision bits (state k < 32: bit k of dlo, else bit
@@ -56,10 +71,9 @@ __device__ __forceinline__ void vitl_or_if(uint32_t& acc, bool p, uint32_t bit) 
 template <bool SATURATING>
 __device__ __forceinline__ void vitl_acs(const uint32_t (&in)[32], uint32_t (&out)[32], const uint32_t (&E)[8], const uint32_t (&Ei)[8],
                                          uint32_t& dlo, uint32_t& dhi) {
-    uint32_t lo = 0, hi = 0;
+    float fl[2] = {8388608.0f, 8388608.0f}, fh[2] = {8388608.0f, 8388608.0f};
 #pragma unroll
     for (int s = 0; s < 16; s++) {
-        constexpr uint32_t dummy = 0; (void)dummy;
         const uint32_t p = vitl_pattern(uint32_t(s));
         const uint32_t A = __byte_perm(in[s], in[s + 16], 0x5410);   // (metric[s],    metric[s+16])
         const uint32_t B = __byte_perm(in[s], in[s + 16], 0x7632);   // (metric[s+32], metric[s+48])
@@ -73,14 +87,14 @@ __device__ __forceinline__ void vitl_acs(const uint32_t (&in)[32], uint32_t (&ou
         }
         bool ph, pl;
         out[2 * s] = __vibmin_u16x2(b0, a0, &ph, &pl);        // pred = (b <= a)
-        vitl_or_if(lo, pl, 1u << (2 * s));
-        vitl_or_if(hi, ph, 1u << (2 * s));
+        vitl_fadd_if(fl[(2 * s) >> 4], pl, float(1u << ((2 * s) & 15)));
+        vitl_fadd_if(fh[(2 * s) >> 4], ph, float(1u << ((2 * s) & 15)));
         out[2 * s + 1] = __vibmin_u16x2(b1, a1, &ph, &pl);
-        vitl_or_if(lo, pl, 1u << (2 * s + 1));
-        vitl_or_if(hi, ph, 1u << (2 * s + 1));
+        vitl_fadd_if(fl[(2 * s + 1) >> 4], pl, float(1u << ((2 * s + 1) & 15)));
+        vitl_fadd_if(fh[(2 * s + 1) >> 4], ph, float(1u << ((2 * s + 1) & 15)));
     }
-    dlo = lo;
-    dhi = hi;
+    dlo = __byte_perm(__float_as_uint(fl[0]), __float_as_uint(fl[1]), 0x5410);
+    dhi = __byte_perm(__float_as_uint(fh[0]), __float_as_uint(fh[1]), 0x5410);
 }
 
 // per-lane reader of the punctured symbols of one job + the depuncture walk (dab_viterbi_decoder.cpp:131-181)
@@ -157,30 +171,27 @@ __device__ __forceinline__ uint64_t viterbi_lane_trellis(const DevSchedule* sch,
         feed.open(view.soft_base(), sch->soft_symbols, sch);
     }
 
+    uint2* drow = dec + lane;   // this lane's slot in the decision row of the current step
     auto step = [&](uint32_t t, const uint32_t (&in)[32], uint32_t (&out)[32]) {
         const uint32_t sym4 = feed.next(t);
         uint32_t e8[8], E[8], Ei[8];
 #pragma unroll
         for (int p = 0; p < 8; p++) e8[p] = vabsdiff4_sum(vitl_table4(uint32_t(p)), sym4);   // <= 1020: adds_epu16 never saturates
 #pragma unroll
-        for (int p = 0; p < 8; p++) E[p] = e8[p] | (e8[p ^ 1] << 16);
-        // subs_epu16(1016, e) == e of the complementary pattern unless a symbol is -128 (|127 + 128| + |-127 + 128| = 256)
-        const uint32_t t80 = sym4 ^ 0x80808080u;
-        const bool has_m128 = ((t80 - 0x01010101u) & ~t80 & 0x80808080u) != 0u;
+        for (int p = 0; p < 8; p++) E[p] = e8[p ^ 1] * 65536u + e8[p];
+        // subs_epu16(1016, e[p]) in terms of the complementary pattern: a symbol s contributes |127 - s| + |-127 - s| = 254 to
+        // e[p] + e[~p], except s = -128 which contributes 256.  So e[p] + e[~p] = 1016 + 2 * (number of -128 symbols) =: 1016 + c
+        // and subs(1016, e[p]) = subs(e[~p], c): one packed max + add per pair, nothing at all to branch on.
+        const uint32_t c = e8[0] + e8[7] - VIT_MAX_ERROR;
+        const uint32_t c2 = c * 0x00010001u;                          // (c, c)
+        const uint32_t nc2 = ((0u - c) & 0xFFFFu) * 0x00010001u;      // (-c, -c) mod 2^16
 #pragma unroll
-        for (int p = 0; p < 8; p++) Ei[p] = E[p ^ 7];
-        if (has_m128) {
-#pragma unroll
-            for (int p = 0; p < 8; p++) {
-                const uint32_t i0 = (e8[p] > VIT_MAX_ERROR) ? 0u : VIT_MAX_ERROR - e8[p];
-                const uint32_t i1 = (e8[p ^ 1] > VIT_MAX_ERROR) ? 0u : VIT_MAX_ERROR - e8[p ^ 1];
-                Ei[p] = i0 | (i1 << 16);
-            }
-        }
+        for (int p = 0; p < 8; p++) Ei[p] = __vadd2(__vmaxu2(E[p ^ 7], c2), nc2);   // max(x, c) - c = subs(x, c)
         uint32_t dlo, dhi;
         if (near_sat) vitl_acs<true>(in, out, E, Ei, dlo, dhi);
         else vitl_acs<false>(in, out, E, Ei, dlo, dhi);
-        __stcs(&dec[size_t(t) * 32u + uint32_t(lane)], make_uint2(dlo, dhi));
+        *drow = make_uint2(dlo, dhi);   // default caching: the newest rows are the first the traceback asks for
+        drow += 32;
         near_sat = false;
         const uint32_t new0 = out[0] & 0xFFFFu;
         if (new0 >= VITL_CAREFUL) {
@@ -219,12 +230,15 @@ __device__ __forceinline__ uint64_t viterbi_lane_trellis(const DevSchedule* sch,
     const uint32_t n_bytes = active ? sch->n_out_bits / 8u : 0u;
     const uint32_t warp_bytes = __reduce_max_sync(0xFFFFFFFFu, n_bytes);
     uint32_t reg = active ? (sch->end_state & 63u) << 2 : 0u;
-    for (int32_t b = int32_t(warp_bytes) - 1; b >= 0; b--) {
-        if (uint32_t(b) < n_bytes) {
-            uint2 w[8];
+    auto load_rows = [&](uint2 (&w)[8], int32_t b) {
+        if (b >= 0 && uint32_t(b) < n_bytes) {
             const uint2* row = dec + (size_t(b) * 8u + 6u) * 32u + uint32_t(lane);
 #pragma unroll
             for (int i = 0; i < 8; i++) w[i] = __ldcs(row + size_t(i) * 32u);
+        }
+    };
+    auto walk_byte = [&](const uint2 (&w)[8], int32_t b) {
+        if (b >= 0 && uint32_t(b) < n_bytes) {
 #pragma unroll
             for (int i = 7; i >= 0; i--) {
                 const uint32_t state = reg >> 2;
@@ -233,6 +247,19 @@ __device__ __forceinline__ uint64_t viterbi_lane_trellis(const DevSchedule* sch,
                 reg = (reg >> 1) | (bit << 7);
             }
             view.store(uint32_t(b), reg & 0xFFu);
+        }
+    };
+    // VITL_TB_BYTES - 1 bytes (8 decision rows each) are in flight per lane while one is walked: the walk is a handful of
+    // instructions, so the traceback runs at whatever rate the memory system returns 256-byte rows
+    uint2 w[VITL_TB_BYTES][8];
+    int32_t b = int32_t(warp_bytes) - 1;
+#pragma unroll
+    for (int i = 0; i < VITL_TB_BYTES - 1; i++) load_rows(w[i], b - i);
+    for (; b >= 0; b -= VITL_TB_BYTES) {
+#pragma unroll
+        for (int i = 0; i < VITL_TB_BYTES; i++) {
+            load_rows(w[(i + VITL_TB_BYTES - 1) % VITL_TB_BYTES], b - i - (VITL_TB_BYTES - 1));
+            walk_byte(w[i], b - i);
         }
     }
     return path_error;

@@ -12,8 +12,11 @@ import goldenutil
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ens(pkg):
+@pytest.fixture(params=["warp", "lanes"])
+def ens(pkg, request, monkeypatch):
+    """every case runs with the Viterbi stage in both forms: one trellis per warp and one per thread (the bulk form the
+    default dispatch takes from 4096 trellises per call) -- DAB_B200_VITERBI_LANES is read at every launch"""
+    monkeypatch.setenv("DAB_B200_VITERBI_LANES", "1" if request.param == "lanes" else "0")
     return importlib.import_module("dab-radio_b200.ensemble")
 
 
