@@ -349,6 +349,7 @@ def run_ours(args):
         del iq
         torch.cuda.empty_cache()
         viterbi = viterbi_leg(torch, pkg, n_streams, 5, not args.no_cpu)
+        viterbi["ensemble"] = ensemble_leg(torch, pkg, n_streams, 5, not args.no_cpu)
 
     # ------------------------------------------------------------------ cpu baseline (rank 0, N = 1 only)
     cpu = None
@@ -447,7 +448,9 @@ def viterbi_leg(torch, pkg, n_streams, reps, with_cpu):
            "unit": "decoded Mbit/s", "ms_per_launch": round(ms, 4), "trellises": int(jobs.size), "streams": n_streams,
            "trellis_steps_per_s": round(steps / ms * 1e3, 0), "ensemble_frames_per_s": round(n_streams / ms * 1e3, 1),
            "realtime_ensembles": round(n_streams / ms * 1e3 * 0.096, 1), "bit_exact_vs_oracle": f"{len(layout)} trellises of stream 0",
-           "bound": "integer ALU (ACS); HBM traffic = soft bits in + bits/8 out, negligible"}
+           "kernel": "viterbi_lanes_kernel (one trellis per thread; batches below 4096 trellises take viterbi_kernel, one per warp)",
+           "bound": "integer issue (fma-heavy + alu pipes); HBM traffic = soft bits in + bits/8 out + 8 B per trellis step of survivor "
+                    "decisions written once and read once by the traceback"}
     if with_cpu:
         try:
             from oracle import pyref
@@ -465,6 +468,93 @@ def viterbi_leg(torch, pkg, n_streams, reps, with_cpu):
         except (FileNotFoundError, OSError, AttributeError) as e:  # noqa: PERF203
             res["cpu_baseline"] = {"unavailable": repr(e)}
     vb.close()
+    return res
+
+
+def ensemble_leg(torch, pkg, n_streams, reps, with_cpu):
+    """SURVEY 8(f) rows 2-3 measured: one OFDM frame of soft bits per stream, resident in HBM, through dab_ensemble_decode_frames_device
+    (CIF time de-interleave ring -> FIC + 18 x EEP 3-A Viterbi -> energy dispersal -> FIB CRC16), i.e. everything between the
+    demodulator's output and the decoded bytes.  Stream 0 is checked against the oracle's FIC_Decoder / MSC_Decoder."""
+    import ensgen
+    from oracle import pyoracle as po
+    ens = importlib.import_module("dab-radio_b200.ensemble")
+    layout = [(48 * k, 48, 0, 0, 2, 0) for k in range(18)]     # 18 DAB+ sub-channels, EEP 3-A, 48 CU each = the whole CIF
+    subs_o = [po.subchannel(*a) for a in layout]
+    n_frames = 5                                               # 20 CIFs: the 16-CIF de-interleaver is full from frame 4 on
+    tx = ensgen.EnsembleTx(1, subs_o, seed=77, sigma=45.0)
+    frames = np.stack([tx.next_frame() for _ in range(n_frames)])
+    want = ensgen.oracle_decode_stream(1, subs_o, frames)
+    d_base = torch.from_numpy(frames).cuda()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+    # every stream: the same code words under its own extra noise; stream 0 keeps the CPU-generated frames for the check
+    d_frames = d_base.view(n_frames, 1, -1).to(torch.int16) + torch.randint(-20, 21, (n_frames, n_streams, frames.shape[1]), device="cuda",
+                                                                            generator=g, dtype=torch.int16)
+    d_frames = d_frames.clamp_(-127, 127).to(torch.int8).contiguous()
+    d_frames[:, 0] = d_base
+    dec = ens.EnsembleDecoder(1, n_streams=n_streams, device=torch.cuda.current_device(), max_subchannels=18)
+    dec.set_cuda_stream(torch.cuda.current_stream().cuda_stream)
+    dec.set_subchannels(-1, [ens.subchannel(*a) for a in layout])
+    frame_bits = frames.shape[1]
+    run = lambda f: dec.decode_frames_device(d_frames[f].data_ptr(), frame_bits, None, 0)
+    for f in range(n_frames):
+        run(f)
+    dec.sync()
+    # stream 0 after the last distinct frame: FIBs, CRC flags, sub-channel bytes and path errors equal the oracle's
+    fb, fv, fe, msc = want[-1]
+    got_b, got_v, got_e = dec.read_fic(0)
+    for c in range(4):
+        assert np.array_equal(got_b[c], fb[c]) and np.array_equal(got_v[c], fv[c]) and int(got_e[c]) == fe[c], f"ensemble FIC cif {c} differs from the oracle"
+        for k in range(len(layout)):
+            b, n, e = dec.read_msc(0, c, k)
+            wb, we = msc[c][k]
+            assert n == wb.size == 192 and np.array_equal(b, wb) and e == we, f"ensemble MSC cif {c} sub {k} differs from the oracle"
+    launches0 = dec.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(reps):
+        run(i % n_frames)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    trellises, steps = dec.last_work()
+    launches = (dec.kernel_launches() - launches0) // reps
+    bits_out = n_streams * (4 * 768 + 4 * 18 * 1536)
+    res = {"metric": "ensemble decode: soft-bit frame -> FIBs + sub-channel bytes (CIF de-interleave, FIC + 18 x EEP 3-A 48 CU x 4 CIF Viterbi, "
+                     "energy dispersal, FIB CRC16), Mode I, soft bits resident in HBM",
+           "value": round(n_streams / ms * 1e3, 1), "unit": "ensemble frames/s", "ms_per_call": round(ms, 4), "streams": n_streams,
+           "realtime_ensembles": round(n_streams / ms * 1e3 * 0.096, 1), "decoded_mbit_s": round(bits_out / ms / 1e3, 1),
+           "trellises_per_call": trellises, "trellis_steps_per_s": round(steps / ms * 1e3, 0), "kernel_launches_per_call": int(launches),
+           "bit_exact_vs_oracle": "stream 0: 4 FIB groups + 72 sub-channel CIFs (bytes, CRC flags, path errors)",
+           "api": "dab_ensemble_decode_frames_device"}
+    if with_cpu:
+        try:
+            from concurrent.futures import ThreadPoolExecutor
+            from oracle import pyref
+            cores = os.cpu_count() or 1
+            n_rep = 40
+
+            def worker(_):
+                fic = pyref.RefFicDecoder(2304, 3)
+                decs = [pyref.RefMscDecoder(*a) for a in layout]
+                for _ in range(n_rep):
+                    for fr in frames:
+                        for c in range(4):
+                            fic.decode_group(fr[c * 2304:(c + 1) * 2304], c)
+                            cif = fr[9216 + c * 55296: 9216 + (c + 1) * 55296]
+                            for d in decs:
+                                d.decode_cif(cif)
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(cores) as ex:
+                list(ex.map(worker, range(cores)))
+            dt = time.perf_counter() - t0
+            res["cpu_baseline"] = {"value": round(cores * n_rep * n_frames / dt, 1), "unit": "ensemble frames/s", "cores": cores, "kind": "reference",
+                                   "sample": f"{cores} threads x {n_rep * n_frames} frames through the reference's FIC_Decoder + 18 MSC_Decoder "
+                                             f"(AVX2 Viterbi) via ctypes, {dt:.1f} s"}
+        except (FileNotFoundError, OSError, AttributeError) as e:  # noqa: PERF203
+            res["cpu_baseline"] = {"unavailable": repr(e)}
+    dec.close()
     return res
 
 
