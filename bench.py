@@ -413,13 +413,12 @@ def viterbi_leg(torch, pkg, n_streams, reps, with_cpu):
     d_soft = (d_base.view(1, -1).to(torch.int16) + torch.randint(-24, 25, (n_streams, frame_soft), device="cuda", generator=g, dtype=torch.int16))
     d_soft = d_soft.clamp_(-128, 127).to(torch.int8).contiguous()
     d_soft[0] = d_base
-    d_jobs = torch.from_numpy(jobs.view(np.uint8)).cuda()
     d_out = torch.zeros(n_streams * frame_out, dtype=torch.uint8, device="cuda")
     d_err = torch.zeros(jobs.size, dtype=torch.int64, device="cuda")
     d_st = torch.zeros(jobs.size, dtype=torch.int32, device="cuda")
-    max_steps = 1542
-    run = lambda: vb.decode_jobs_device(d_soft.data_ptr(), d_soft.numel(), d_jobs.data_ptr(), jobs.size, max_steps, d_out.data_ptr(), d_out.numel(),
-                                        d_err.data_ptr(), d_st.data_ptr())
+    # the job list of an ensemble configuration is prepared once (ordered by schedule, short FIC trellises packed two to a warp)
+    plan = vb.prepare_jobs(jobs)
+    run = lambda: vb.decode_prepared(plan, d_soft.data_ptr(), d_soft.numel(), d_out.data_ptr(), d_out.numel(), d_err.data_ptr(), d_st.data_ptr())
     for _ in range(2):
         run()
     torch.cuda.synchronize()

@@ -135,7 +135,7 @@ EXPORTED_SYMBOLS = (
     "dab_ofdm_kernel_launches", "dab_ofdm_set_kernel_timing", "dab_ofdm_get_kernel_times", "dab_ofdm_demod_frames_device",
     "dab_viterbi_create", "dab_viterbi_destroy", "dab_viterbi_set_cuda_stream", "dab_viterbi_add_schedule",
     "dab_viterbi_schedule_soft_symbols", "dab_viterbi_decode_batch", "dab_viterbi_decode_batch_device",
-    "dab_viterbi_decode_jobs_device", "dab_viterbi_decode_one", "dab_viterbi_sync", "dab_viterbi_kernel_launches",
+    "dab_viterbi_decode_jobs_device", "dab_viterbi_prepare_jobs", "dab_viterbi_decode_prepared", "dab_viterbi_release_jobs", "dab_viterbi_decode_one", "dab_viterbi_sync", "dab_viterbi_kernel_launches",
     "dab_get_dab_parameters", "dab_ensemble_create", "dab_ensemble_destroy", "dab_ensemble_set_cuda_stream",
     "dab_ensemble_set_subchannels", "dab_ensemble_subchannel_schedule", "dab_ensemble_decode_frames_device",
     "dab_ensemble_decode_frames", "dab_ensemble_device_results", "dab_ensemble_read_fic", "dab_ensemble_read_msc",
@@ -218,6 +218,9 @@ def _bind_viterbi(L):
     L.dab_viterbi_decode_batch.argtypes = [vp, vp, sz, vp, i32, vp, sz, vp, vp]
     L.dab_viterbi_decode_batch_device.argtypes = [vp, vp, sz, vp, i32, vp, sz, vp, vp]
     L.dab_viterbi_decode_jobs_device.argtypes = [vp, vp, sz, vp, i32, u32, vp, sz, vp, vp]
+    L.dab_viterbi_prepare_jobs.argtypes = [vp, vp, i32]
+    L.dab_viterbi_decode_prepared.argtypes = [vp, i32, vp, sz, vp, sz, vp, vp]
+    L.dab_viterbi_release_jobs.argtypes = [vp, i32]
     L.dab_viterbi_decode_one.argtypes = [vp, C.POINTER(VitSchedule), vp, sz, vp, C.POINTER(u64)]
     L.dab_viterbi_sync.argtypes = [vp]
     L.dab_viterbi_kernel_launches.argtypes = [vp]

@@ -223,21 +223,23 @@ ens_viterbi_kernel(EnsGeom g, const int8_t* __restrict__ bits, size_t stream_str
     }
 }
 
-// The same stage with one trellis per THREAD (viterbi_lanes.cuh), used when a call carries thousands of trellises.  Warps are
-// laid out slot-major: warp w serves slot w / warps_per_slot (0 = FIC when enabled, then the sub-channel slots), and within the
-// slot the 32 consecutive (cif, stream) pairs starting at (w % warps_per_slot) * 32, stream fastest -- streams tuned to the same
-// ensemble walk the same schedule in lock step.  slot_row[k] = first decision row (of 32 uint2) of slot k's warps.
+// The same stage with one trellis per THREAD (viterbi_lanes.cuh), used when a call carries thousands of trellises.  A group
+// is 32 consecutive (cif, stream) pairs of one slot (0 = FIC when enabled, then the sub-channel slots), stream fastest -- streams
+// tuned to the same ensemble walk the same schedule in lock step; group id = slot * groups_per_slot + chunk.  Warp w runs group
+// groups[w], longest slots first (vitl_plan: the short FIC groups are launched last and fill the gaps), with its decision rows
+// starting at row warp_row[w] of the scratch.
 __global__ void __maxnreg__(VITL_MAX_REGS)
 ens_viterbi_lanes_kernel(EnsGeom g, const int8_t* __restrict__ bits, size_t stream_stride, const int32_t* __restrict__ frames_in_call, int slot,
                          const int8_t* __restrict__ deint, const SubDesc* __restrict__ subs, const int32_t* __restrict__ stored,
-                         const DevSchedule* __restrict__ schedules, const uint8_t* __restrict__ prbs, EnsOut o, int warps_per_slot,
-                         const unsigned long long* __restrict__ slot_row, const uint32_t* __restrict__ slot_steps, uint2* __restrict__ scratch) {
+                         const DevSchedule* __restrict__ schedules, const uint8_t* __restrict__ prbs, EnsOut o, int groups_per_slot,
+                         const int32_t* __restrict__ groups, const unsigned long long* __restrict__ warp_row, uint2* __restrict__ scratch) {
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int slot_k = w / warps_per_slot;
-    const int wj = w - slot_k * warps_per_slot;
-    const long long j = (long long)(wj) * 32 + lane;
+    const uint32_t rows = uint32_t(warp_row[w + 1] - warp_row[w]);
     const long long per_slot = (long long)(g.nb_cifs) * g.n_streams;
+    const int gid = groups[w];
+    const int slot_k = gid / groups_per_slot;
+    const long long j = (long long)(gid - slot_k * groups_per_slot) * 32 + lane;
     const int s = int(j % g.n_streams);
     const int c = int(j / g.n_streams);
     const bool is_fic = g.fic_enabled && slot_k == 0;
@@ -260,7 +262,7 @@ ens_viterbi_lanes_kernel(EnsGeom g, const int8_t* __restrict__ bits, size_t stre
                     if (sd.overflow) *nbytes = -1;
                     // CIF_Deinterleaver::Deinterleave refuses until 16 CIFs were consumed (cif_deinterleaver.cpp:40-43)
                     else if (stored[size_t(s) * g.max_subs + k] + c + 1 < ENS_DEINT_DEPTH) *nbytes = 0;
-                    else if (schedules[sd.schedule].total_steps <= slot_steps[slot_k]) {
+                    else if (schedules[sd.schedule].total_steps <= rows) {
                         active = true;
                         sch = schedules + sd.schedule;
                         soft = deint + (size_t(s) * g.nb_cifs + c) * size_t(g.cif_pitch) + size_t(sd.start_cu) * 64u;
@@ -271,8 +273,7 @@ ens_viterbi_lanes_kernel(EnsGeom g, const int8_t* __restrict__ bits, size_t stre
         }
     }
     EnsView view{soft, out, prbs};
-    uint2* dec = scratch + (size_t(slot_row[slot_k]) + size_t(wj) * slot_steps[slot_k]) * 32u;
-    const uint64_t err = viterbi_lane_trellis(sch, view, dec, lane, active);
+    const uint64_t err = viterbi_lane_trellis(sch, view, scratch + size_t(warp_row[w]) * 32u, lane, active);
     if (!active) return;
     if (is_fic) {
         const int fib_bytes = g.fib_group_bytes / g.nb_fibs_per_cif;
@@ -396,11 +397,10 @@ struct Ensemble {
     DeviceBuffer<uint8_t> d_prbs, d_fib_bytes, d_fib_valid, d_msc_bytes;
     DeviceBuffer<uint2> d_scratch;
     // one-trellis-per-thread form (ens_viterbi_lanes_kernel): decision rows per slot
-    int warps_per_slot = 0;
-    std::vector<unsigned long long> lane_slot_row;   // [jobs_per_cif + 1] first row of each slot's warps
-    std::vector<uint32_t> lane_slot_steps;           // [jobs_per_cif] rows per warp
-    DeviceBuffer<unsigned long long> d_slot_row;
-    DeviceBuffer<uint32_t> d_slot_steps;
+    int groups_per_slot = 0;
+    VitlPlan lane_plan;
+    DeviceBuffer<int32_t> d_groups;
+    DeviceBuffer<unsigned long long> d_warp_row;
     DeviceBuffer<uint2> d_lane_scratch;
     uint64_t launches = 0;
 };
@@ -457,20 +457,21 @@ static int upload_tables(Ensemble* e) {
     e->window_steps = std::min(cap_steps, std::max((window + 31u) & ~31u, 32u));
     e->scratch_steps = (longest + 31u) & ~31u;
     if (e->n_long > 0) DAB_CUDA_CHECK(e->d_scratch.reserve(size_t(e->n_long) * g.nb_cifs * g.n_streams * e->scratch_steps));
-    e->warps_per_slot = int((size_t(g.nb_cifs) * size_t(g.n_streams) + 31) / 32);
-    e->lane_slot_steps.assign(size_t(std::max(e->jobs_per_cif, 1)), 0u);
-    e->lane_slot_row.assign(size_t(e->jobs_per_cif) + 1, 0ull);
-    for (int sk = 0; sk < e->jobs_per_cif; sk++) {
-        const bool fic = g.fic_enabled && sk == 0;
-        const uint32_t st = fic ? e->schedules[0].total_steps : slot_steps[size_t(sk - (g.fic_enabled ? 1 : 0))];
-        const uint32_t rows = std::max(8u, (st + 1u) & ~1u);
-        e->lane_slot_steps[size_t(sk)] = rows;
-        e->lane_slot_row[size_t(sk) + 1] = e->lane_slot_row[size_t(sk)] + (unsigned long long)(e->warps_per_slot) * rows;
+    e->groups_per_slot = int((size_t(g.nb_cifs) * size_t(g.n_streams) + 31) / 32);
+    {
+        std::vector<uint32_t> cost(size_t(e->jobs_per_cif) * size_t(e->groups_per_slot), 0u);
+        for (int sk = 0; sk < e->jobs_per_cif; sk++) {
+            const bool fic = g.fic_enabled && sk == 0;
+            const uint32_t st = fic ? e->schedules[0].total_steps : slot_steps[size_t(sk - (g.fic_enabled ? 1 : 0))];
+            for (int q = 0; q < e->groups_per_slot; q++) cost[size_t(sk) * size_t(e->groups_per_slot) + size_t(q)] = st;
+        }
+        vitl_plan(cost, e->lane_plan);
     }
-    DAB_CUDA_CHECK(e->d_slot_row.reserve(e->lane_slot_row.size()));
-    DAB_CUDA_CHECK(e->d_slot_steps.reserve(e->lane_slot_steps.size()));
-    DAB_CUDA_CHECK(cudaMemcpyAsync(e->d_slot_row.ptr, e->lane_slot_row.data(), e->lane_slot_row.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, e->stream));
-    DAB_CUDA_CHECK(cudaMemcpyAsync(e->d_slot_steps.ptr, e->lane_slot_steps.data(), e->lane_slot_steps.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    const VitlPlan& lp = e->lane_plan;
+    DAB_CUDA_CHECK(e->d_groups.reserve(std::max<size_t>(lp.groups.size(), 1)));
+    DAB_CUDA_CHECK(e->d_warp_row.reserve(lp.warp_row.size()));
+    DAB_CUDA_CHECK(cudaMemcpyAsync(e->d_groups.ptr, lp.groups.data(), lp.groups.size() * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    DAB_CUDA_CHECK(cudaMemcpyAsync(e->d_warp_row.ptr, lp.warp_row.data(), lp.warp_row.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, e->stream));
     DAB_CUDA_CHECK(e->d_schedules.reserve(std::max<size_t>(e->schedules.size(), 64)));
     DAB_CUDA_CHECK(cudaMemcpyAsync(e->d_schedules.ptr, e->schedules.data(), e->schedules.size() * sizeof(DevSchedule), cudaMemcpyHostToDevice, e->stream));
     DAB_CUDA_CHECK(cudaMemcpyAsync(e->d_subs.ptr, e->h_subs.data(), e->h_subs.size() * sizeof(SubDesc), cudaMemcpyHostToDevice, e->stream));
@@ -497,13 +498,11 @@ static int decode_device(Ensemble* e, const int8_t* d_bits, size_t stream_stride
     }
     const long long total_jobs = (long long)(e->jobs_per_cif) * g.nb_cifs * g.n_streams;
     if (e->jobs_per_cif > 0 && vitl_use_lanes(total_jobs)) {
-        DAB_CUDA_CHECK(e->d_lane_scratch.reserve(size_t(e->lane_slot_row.back()) * 32u));
+        DAB_CUDA_CHECK(e->d_lane_scratch.reserve(size_t(e->lane_plan.rows()) * 32u));
         EnsOut o{e->d_fib_bytes.ptr, e->d_fib_valid.ptr, e->d_fic_error.ptr, e->d_msc_bytes.ptr, e->d_msc_nbytes.ptr, e->d_msc_error.ptr};
-        const unsigned grid = unsigned(e->warps_per_slot) * unsigned(e->jobs_per_cif);
-        ens_viterbi_lanes_kernel<<<grid, VITL_THREADS, 0, e->stream>>>(g, d_bits, stream_stride, d_frames_in_call, slot, e->d_deint.ptr,
-                                                                       e->d_subs.ptr, e->d_stored.ptr, e->d_schedules.ptr, e->d_prbs.ptr, o,
-                                                                       e->warps_per_slot, e->d_slot_row.ptr, e->d_slot_steps.ptr,
-                                                                       e->d_lane_scratch.ptr);
+        ens_viterbi_lanes_kernel<<<unsigned(e->lane_plan.n_warps()), VITL_THREADS, 0, e->stream>>>(
+            g, d_bits, stream_stride, d_frames_in_call, slot, e->d_deint.ptr, e->d_subs.ptr, e->d_stored.ptr, e->d_schedules.ptr, e->d_prbs.ptr, o,
+            e->groups_per_slot, e->d_groups.ptr, e->d_warp_row.ptr, e->d_lane_scratch.ptr);
         e->launches++;
     } else if (e->jobs_per_cif > 0) {
         const size_t smem = size_t(VIT_WARPS_PER_CTA) * (size_t(e->window_steps) * sizeof(uint2) + sizeof(DevSchedule));

@@ -18,6 +18,7 @@
 //     otherwise they stream to a global scratch in 256-byte rows and are paged back per window for the traceback.
 //   * traceback walks the 8-bit register of ViterbiTracebackBuffer<7> (state = reg >> 2) from shared memory.
 #include <algorithm>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -78,18 +79,21 @@ viterbi_kernel(const int8_t* __restrict__ soft, size_t soft_bytes, const dab_vit
     }
 }
 
-// The bulk form: one trellis per thread (viterbi_lanes.cuh).  Thread i decodes job order[i] (order == nullptr: job i); the
-// host sorts `order` by schedule so that the 32 trellises of a warp walk the same puncturing schedule in lock step.
+// The bulk form: one trellis per thread (viterbi_lanes.cuh).  Warp w runs group groups[w]: the 32 jobs order[32 g + lane]
+// (order == nullptr: job 32 g + lane).  The host orders the jobs by schedule so that the 32 trellises of a group walk the same
+// puncturing schedule in lock step, and launches the longest groups first (vitl_plan).  Decision rows of warp w start at row
+// warp_row[w] of the scratch.
 __global__ void __maxnreg__(VITL_MAX_REGS)
 viterbi_lanes_kernel(const int8_t* __restrict__ soft, size_t soft_bytes, const dab_vit_job* __restrict__ jobs, int n_jobs,
-                     const int32_t* __restrict__ order, const DevSchedule* __restrict__ schedules, int n_schedules,
-                     uint8_t* __restrict__ out, size_t out_bytes, uint64_t* __restrict__ path_error, int32_t* __restrict__ job_status,
-                     uint2* __restrict__ scratch, uint32_t scratch_steps) {
+                     const int32_t* __restrict__ order, const int32_t* __restrict__ groups, const unsigned long long* __restrict__ warp_row,
+                     const DevSchedule* __restrict__ schedules, int n_schedules, uint8_t* __restrict__ out, size_t out_bytes,
+                     uint64_t* __restrict__ path_error, int32_t* __restrict__ job_status, uint2* __restrict__ scratch) {
     const int lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * VITL_THREADS + threadIdx.x;
-    const size_t warp_global = size_t(slot) >> 5;
+    const int w = blockIdx.x * (VITL_THREADS / 32) + (threadIdx.x >> 5);
+    const uint32_t rows = uint32_t(warp_row[w + 1] - warp_row[w]);
+    const long long slot = (long long)(groups[w]) * 32 + lane;
     int job_index = -1;
-    if (slot < n_jobs) job_index = order ? order[slot] : slot;
+    if (slot < n_jobs) job_index = order ? order[slot] : int(slot);
     int status = DAB_OK;
     dab_vit_job job{};
     const DevSchedule* sch = schedules;
@@ -101,12 +105,12 @@ viterbi_lanes_kernel(const int8_t* __restrict__ soft, size_t soft_bytes, const d
             if (sch->soft_symbols > job.n_soft || job.soft_offset + sch->soft_symbols > soft_bytes) status = DAB_ERR_UNDERRUN;
             else if (sch->n_out_bits + 6u > sch->total_steps) status = DAB_ERR_TRACEBACK;
             else if (job.out_offset + sch->n_out_bits / 8u > out_bytes) status = DAB_ERR_CAPACITY;
-            else if (sch->total_steps > scratch_steps) status = DAB_ERR_CAPACITY;
+            else if (sch->total_steps > rows) status = DAB_ERR_CAPACITY;
         }
     }
     const bool active = job_index >= 0 && status == DAB_OK;
     PlainView view{soft + job.soft_offset, out + job.out_offset};
-    const uint64_t err = viterbi_lane_trellis(sch, view, scratch + warp_global * size_t(scratch_steps) * 32u, lane, active);
+    const uint64_t err = viterbi_lane_trellis(sch, view, scratch + size_t(warp_row[w]) * 32u, lane, active);
     if (job_index >= 0) {
         if (path_error) path_error[job_index] = active ? err : 0;
         if (job_status) job_status[job_index] = status;
@@ -128,8 +132,20 @@ struct Viterbi {
     DeviceBuffer<uint64_t> d_error;
     DeviceBuffer<int32_t> d_status;
     DeviceBuffer<uint2> d_scratch;
-    DeviceBuffer<int32_t> d_order;
-    std::vector<int32_t> order;
+    // job orders / warp plans of the bulk form: slot 0 is rebuilt by every call that brings its own job list, the others belong
+    // to dab_viterbi_prepare_jobs
+    struct Prepared {
+        bool used = false;
+        int n_jobs = 0;
+        uint32_t max_steps = 0;
+        bool has_order = false;
+        int n_warps = 0;
+        unsigned long long rows = 0;
+        DeviceBuffer<dab_vit_job> d_jobs;
+        DeviceBuffer<int32_t> d_order, d_groups;
+        DeviceBuffer<unsigned long long> d_warp_row;
+    };
+    std::vector<std::unique_ptr<Prepared>> prepared;
     int max_smem_optin = 0;
     int oneshot_slot = -1;  // schedule slot reused by dab_viterbi_decode_one
     uint64_t launches = 0;
@@ -157,40 +173,8 @@ static uint32_t pick_window(const Viterbi* v, uint32_t max_steps, size_t* smem_b
     return window;
 }
 
-static int launch_lanes(Viterbi* v, const int8_t* d_soft, size_t soft_bytes, const dab_vit_job* d_jobs, const dab_vit_job* host_jobs,
-                        int n_jobs, uint32_t max_steps, uint8_t* d_out, size_t out_bytes, uint64_t* d_error, int32_t* d_status) {
-    const uint32_t scratch_steps = std::max(8u, (max_steps + 1u) & ~1u);
-    const size_t n_warps = (size_t(n_jobs) + 31) / 32;
-    DAB_CUDA_CHECK(v->d_scratch.reserve(n_warps * size_t(scratch_steps) * 32u));
-    const int32_t* d_order = nullptr;
-    if (host_jobs) {
-        // lanes of a warp should walk the same schedule: order the jobs by schedule (stable, so neighbours stay neighbours)
-        bool mixed = false;
-        for (int i = 1; i < n_jobs && !mixed; i++) mixed = host_jobs[i].schedule != host_jobs[0].schedule;
-        if (mixed) {
-            v->order.resize(size_t(n_jobs));
-            for (int i = 0; i < n_jobs; i++) v->order[size_t(i)] = i;
-            std::stable_sort(v->order.begin(), v->order.end(), [&](int32_t a, int32_t b) { return host_jobs[a].schedule < host_jobs[b].schedule; });
-            DAB_CUDA_CHECK(v->d_order.reserve(size_t(n_jobs)));
-            DAB_CUDA_CHECK(cudaMemcpyAsync(v->d_order.ptr, v->order.data(), size_t(n_jobs) * sizeof(int32_t), cudaMemcpyHostToDevice, v->stream));
-            d_order = v->d_order.ptr;
-        }
-    }
-    const int grid = (n_jobs + VITL_THREADS - 1) / VITL_THREADS;
-    viterbi_lanes_kernel<<<grid, VITL_THREADS, 0, v->stream>>>(d_soft, soft_bytes, d_jobs, n_jobs, d_order, v->d_schedules.ptr,
-                                                              int(v->schedules.size()), d_out, out_bytes, d_error, d_status,
-                                                              v->d_scratch.ptr, scratch_steps);
-    v->launches++;
-    DAB_CUDA_CHECK(cudaGetLastError());
-    return DAB_OK;
-}
-
-static int launch(Viterbi* v, const int8_t* d_soft, size_t soft_bytes, const dab_vit_job* d_jobs, const dab_vit_job* host_jobs, int n_jobs,
-                  uint32_t max_steps, uint8_t* d_out, size_t out_bytes, uint64_t* d_error, int32_t* d_status) {
-    if (n_jobs <= 0) return DAB_OK;
-    int rc = upload_schedules(v);
-    if (rc != DAB_OK) return rc;
-    if (vitl_use_lanes(n_jobs)) return launch_lanes(v, d_soft, soft_bytes, d_jobs, host_jobs, n_jobs, max_steps, d_out, out_bytes, d_error, d_status);
+static int launch_warps(Viterbi* v, const int8_t* d_soft, size_t soft_bytes, const dab_vit_job* d_jobs, int n_jobs, uint32_t max_steps,
+                        uint8_t* d_out, size_t out_bytes, uint64_t* d_error, int32_t* d_status) {
     size_t smem = 0;
     const uint32_t window = pick_window(v, max_steps, &smem);
     uint32_t scratch_steps = 0;
@@ -206,6 +190,78 @@ static int launch(Viterbi* v, const int8_t* d_soft, size_t soft_bytes, const dab
     v->launches++;
     DAB_CUDA_CHECK(cudaGetLastError());
     return DAB_OK;
+}
+
+
+// Order the jobs (when the host can see them) and plan the warps of the bulk form into `p`.
+static int plan_lanes(Viterbi* v, Viterbi::Prepared* p, const dab_vit_job* host_jobs, int n_jobs, uint32_t max_steps) {
+    const int n_groups = (n_jobs + 31) / 32;
+    std::vector<uint32_t> cost(static_cast<size_t>(n_groups), max_steps);
+    p->has_order = false;
+    if (host_jobs) {
+        auto steps_of = [&](int32_t j) { return host_jobs[j].schedule < v->schedules.size() ? v->schedules[host_jobs[j].schedule].total_steps : 0u; };
+        bool mixed = false;
+        for (int i = 1; i < n_jobs && !mixed; i++) mixed = host_jobs[i].schedule != host_jobs[0].schedule;
+        std::vector<int32_t> order(static_cast<size_t>(n_jobs));
+        for (int i = 0; i < n_jobs; i++) order[size_t(i)] = i;
+        if (mixed) {
+            // longest schedules first, equal schedules together (stable: neighbouring jobs stay neighbours)
+            std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+                const uint32_t sa = steps_of(a), sb = steps_of(b);
+                return sa != sb ? sa > sb : host_jobs[a].schedule < host_jobs[b].schedule;
+            });
+            DAB_CUDA_CHECK(p->d_order.reserve(size_t(n_jobs)));
+            DAB_CUDA_CHECK(cudaMemcpyAsync(p->d_order.ptr, order.data(), size_t(n_jobs) * sizeof(int32_t), cudaMemcpyHostToDevice, v->stream));
+            p->has_order = true;
+        }
+        for (int g = 0; g < n_groups; g++) {
+            uint32_t c = 0;
+            for (int i = 32 * g; i < std::min(n_jobs, 32 * g + 32); i++) c = std::max(c, steps_of(order[size_t(i)]));
+            cost[size_t(g)] = c;
+        }
+    }
+    VitlPlan plan;
+    vitl_plan(cost, plan);
+    p->n_jobs = n_jobs;
+    p->max_steps = max_steps;
+    p->n_warps = plan.n_warps();
+    p->rows = plan.rows();
+    DAB_CUDA_CHECK(p->d_groups.reserve(std::max<size_t>(plan.groups.size(), 1)));
+    DAB_CUDA_CHECK(p->d_warp_row.reserve(plan.warp_row.size()));
+    DAB_CUDA_CHECK(cudaMemcpyAsync(p->d_groups.ptr, plan.groups.data(), plan.groups.size() * sizeof(int32_t), cudaMemcpyHostToDevice, v->stream));
+    DAB_CUDA_CHECK(cudaMemcpyAsync(p->d_warp_row.ptr, plan.warp_row.data(), plan.warp_row.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, v->stream));
+    DAB_CUDA_CHECK(cudaStreamSynchronize(v->stream));   // the sources are local vectors
+    return DAB_OK;
+}
+
+static int launch_lanes(Viterbi* v, const Viterbi::Prepared* p, const int8_t* d_soft, size_t soft_bytes, const dab_vit_job* d_jobs,
+                        uint8_t* d_out, size_t out_bytes, uint64_t* d_error, int32_t* d_status) {
+    DAB_CUDA_CHECK(v->d_scratch.reserve(size_t(p->rows) * 32u));
+    viterbi_lanes_kernel<<<p->n_warps, VITL_THREADS, 0, v->stream>>>(d_soft, soft_bytes, d_jobs, p->n_jobs, p->has_order ? p->d_order.ptr : nullptr,
+                                                                    p->d_groups.ptr, p->d_warp_row.ptr, v->d_schedules.ptr,
+                                                                    int(v->schedules.size()), d_out, out_bytes, d_error, d_status, v->d_scratch.ptr);
+    v->launches++;
+    DAB_CUDA_CHECK(cudaGetLastError());
+    return DAB_OK;
+}
+
+static int launch(Viterbi* v, const int8_t* d_soft, size_t soft_bytes, const dab_vit_job* d_jobs, const dab_vit_job* host_jobs, int n_jobs,
+                  uint32_t max_steps, uint8_t* d_out, size_t out_bytes, uint64_t* d_error, int32_t* d_status) {
+    if (n_jobs <= 0) return DAB_OK;
+    int rc = upload_schedules(v);
+    if (rc != DAB_OK) return rc;
+    if (vitl_use_lanes(n_jobs)) {
+        if (v->prepared.empty()) v->prepared.emplace_back(new Viterbi::Prepared());
+        Viterbi::Prepared* p = v->prepared[0].get();
+        // a device-resident job list (host_jobs == nullptr) of the same shape as last time keeps its plan
+        if (host_jobs || !p->used || p->n_jobs != n_jobs || p->max_steps != max_steps || p->has_order) {
+            rc = plan_lanes(v, p, host_jobs, n_jobs, max_steps);
+            if (rc != DAB_OK) return rc;
+            p->used = true;
+        }
+        return launch_lanes(v, p, d_soft, soft_bytes, d_jobs, d_out, out_bytes, d_error, d_status);
+    }
+    return launch_warps(v, d_soft, soft_bytes, d_jobs, n_jobs, max_steps, d_out, out_bytes, d_error, d_status);
 }
 
 static uint32_t max_steps_of(const Viterbi* v, const dab_vit_job* jobs, int n_jobs, int* bad) {
@@ -364,6 +420,56 @@ int dab_viterbi_decode_one(dab_viterbi* h, const dab_vit_schedule* s, const int8
     int32_t st = 0;
     rc = dab_viterbi_decode_batch(h, soft, n_soft, &job, 1, out, s->n_out_bytes, path_error, &st);
     return rc;
+}
+
+int dab_viterbi_prepare_jobs(dab_viterbi* h, const dab_vit_job* jobs, int n_jobs) {
+    auto* v = reinterpret_cast<Viterbi*>(h);
+    if (!v) return set_error(DAB_ERR_INVALID, "null handle");
+    if (!jobs || n_jobs <= 0) return set_error(DAB_ERR_INVALID, "empty job list");
+    std::lock_guard<std::mutex> lock(v->mtx);
+    DAB_CUDA_CHECK(cudaSetDevice(v->device));
+    int bad = -1;
+    const uint32_t max_steps = max_steps_of(v, jobs, n_jobs, &bad);
+    if (bad >= 0) return set_error(DAB_ERR_INVALID, "job %d names unknown schedule %u", bad, jobs[bad].schedule);
+    int rc = upload_schedules(v);
+    if (rc != DAB_OK) return rc;
+    if (v->prepared.empty()) v->prepared.emplace_back(new Viterbi::Prepared());   // slot 0 stays with the ad-hoc calls
+    size_t id = 1;
+    while (id < v->prepared.size() && v->prepared[id]->used) id++;
+    if (id == v->prepared.size()) v->prepared.emplace_back(new Viterbi::Prepared());
+    Viterbi::Prepared* p = v->prepared[id].get();
+    DAB_CUDA_CHECK(p->d_jobs.reserve(size_t(n_jobs)));
+    DAB_CUDA_CHECK(cudaMemcpyAsync(p->d_jobs.ptr, jobs, size_t(n_jobs) * sizeof(dab_vit_job), cudaMemcpyHostToDevice, v->stream));
+    rc = plan_lanes(v, p, jobs, n_jobs, max_steps);   // synchronises: `jobs` is free again on return
+    if (rc != DAB_OK) return rc;
+    p->used = true;
+    return int(id);
+}
+
+int dab_viterbi_decode_prepared(dab_viterbi* h, int plan, const int8_t* d_soft, size_t soft_bytes, uint8_t* d_out, size_t out_bytes,
+                                uint64_t* d_path_error, int32_t* d_job_status) {
+    auto* v = reinterpret_cast<Viterbi*>(h);
+    if (!v) return set_error(DAB_ERR_INVALID, "null handle");
+    if (!d_soft || !d_out) return set_error(DAB_ERR_INVALID, "null buffer");
+    std::lock_guard<std::mutex> lock(v->mtx);
+    if (plan < 1 || size_t(plan) >= v->prepared.size() || !v->prepared[size_t(plan)]->used) return set_error(DAB_ERR_INVALID, "unknown job plan %d", plan);
+    DAB_CUDA_CHECK(cudaSetDevice(v->device));
+    Viterbi::Prepared* p = v->prepared[size_t(plan)].get();
+    int rc = upload_schedules(v);
+    if (rc != DAB_OK) return rc;
+    if (vitl_use_lanes(p->n_jobs)) return launch_lanes(v, p, d_soft, soft_bytes, p->d_jobs.ptr, d_out, out_bytes, d_path_error, d_job_status);
+    return launch_warps(v, d_soft, soft_bytes, p->d_jobs.ptr, p->n_jobs, p->max_steps, d_out, out_bytes, d_path_error, d_job_status);
+}
+
+int dab_viterbi_release_jobs(dab_viterbi* h, int plan) {
+    auto* v = reinterpret_cast<Viterbi*>(h);
+    if (!v) return set_error(DAB_ERR_INVALID, "null handle");
+    std::lock_guard<std::mutex> lock(v->mtx);
+    if (plan < 1 || size_t(plan) >= v->prepared.size() || !v->prepared[size_t(plan)]->used) return set_error(DAB_ERR_INVALID, "unknown job plan %d", plan);
+    DAB_CUDA_CHECK(cudaSetDevice(v->device));
+    DAB_CUDA_CHECK(cudaStreamSynchronize(v->stream));
+    v->prepared[size_t(plan)].reset(new Viterbi::Prepared());
+    return DAB_OK;
 }
 
 int dab_viterbi_sync(dab_viterbi* h) {

@@ -76,6 +76,17 @@ class ViterbiBatch:
         capi.check(self.L.dab_viterbi_decode_jobs_device(self.h, d_soft, soft_bytes, d_jobs, n_jobs, max_steps, d_out, out_bytes, d_err,
                                                          d_status))
 
+    def prepare_jobs(self, jobs):
+        """Upload + order + pack a job list that will be decoded repeatedly; returns the plan id."""
+        jobs = np.ascontiguousarray(jobs)
+        return capi.check(self.L.dab_viterbi_prepare_jobs(self.h, capi.ptr(jobs), jobs.size))
+
+    def decode_prepared(self, plan, d_soft, soft_bytes, d_out, out_bytes, d_err=None, d_status=None):
+        capi.check(self.L.dab_viterbi_decode_prepared(self.h, plan, d_soft, soft_bytes, d_out, out_bytes, d_err, d_status))
+
+    def release_jobs(self, plan):
+        capi.check(self.L.dab_viterbi_release_jobs(self.h, plan))
+
     def sync(self):
         capi.check(self.L.dab_viterbi_sync(self.h))
 

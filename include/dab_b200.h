@@ -261,6 +261,15 @@ DAB_API int dab_viterbi_decode_batch_device(dab_viterbi* h, const int8_t* d_soft
 DAB_API int dab_viterbi_decode_jobs_device(dab_viterbi* h, const int8_t* d_soft, size_t soft_bytes, const dab_vit_job* d_jobs,
                                            int n_jobs, uint32_t max_steps, uint8_t* d_out, size_t out_bytes,
                                            uint64_t* d_path_error, int32_t* d_job_status);
+/* A job list that is decoded again and again (the sub-channel layout of an ensemble changes rarely): uploads the jobs once,
+ * orders them so that the 32 trellises a warp runs in lock step share a puncturing schedule, and launches the longest trellises
+ * first so that the short ones (FIC groups next to 1.5-kbit sub-channel trellises) fill the gaps at the end of the launch instead
+ * of delaying a long one.  Returns a plan id >= 1.  dab_viterbi_decode_prepared is asynchronous on the handle's stream; soft bits, output,
+ * path errors and job status are device pointers laid out as the jobs' offsets say. */
+DAB_API int dab_viterbi_prepare_jobs(dab_viterbi* h, const dab_vit_job* jobs, int n_jobs);
+DAB_API int dab_viterbi_decode_prepared(dab_viterbi* h, int plan, const int8_t* d_soft, size_t soft_bytes, uint8_t* d_out, size_t out_bytes,
+                                        uint64_t* d_path_error, int32_t* d_job_status);
+DAB_API int dab_viterbi_release_jobs(dab_viterbi* h, int plan);
 /* One trellis with an ad-hoc schedule (what the streaming reset/update/chainback mirror class issues on chainback) */
 DAB_API int dab_viterbi_decode_one(dab_viterbi* h, const dab_vit_schedule* s, const int8_t* soft, size_t n_soft, uint8_t* out,
                                    uint64_t* path_error);

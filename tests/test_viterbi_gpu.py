@@ -240,3 +240,48 @@ def test_bulk_batch_default_dispatch(pkg, oracle, monkeypatch):
         assert np.array_equal(results[""][0][off:off + nb], ref_out), i
         assert int(results[""][1][i]) == ref_err, i
     vb.close()
+
+
+def test_prepared_jobs_pack_short_trellises(pkg, oracle, monkeypatch):
+    """dab_viterbi_prepare_jobs / decode_prepared: a job list uploaded once (long EEP trellises and half-length FIC groups
+    interleaved, so that FIC groups share warps), device buffers in and out; every job equals dab_viterbi_decode_batch, in both
+    kernel forms, across repeated calls"""
+    import torch
+    v = importlib.import_module("dab-radio_b200.viterbi")
+    rng = np.random.default_rng(321)
+    specs = [(FIC, 96), (EEP_3A_48CU, 192)]
+    base = [[_make_case(oracle, rng, sp, nb, sigma) for sigma in (0, 70, 130) for _ in range(3)] for sp, nb in specs]
+    n = 4608
+    vb = v.ViterbiBatch(0)
+    sids = [vb.add_schedule(v.make_schedule(_segments(oracle, sp), nb)) for sp, nb in specs]
+    jobs = np.zeros(n, v.capi.VIT_JOB_DTYPE)
+    chunks, soft_off, out_off = [], 0, 0
+    for i in range(n):
+        k = 0 if i % 3 == 0 else 1
+        rx = base[k][int(rng.integers(0, len(base[k])))][1].copy()
+        rx[rng.integers(0, rx.size, 6)] = rng.integers(-128, 128, 6).astype(np.int8)
+        jobs[i] = (sids[k], rx.size, soft_off, out_off)
+        chunks.append(rx)
+        soft_off += rx.size
+        out_off += specs[k][1]
+    soft = np.concatenate(chunks)
+    monkeypatch.setenv("DAB_B200_VITERBI_LANES", "0")
+    want_out, want_err, st = vb.decode_batch(soft, jobs, out_off)
+    assert np.all(st == 0)
+    d_soft = torch.from_numpy(soft).cuda()
+    plan = vb.prepare_jobs(jobs)
+    assert plan >= 1
+    for form in ("1", "0", "1"):
+        monkeypatch.setenv("DAB_B200_VITERBI_LANES", form)
+        d_out = torch.zeros(out_off, dtype=torch.uint8, device="cuda")
+        d_err = torch.zeros(n, dtype=torch.int64, device="cuda")
+        d_st = torch.full((n,), -99, dtype=torch.int32, device="cuda")
+        vb.decode_prepared(plan, d_soft.data_ptr(), d_soft.numel(), d_out.data_ptr(), d_out.numel(), d_err.data_ptr(), d_st.data_ptr())
+        vb.sync()
+        assert int(d_st.abs().max().item()) == 0
+        assert np.array_equal(d_out.cpu().numpy(), want_out), form
+        assert np.array_equal(d_err.cpu().numpy().view(np.uint64), want_err), form
+    vb.release_jobs(plan)
+    with pytest.raises(v.capi.DabError):
+        vb.decode_prepared(plan, d_soft.data_ptr(), d_soft.numel(), d_out.data_ptr(), d_out.numel())
+    vb.close()
