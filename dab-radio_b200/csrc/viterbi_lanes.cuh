@@ -251,9 +251,9 @@ __device__ __forceinline__ uint64_t viterbi_lane_trellis(const DevSchedule* sch,
 #pragma unroll
                 for (int k = 1; k < 32; k++) m2 = __vminu2(m2, out[k]);
                 const uint32_t mn = vitl_min_halves(m2);
-                const uint32_t mn2 = mn | (mn << 16);
+                const uint32_t nmn2 = ((0u - mn) & 0xFFFFu) * 0x00010001u;   // (-mn, -mn): no half goes below zero, mn is the minimum
 #pragma unroll
-                for (int k = 0; k < 32; k++) out[k] = __vsub2(out[k], mn2);
+                for (int k = 0; k < 32; k++) out[k] = __vadd2(out[k], nmn2);
                 renorm_acc += mn;
                 new0 -= mn;
             }
