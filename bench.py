@@ -572,8 +572,8 @@ def modes_leg(torch, pkg, n_streams, steps):
     ofdm = importlib.import_module("dab-radio_b200.ofdm")
     W = 6
     res = {"note": "frames_per_stream_per_step < 1 in Modes II / III is the reference's own behaviour, reproduced bit for bit (parity tests, "
-                   "config 5): its null detector looks at 100 samples out of every 500 and misses the 664 / 345-sample NULL symbol for "
-                   "most start offsets, so those streams stay in the (slower) acquisition path"}
+                   "config 5; the CPU oracle shows the same lock failures on such streams): its power-dip frame detector does not lock most "
+                   "Mode II / III streams of this synthetic set, which then stay in the acquisition path (FindNullPowerDip over whole blocks)"}
 
     def make(mode, n, block):
         fl = MODE_FRAME_LEN[mode]

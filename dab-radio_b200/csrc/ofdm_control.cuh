@@ -137,6 +137,37 @@ struct Control {
         __syncthreads();
     }
 
+    // The same for FindNullPowerDip, which scans whole blocks while a stream is unlocked: a warp takes 8 consecutive windows at a
+    // time and walks them together, so that 8 independent loads are in flight per lane.  One window after the other costs a full
+    // memory latency per window (~1 us), which made a single unlocked stream the long pole of a 1024-stream step (1.5 - 2.3 ms).
+    // Per window the order of the additions is the same as above (lane-strided partial sums, then the butterfly), so the averages
+    // are bit-identical.
+    __device__ void l1_windows_contiguous(int64_t first, int K, int count) {
+        constexpr int U = 8;
+        const int lane = tid & 31, warp = tid >> 5, n_warps = THREADS / 32;
+        for (int w = warp * U; w < count; w += n_warps * U) {
+            const int64_t base = first + int64_t(w) * K + lane;
+            float acc[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) acc[u] = 0.0f;
+            for (int i = lane; i < K; i += 32) {
+                float2 v[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) v[u] = (w + u < count) ? sample(base + (i - lane) + int64_t(u) * K) : make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int u = 0; u < U; u++) acc[u] += fabsf(v[u].x) + fabsf(v[u].y);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                float a = acc[u];
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, d);
+                if (lane == 0 && w + u < count) l1buf[w + u] = a / float(K);
+            }
+        }
+        __syncthreads();
+    }
+
     // ---- UpdateSignalAverage (ofdm_demodulator.cpp:934-950): the per-window L1 averages of this call were computed by
     // ofdm_l1_windows_kernel (all streams, all windows in parallel); only the sequential exponential average is left
     __device__ void update_signal_average() {
@@ -180,7 +211,7 @@ struct Control {
         __syncthreads();
         for (int64_t w0 = 0; w0 < n_windows; w0 += CTRL_L1_BATCH) {
             const int count = int(min(int64_t(CTRL_L1_BATCH), n_windows - w0));
-            l1_windows(c0 + w0 * K, K, K, count);
+            l1_windows_contiguous(c0 + w0 * K, K, count);
             if (tid == 0) {
                 const float start_thresh = st.l1_average * st.cfg.null_l1_thresh_null_start;
                 const float end_thresh = st.l1_average * st.cfg.null_l1_thresh_null_end;
