@@ -526,28 +526,30 @@ static int deliver(Ofdm* o) {
         const WayRange r = way_range(o, w, ways);
         DAB_CUDA_CHECK(cudaEventSynchronize(o->counts_ready[w]));
         size_t k = first_k[size_t(w)];
-        // device source of frame (s, f) is (s * slots + f) * fb: frames of consecutive streams are contiguous when every
-        // stream filled all of its slots, which is the steady state with one-frame blocks
-        size_t run_src = 0, run_dst = 0, run_len = 0;
+        // device source of frame (s, f) is (s * slots + f) * fb, host destination (callback order: stream, then frame) is k * fb.
+        // Consecutive streams that completed the same number of frames c form a run whose frame f goes down as ONE pitched copy
+        // (rows of fb bytes, source pitch slots * fb, destination pitch c * fb): one copy per way in the steady state instead of
+        // one per stream -- 1024 separate 230 KB copies cost 6.7 ms of set-up per step, more than the transfer itself.
         cudaStream_t down = (ways > 1) ? o->down_stream : r.st;  // counts_ready[w] (synchronised above) follows the way's kernels
-        auto flush = [&]() -> int {
-            if (run_len) DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_bits.ptr + run_dst, o->bits.ptr + run_src, run_len, cudaMemcpyDeviceToHost, down));
-            run_len = 0;
-            return DAB_OK;
-        };
-        for (int s = r.lo; s < r.hi; s++)
-            for (int f = 0; f < o->h_frames.ptr[s]; f++, k++) {
-                const size_t src = (size_t(s) * slots + size_t(f)) * fb, dst = k * fb;
-                if (run_len && src == run_src + run_len && dst == run_dst + run_len) {
-                    run_len += fb;
-                } else {
-                    int rc = flush();
-                    if (rc != DAB_OK) return rc;
-                    run_src = src; run_dst = dst; run_len = fb;
+        for (int s0 = r.lo; s0 < r.hi;) {
+            const int c = o->h_frames.ptr[s0];
+            int s1 = s0 + 1;
+            while (s1 < r.hi && o->h_frames.ptr[s1] == c) s1++;
+            if (c > 0) {
+                const size_t rows = size_t(s1 - s0);
+                for (int f = 0; f < c; f++) {
+                    const int8_t* src = o->bits.ptr + (size_t(s0) * slots + size_t(f)) * fb;
+                    int8_t* dst = o->h_bits.ptr + (k + size_t(f)) * fb;
+                    if (size_t(c) == slots && c == 1) {
+                        DAB_CUDA_CHECK(cudaMemcpyAsync(dst, src, rows * fb, cudaMemcpyDeviceToHost, down));
+                    } else {
+                        DAB_CUDA_CHECK(cudaMemcpy2DAsync(dst, size_t(c) * fb, src, slots * fb, fb, rows, cudaMemcpyDeviceToHost, down));
+                    }
                 }
+                k += rows * size_t(c);
             }
-        int rc = flush();
-        if (rc != DAB_OK) return rc;
+            s0 = s1;
+        }
         first_k[size_t(w) + 1] = k;
         DAB_CUDA_CHECK(cudaEventRecord(o->bits_ready[w], down));
         // the previous way's soft bits arrived while this way was uploading / computing: hand them over now
