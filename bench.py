@@ -340,10 +340,67 @@ def run_ours(args):
         del host
         return out
 
+    def full_chain_leg():
+        """Raw 8-bit IQ in pinned host memory -> decoded FIBs + sub-channel bytes in pinned host memory, per call: upload,
+        demodulate (dab_ofdm_process_batch_u8, soft bits stay in HBM), decode (dab_ensemble_decode_frames_device: FIC + 18 x EEP 3-A
+        48 CU sub-channels = a full Mode I ensemble), download only the decoded bytes and CRC flags.  The synthetic IQ carries
+        random payload, so the decoded bytes are not checked here (tests/test_ensemble_gpu.py::test_demod_to_bytes_on_device checks
+        the chain against the oracle); the work per frame does not depend on the payload."""
+        from cuda.bindings import runtime as cudart
+        ens = importlib.import_module("dab-radio_b200.ensemble")
+        src = torch.view_as_real(iq[:, :FRAME_LEN])
+        host = torch.empty((n_streams, FRAME_LEN, 2), dtype=torch.uint8).pin_memory()
+        host.copy_(torch.clamp(src * 127.5 + 127.5, 0.0, 255.0).to(torch.uint8))
+        torch.cuda.synchronize()
+        d = ofdm.OfdmDemodBatch(MODE, n_streams=n_streams, device=local_rank, max_block_samples=FRAME_LEN, raw_u8=True)
+        d.set_cuda_stream(work_stream.cuda_stream)
+        d.disable_callback()
+        dec = ens.EnsembleDecoder(1, n_streams=n_streams, device=local_rank, max_subchannels=18)
+        dec.set_cuda_stream(work_stream.cuda_stream)
+        dec.set_subchannels(-1, [ens.subchannel(48 * k, 48, 0, 0, 2, 0) for k in range(18)])
+        res = dec.device_results()
+        sizes = {"msc_bytes": n_streams * res.nb_cifs * res.msc_cif_bytes, "fib_bytes": n_streams * res.nb_cifs * res.fib_group_bytes,
+                 "fib_valid": n_streams * res.nb_cifs * res.nb_fibs_per_cif, "msc_nbytes": n_streams * res.nb_cifs * res.max_subchannels * 4}
+        h_out = {k: torch.empty(v, dtype=torch.uint8).pin_memory() for k, v in sizes.items()}
+        p, n = d.pointer_arrays([host[s].data_ptr() for s in range(n_streams)], [FRAME_LEN] * n_streams)
+        d_bits, n_bits, slots, d_fic = d.device_bits()
+
+        def step():
+            d.process_batch_prepared(p, n, True)
+            d.join()
+            for slot in range(slots):
+                dec.decode_frames_device(d_bits + slot * n_bits, slots * n_bits, d_fic, slot)
+            r = dec.device_results()
+            for k in sizes:
+                (err,) = cudart.cudaMemcpyAsync(h_out[k].data_ptr(), getattr(r, k), sizes[k], cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost,
+                                                work_stream.cuda_stream)
+                assert int(err) == 0, err
+            work_stream.synchronize()
+
+        for _ in range(max(W, 5)):
+            step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            step()
+        dt = time.perf_counter() - t0
+        dt_max = aggregate(dt * 1e3, 0, world, dist)[0] * 1e-3
+        nbytes = h_out["msc_nbytes"].view(torch.int32)
+        out = {"value": round(world * n_streams * FRAME_LEN * K / dt_max / 1e6, 1), "unit": "MSamples/s",
+               "ensemble_frames_per_s": round(world * n_streams * K / dt_max, 1), "realtime_ensembles": round(world * n_streams * K / dt_max * 0.096, 1),
+               "ms_per_step": round(dt_max / K * 1e3, 3), "h2d_bytes_per_step": int(n_streams * FRAME_LEN * 2),
+               "d2h_bytes_per_step": int(sum(sizes.values())), "subchannel_cifs_decoded_last_step": int((nbytes > 0).sum().item()),
+               "api": "dab_ofdm_process_batch_u8 (pinned host uint8 IQ) -> dab_ensemble_decode_frames_device -> decoded bytes to pinned host memory"}
+        dec.close()
+        d.close()
+        del host
+        return out
+
     e2e = None
     if not args.no_e2e:
         e2e = e2e_leg(False)
         e2e["raw_u8_ingest"] = e2e_leg(True)   # SURVEY 8(f) rank 1: raw 8-bit IQ uploaded and dequantised on the device
+        e2e["raw_u8_to_decoded_bytes"] = full_chain_leg()   # SURVEY 8(f) ranks 1-3 chained: IQ in, FIBs + sub-channel bytes out
 
     # ------------------------------------------------------------------ Viterbi (secondary line; rank 0, N = 1 only)
     viterbi = None
