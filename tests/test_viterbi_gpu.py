@@ -285,3 +285,36 @@ def test_prepared_jobs_pack_short_trellises(pkg, oracle, monkeypatch):
     with pytest.raises(v.capi.DabError):
         vb.decode_prepared(plan, d_soft.data_ptr(), d_soft.numel(), d_out.data_ptr(), d_out.numel())
     vb.close()
+
+
+def test_start_and_end_state(vit, oracle):
+    """reset(start_state) / chainback(end_state) other than 0 (DAB_Viterbi_Decoder::reset, ::chainback arguments), states on both
+    sides of 32 (the two halves of a packed metric register), noisy input"""
+    rng = np.random.default_rng(55)
+    segs = _segments(oracle, [(8, 128 * 6), (0, 24)])
+    nb = ((128 * 6 + 24) // 4 - 6) // 8   # 192 decoded bits = all 198 trellis steps minus the tail
+    vb = vit.ViterbiBatch(0)
+    cases = []
+    jobs = np.zeros(12, vit.capi.VIT_JOB_DTYPE)
+    chunks, soft_off = [], 0
+    for i, (start, end) in enumerate([(0, 0), (5, 0), (37, 0), (63, 0), (0, 9), (0, 41), (0, 63), (17, 50), (33, 2), (62, 31), (1, 32), (32, 1)]):
+        sid = vb.add_schedule(vit.make_schedule(segs, nb, start_state=start, end_state=end))
+        n_soft = sum(int(np.resize(c, n // 4).astype(np.int64).sum()) for c, n in segs)
+        rx = rng.integers(-128, 128, n_soft).astype(np.int8)
+        jobs[i] = (sid, rx.size, soft_off, i * nb)
+        chunks.append(rx)
+        soft_off += rx.size
+        cases.append((start, end, rx))
+    out, err, st = vb.decode_batch(np.concatenate(chunks), jobs, len(cases) * nb)
+    assert np.all(st == 0)
+    o = oracle.OracleViterbi()
+    o.set_traceback_length(nb * 8)
+    for i, (start, end, rx) in enumerate(cases):
+        o.reset(start)
+        used = 0
+        for code, n_out in segs:
+            used += o.update(rx[used:], code, n_out)
+        ref_out, ref_err = o.chainback(nb, end)
+        assert np.array_equal(out[i * nb:(i + 1) * nb], ref_out), (i, start, end)
+        assert int(err[i]) == ref_err, (i, start, end)
+    vb.close()
