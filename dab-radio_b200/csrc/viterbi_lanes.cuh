@@ -37,7 +37,7 @@ namespace dabb200 {
 
 constexpr int VITL_THREADS = 32;              // one warp per CTA: the finest grain the block scheduler can balance
 constexpr int VITL_MAX_REGS = 128;            // 4 warps per scheduler (16384 registers each): 96 would buy a fifth warp at the price of spills
-constexpr int VITL_TB_BYTES = 6;               // traceback: decoded bytes (x 8 decision rows) buffered per lane
+constexpr int VITL_TB_BYTES = 5;               // traceback: decoded bytes (x 8 decision rows) buffered per lane
 constexpr uint32_t VITL_CAREFUL = 58000;      // < 65535 - 1020 - 6 * 1020: below this no metric can be near saturation
 
 // Batches of at least this many trellises run one trellis per thread; smaller ones one per warp (viterbi_core.cuh), which
