@@ -282,8 +282,17 @@ def run_ours(args):
     frame_ms = kt["frame_ms"][0] / max(1, kt["frame_launches"][0])
     achieved = ALGO_BYTES_PER_FRAME * n_streams * frames_per_stream / K / (frame_ms * 1e-3) / 1e9 if frame_ms > 0 else 0.0
     kernel_ms_total = sum(kt["frame_ms"]) + sum(kt["control_ms"])
+    # DRAM traffic of the same kernel from the committed ncu --set full capture, scaled to the frames of one timed launch
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)["ofdm_frame_v3_kernel<2048>"]
+        traffic = int((t["dram_bytes_read"] + t["dram_bytes_write"]) / t["frames_in_launch"] * n_streams * frames_per_stream / K)
+        traffic_src = t["source"]
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"bound": "hbm", "kernel": "ofdm_frame_v3_kernel<2048>", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel_ms_per_launch": round(frame_ms, 4), "algorithmic_bytes_per_launch": int(ALGO_BYTES_PER_FRAME * n_streams),
                 "timed": "separate pass of the same K steps with DAB_B200_PIPELINE_WAYS=1 (every kernel alone on the stream)",
                 "serial_ms_per_step": round(serial_ms / K, 4),
