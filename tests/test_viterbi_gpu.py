@@ -318,3 +318,62 @@ def test_start_and_end_state(vit, oracle):
         assert np.array_equal(out[i * nb:(i + 1) * nb], ref_out), (i, start, end)
         assert int(err[i]) == ref_err, (i, start, end)
     vb.close()
+
+
+def test_every_protection_profile_both_forms(pkg, oracle, monkeypatch):
+    """all 64 UEP rows, EEP 1-A..4-A and 1-B..4-B at several sizes (incl. the 2-A n = 1 special case) and the FIC schedule, 70
+    trellises of each in one bulk call, random soft bits: the one-trellis-per-thread form equals the one-trellis-per-warp form
+    job by job (bytes and path error), and one trellis of every profile equals the oracle"""
+    v = importlib.import_module("dab-radio_b200.viterbi")
+    ens = importlib.import_module("dab-radio_b200.ensemble")
+    rng = np.random.default_rng(2024)
+    subs = [(ens.subchannel(0, oracle.uep_subchannel_size(i), True, i), oracle.subchannel(0, oracle.uep_subchannel_size(i), True, i)) for i in range(64)]
+    for type_b, mult in ((False, (12, 8, 6, 4)), (True, (27, 21, 18, 15))):
+        for level in range(4):
+            for n in (1, 2, 5):
+                L = mult[level] * n
+                subs.append((ens.subchannel(0, L, False, 0, level, type_b), oracle.subchannel(0, L, False, 0, level, type_b)))
+    vb = v.ViterbiBatch(0)
+    profiles = []   # (schedule id, n_soft, n_out_bytes, oracle segments)
+    for sg, so in subs:
+        sch, n_soft = ens.subchannel_schedule(sg)
+        if sch.n_out_bytes == 0:
+            continue
+        profiles.append((vb.add_schedule(sch), n_soft, int(sch.n_out_bytes), oracle.msc_segments(so)))
+    profiles.append((vb.add_schedule(v.fic_schedule()), 2304, 96, _segments(oracle, FIC)))
+    reps = 70
+    n = len(profiles) * reps
+    assert n >= 4096
+    jobs = np.zeros(n, v.capi.VIT_JOB_DTYPE)
+    soft_off = out_off = 0
+    meta = []
+    order = rng.permutation(n)            # profiles interleaved at random: the library has to group them itself
+    for i in order:
+        sid, n_soft, nb, segs = profiles[i % len(profiles)]
+        jobs[i] = (sid, n_soft, soft_off, out_off)
+        meta.append((i, soft_off, n_soft, out_off, nb, segs))
+        soft_off += n_soft
+        out_off += nb
+    soft = rng.integers(-128, 128, soft_off).astype(np.int8)
+    soft[rng.random(soft_off) < 0.5] //= 4   # mix of confident and weak symbols
+    res = {}
+    for form in ("0", "1"):
+        monkeypatch.setenv("DAB_B200_VITERBI_LANES", form)
+        out, err, st = vb.decode_batch(soft, jobs, out_off)
+        assert np.all(st == 0)
+        res[form] = (out, err)
+    assert np.array_equal(res["0"][0], res["1"][0])
+    assert np.array_equal(res["0"][1], res["1"][1])
+    o = oracle.OracleViterbi()
+    seen = set()
+    for i, s_off, n_soft, o_off, nb, segs in meta:
+        k = i % len(profiles)
+        if k in seen:
+            continue
+        seen.add(k)
+        o.set_traceback_length(sum(nn for _, nn in segs) // 4)
+        ref_out, ref_err, used = o.decode_job(soft[s_off:s_off + n_soft], segs, nb)
+        assert np.array_equal(res["1"][0][o_off:o_off + nb], ref_out), k
+        assert int(res["1"][1][i]) == ref_err, k
+    assert len(seen) == len(profiles)
+    vb.close()
