@@ -162,7 +162,8 @@ def build_streams_on_device(torch, n_streams, n_frames, seed, mode=None, frame_l
     g = torch.Generator(device="cuda")
     g.manual_seed(seed)
     starts = rng.integers(0, frame_len, n_streams)
-    cfo_bins = rng.integers(-4800, 4801, n_streams)          # x Fs/frame_len = 10.4 Hz: +-50 kHz
+    max_bin = 4800 * frame_len // FRAME_LEN                   # x Fs/frame_len: +-50 kHz in every mode (10.4 Hz steps in Mode I)
+    cfo_bins = rng.integers(-max_bin, max_bin + 1, n_streams)
     choice = rng.integers(0, POOL_FRAMES, (n_streams, n_frames + 1))
     chunk = 16
     ar = torch.arange(total, device="cuda", dtype=torch.int64)
