@@ -72,6 +72,7 @@ struct Ofdm {
     // link serves the ways first-in first-out (copies queued on the way streams themselves share the link and all finish last)
     cudaStream_t up_stream = nullptr, down_stream = nullptr;
     cudaEvent_t fork_event = nullptr;
+    std::vector<dab_ofdm_config> cfgs;  // per-stream configuration as last set by the caller (survives init_states)
     bool ways_pending = false;          // way streams carry work the handle's stream has not been ordered after yet
     // device memory
     DeviceBuffer<unsigned char> ring_iq;
@@ -566,11 +567,18 @@ static int deliver(Ofdm* o) {
 }
 
 static int init_states(Ofdm* o) {
+    // the configuration is the caller's (OFDM_Demod::GetConfig() is mutable state of the object, not of a run): it survives a
+    // re-initialisation of the stream states, e.g. attaching device-resident streams after dab_ofdm_set_config
+    if (o->cfgs.size() != size_t(o->n_streams)) {
+        o->cfgs.resize(size_t(o->n_streams));
+        for (auto& c : o->cfgs) dab_ofdm_default_config(&c);
+    }
     std::vector<StreamState> init(size_t(o->n_streams));
-    for (auto& st : init) {
+    for (size_t s = 0; s < init.size(); s++) {
+        StreamState& st = init[s];
         memset(&st, 0, sizeof(st));
         st.state = DAB_OFDM_FINDING_NULL_POWER_DIP;
-        dab_ofdm_default_config(&st.cfg);
+        st.cfg = o->cfgs[s];
     }
     DAB_CUDA_CHECK(cudaMemcpy(o->states.ptr, init.data(), init.size() * sizeof(StreamState), cudaMemcpyHostToDevice));
     DAB_CUDA_CHECK(cudaMemset(o->null_ring.ptr, 0, o->null_ring.count * sizeof(float2)));
@@ -789,8 +797,10 @@ int dab_ofdm_set_config(dab_ofdm* h, int stream, const dab_ofdm_config* cfg) {
     if (!cfg || stream < -1 || stream >= o->n_streams) return set_error(DAB_ERR_INVALID, "bad stream / config");
     DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
     const int lo = (stream < 0) ? 0 : stream, hi = (stream < 0) ? o->n_streams : stream + 1;
-    for (int s = lo; s < hi; s++)
+    for (int s = lo; s < hi; s++) {
+        if (size_t(s) < o->cfgs.size()) o->cfgs[size_t(s)] = *cfg;
         DAB_CUDA_CHECK(cudaMemcpy(reinterpret_cast<char*>(o->states.ptr + s) + offsetof(StreamState, cfg), cfg, sizeof(*cfg), cudaMemcpyHostToDevice));
+    }
     return DAB_OK;
 }
 

@@ -122,38 +122,23 @@ struct Control {
     }
 
     // ---- CalculateL1Average (ofdm_demodulator.cpp:922-932) of `count` windows of K samples, window w at first + w * step
+    // L1 averages of `count` windows of K samples, window w starting at first + w * step, into l1buf.  A warp takes 8 windows at
+    // a time and walks them together, so that 8 independent loads are in flight per lane: one window after the other costs a
+    // full memory latency per window (~1 us), which made a single unlocked stream (FindNullPowerDip scans whole blocks) or a
+    // non-default signal_l1 configuration (more windows than the precomputed buffer holds) the long pole of a 1024-stream step
+    // (1.5 - 2.3 ms).  Per window the additions keep their order (lane-strided partial sums, then the butterfly).
     __device__ void l1_windows(int64_t first, int step, int K, int count) {
-        const int lane = tid & 31, warp = tid >> 5, n_warps = THREADS / 32;
-        for (int w = warp; w < count; w += n_warps) {
-            float acc = 0.0f;
-            for (int i = lane; i < K; i += 32) {
-                const float2 v = sample(first + int64_t(w) * step + i);
-                acc += fabsf(v.x) + fabsf(v.y);
-            }
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
-            if (lane == 0) l1buf[w] = acc / float(K);
-        }
-        __syncthreads();
-    }
-
-    // The same for FindNullPowerDip, which scans whole blocks while a stream is unlocked: a warp takes 8 consecutive windows at a
-    // time and walks them together, so that 8 independent loads are in flight per lane.  One window after the other costs a full
-    // memory latency per window (~1 us), which made a single unlocked stream the long pole of a 1024-stream step (1.5 - 2.3 ms).
-    // Per window the order of the additions is the same as above (lane-strided partial sums, then the butterfly), so the averages
-    // are bit-identical.
-    __device__ void l1_windows_contiguous(int64_t first, int K, int count) {
         constexpr int U = 8;
         const int lane = tid & 31, warp = tid >> 5, n_warps = THREADS / 32;
         for (int w = warp * U; w < count; w += n_warps * U) {
-            const int64_t base = first + int64_t(w) * K + lane;
+            const int64_t base = first + int64_t(w) * step;
             float acc[U];
 #pragma unroll
             for (int u = 0; u < U; u++) acc[u] = 0.0f;
             for (int i = lane; i < K; i += 32) {
                 float2 v[U];
 #pragma unroll
-                for (int u = 0; u < U; u++) v[u] = (w + u < count) ? sample(base + (i - lane) + int64_t(u) * K) : make_float2(0.0f, 0.0f);
+                for (int u = 0; u < U; u++) v[u] = (w + u < count) ? sample(base + int64_t(u) * step + i) : make_float2(0.0f, 0.0f);
 #pragma unroll
                 for (int u = 0; u < U; u++) acc[u] += fabsf(v[u].x) + fabsf(v[u].y);
             }
@@ -211,7 +196,7 @@ struct Control {
         __syncthreads();
         for (int64_t w0 = 0; w0 < n_windows; w0 += CTRL_L1_BATCH) {
             const int count = int(min(int64_t(CTRL_L1_BATCH), n_windows - w0));
-            l1_windows_contiguous(c0 + w0 * K, K, count);
+            l1_windows(c0 + w0 * K, K, K, count);
             if (tid == 0) {
                 const float start_thresh = st.l1_average * st.cfg.null_l1_thresh_null_start;
                 const float end_thresh = st.l1_average * st.cfg.null_l1_thresh_null_end;

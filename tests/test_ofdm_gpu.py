@@ -293,3 +293,50 @@ def test_full_size_batch_of_1024_streams(ofdm, oracle):
             assert gi["frame_start"] == wi["frame_start"] and gi["fine_offset_after"] == wi["fine_offset_after"]
             assert np.array_equal(gb, wb), f"stream {s} differs from its base stream {s % n_base}"
     d.close()
+
+
+@pytest.mark.parametrize("mode,block,start,cfo_hz", [(3, 49152, 4321, 333.0), (3, 4096, 30000, -47000.0), (2, 49152, 100, 20000.0), (1, 196608, 50001, 5000.0)])
+def test_signal_average_config_is_honoured(ofdm, oracle, mode, block, start, cfo_hz):
+    """OFDM_Demod_Config::signal_l1 (ofdm_demodulator.h:24-31) away from its defaults: 25-sample windows, every second one -- the
+    setting under which the reference's power-dip detector also catches the short NULL symbols of Modes II / III when fed whole
+    frames.  Window averages, EMA, null search thresholds and everything downstream must follow the oracle."""
+    x = dabgen.make_stream(mode, 8, seed=5, cfo_hz=cfo_hz, start=start, snr_db=25.0)
+    o = oracle.OracleOfdmDemod(mode)
+    o.config.signal_l1_nb_samples = 25
+    o.config.signal_l1_nb_decimate = 2
+    d = ofdm.OfdmDemodBatch(mode, n_streams=1, max_block_samples=max(block, 4096))
+    cfg = d.get_config(0)
+    cfg.signal_l1_nb_samples = 25
+    cfg.signal_l1_nb_decimate = 2
+    d.set_config(cfg)
+    for off in range(0, x.size, block):
+        o.process(x[off:off + block])
+        d.process(0, x[off:off + block])
+    _assert_stream_parity(oracle, mode, o, d, min_frames=5)
+    d.close()
+
+
+def test_config_survives_attaching_device_streams(ofdm, oracle):
+    """dab_ofdm_set_config before dab_ofdm_attach_device_streams: attaching re-initialises the receive state but the configuration
+    is the caller's (OFDM_Demod::GetConfig()).  Mode III, whole-frame blocks: locks only with the 25-sample windows"""
+    torch = _torch()
+    mode, block = 3, 49152
+    x = dabgen.make_stream(mode, 8, seed=5, cfo_hz=333.0, start=4321, snr_db=25.0)
+    o = oracle.OracleOfdmDemod(mode)
+    o.config.signal_l1_nb_samples = 25
+    o.config.signal_l1_nb_decimate = 2
+    o.process_blocks(x, block)
+    assert o.frames_done() >= 5
+    d = ofdm.OfdmDemodBatch(mode, n_streams=1, max_block_samples=block)
+    cfg = d.get_config(0)
+    cfg.signal_l1_nb_samples = 25
+    cfg.signal_l1_nb_decimate = 2
+    d.set_config(cfg)
+    t = torch.from_numpy(x.view(np.float32)).cuda()
+    d.attach_device_streams(t.data_ptr(), x.size, x.size)
+    assert d.get_config(0).signal_l1_nb_samples == 25
+    for off in range(0, x.size - block + 1, block):
+        d.advance_uniform(block)
+    d.sync()
+    _assert_stream_parity(oracle, mode, o, d, min_frames=5)
+    d.close()
