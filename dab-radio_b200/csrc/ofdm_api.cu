@@ -801,6 +801,16 @@ int dab_ofdm_set_config(dab_ofdm* h, int stream, const dab_ofdm_config* cfg) {
         if (size_t(s) < o->cfgs.size()) o->cfgs[size_t(s)] = *cfg;
         DAB_CUDA_CHECK(cudaMemcpy(reinterpret_cast<char*>(o->states.ptr + s) + offsetof(StreamState, cfg), cfg, sizeof(*cfg), cudaMemcpyHostToDevice));
     }
+    // the precomputed window averages of UpdateSignalAverage (ofdm_l1_windows_kernel) must cover a whole call under this
+    // configuration too, otherwise every stream evaluates its windows inside the control kernel
+    if (cfg->signal_l1_nb_samples > 0 && cfg->signal_l1_nb_decimate > 0) {
+        const size_t step = size_t(cfg->signal_l1_nb_samples) * size_t(cfg->signal_l1_nb_decimate);
+        const size_t need = std::min<size_t>(o->max_block / step + 2, size_t(1) << 20);
+        if (need > size_t(o->l1_windows_stride)) {
+            DAB_CUDA_CHECK(o->l1_windows.reserve(size_t(o->n_streams) * need));
+            o->l1_windows_stride = int(need);
+        }
+    }
     return DAB_OK;
 }
 
