@@ -410,7 +410,10 @@ def run_ours(args):
     if not args.no_e2e:
         e2e = e2e_leg(False)
         e2e["raw_u8_ingest"] = e2e_leg(True)   # raw 8-bit IQ uploaded and dequantised on the device
-        e2e["raw_u8_to_decoded_bytes"] = full_chain_leg()   # SURVEY 8(f) ranks 1-3 chained: IQ in, FIBs + sub-channel bytes out
+        try:   # SURVEY 8(f) ranks 1-3 chained: IQ in, FIBs + sub-channel bytes out (a secondary line must not take the headline down)
+            e2e["raw_u8_to_decoded_bytes"] = full_chain_leg()
+        except Exception as ex:  # noqa: BLE001
+            e2e["raw_u8_to_decoded_bytes"] = {"unavailable": repr(ex)}
 
     # ------------------------------------------------------------------ Viterbi (secondary line; rank 0, N = 1 only)
     viterbi = None
@@ -419,9 +422,15 @@ def run_ours(args):
         del iq
         torch.cuda.empty_cache()
         viterbi = viterbi_leg(torch, pkg, n_streams, 5, not args.no_cpu)
-        viterbi["ensemble"] = ensemble_leg(torch, pkg, n_streams, 5, not args.no_cpu)
+        try:
+            viterbi["ensemble"] = ensemble_leg(torch, pkg, n_streams, 5, not args.no_cpu)
+        except Exception as ex:  # noqa: BLE001
+            viterbi["ensemble"] = {"unavailable": repr(ex)}
         torch.cuda.empty_cache()
-        modes = modes_leg(torch, pkg, n_streams, 8)
+        try:
+            modes = modes_leg(torch, pkg, n_streams, 8)
+        except Exception as ex:  # noqa: BLE001
+            modes = {"unavailable": repr(ex)}
 
     # ------------------------------------------------------------------ cpu baseline (rank 0, N = 1 only)
     cpu = None
