@@ -1,11 +1,6 @@
-// Stand-in for the reference's src/ofdm/ofdm_params.h (field-for-field the same struct; layout shared with dab_ofdm_params).
+// Stand-in for the reference's src/ofdm/ofdm_params.h for builds OUTSIDE its tree: OFDM_Params is the C ABI's dab_ofdm_params
+// (include/dab_b200.h, same fields in the same order), so the two never drift apart.  Inside the reference tree its own header
+// is found first and ofdm_demodulator.cpp checks that the layouts agree.
 #pragma once
-#include <stddef.h>
-struct OFDM_Params {
-    size_t nb_frame_symbols;
-    size_t nb_symbol_period;
-    size_t nb_null_period;
-    size_t nb_cyclic_prefix;
-    size_t nb_fft;
-    size_t nb_data_carriers;
-};
+#include "dab_b200.h"
+using OFDM_Params = dab_ofdm_params;
