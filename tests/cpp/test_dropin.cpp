@@ -19,6 +19,7 @@
 #include "dab/fic/fic_decoder.h"
 #include "dab/msc/msc_decoder.h"
 #include "ofdm/ofdm_helpers.h"
+#include "dab_b200.h"
 
 static std::vector<char> slurp(const char* path) {
     std::ifstream f(path, std::ios::binary);

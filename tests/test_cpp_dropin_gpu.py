@@ -15,8 +15,17 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def dropin(pkg, tmp_path_factory):
+@pytest.fixture(scope="module", params=["mirror_classes", "reference_callers_on_mirrors"])
+def dropin(pkg, tmp_path_factory, request):
+    """the driver binary in two builds: (1) every class from dab-radio_b200/cpp, compiled here; (2) oracle/_ref/dropin_ref_callers
+    (make -C oracle refcallers, built where /root/reference exists): the REFERENCE's unchanged FIC_Decoder / MSC_Decoder /
+    CIF_Deinterleaver / table code / Create_OFDM_Demodulator on top of the mirror OFDM_Demod and DAB_Viterbi_Decoder, overlaid as
+    INTEGRATION.md section 2 describes -- the same caller code, the same expected outputs"""
+    if request.param == "reference_callers_on_mirrors":
+        exe = os.path.join(ROOT, "oracle", "_ref", "dropin_ref_callers")
+        if not os.path.exists(exe):
+            pytest.skip("oracle/_ref/dropin_ref_callers not built (needs /root/reference at build time)")
+        return exe
     out = str(tmp_path_factory.mktemp("dropin") / "test_dropin")
     cpp = os.path.join(ROOT, "dab-radio_b200", "cpp")
     cmd = ["g++", "-std=c++20", "-O2", "-I", os.path.join(ROOT, "include"), "-I", cpp, "-I", os.path.join(cpp, "standalone"),
