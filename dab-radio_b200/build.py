@@ -65,7 +65,7 @@ def build(force=False, verbose=False, extra_flags=()):
     if failed:
         raise RuntimeError("nvcc failed:\n" + "\n".join(f"{s}:\n{o}" for s, o in failed))
     if force or procs or _stale(OUT, objs):
-        cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+        cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"]
         subprocess.check_call(cmd)
     return OUT
 

@@ -67,7 +67,7 @@ OFDM_Demod::OFDM_Demod(const OFDM_Params& params, const tcb::span<const std::com
     m_max_block = size_t(1) << 20;
     opt.max_block_samples = m_max_block;
     opt.keep_debug_taps = g_gui_taps ? 1 : 0;
-    opt.raw_u8_ingest = 0;
+    opt.sample_format = DAB_IQ_F32;
     int status = DAB_OK;
     m_handle = dab_ofdm_create(&p, reinterpret_cast<const dab_c32*>(prs_fft_ref.data()), carrier_mapper.data(), &opt, &status);
     if (!m_handle) fail("OFDM_Demod: dab_ofdm_create", status);  // no CPU fallback: a missing B200 is a hard error

@@ -28,6 +28,20 @@ int set_error(int status, const char* fmt, ...);
 // Selects the device and refuses anything that is not Blackwell sm_100: there is no fallback path.
 int select_device(int device);
 
+// Restores the caller's current CUDA device when a library call returns (a single-process multi-GPU host such as PyTorch must
+// not find its current device switched by a call into this library).
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 template <typename T>
 struct DeviceBuffer {
     T* ptr = nullptr;

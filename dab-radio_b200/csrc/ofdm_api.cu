@@ -9,24 +9,14 @@
 #include <mutex>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 #include "ofdm_control.cuh"
 #include "ofdm_frame.cuh"
-#include "ofdm_frame_dab.cuh"
 #include "ofdm_frame_v3.cuh"
 
 namespace dabb200 {
-
-__global__ void ofdm_begin_call_kernel(StreamState* states, const uint64_t* n_per_stream, uint64_t n_uniform, int n_streams) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_streams) return;
-    StreamState& st = states[s];
-    const uint64_t n = n_per_stream ? n_per_stream[s] : n_uniform;
-    st.call_begin = st.call_end;
-    st.call_end = st.call_begin + int64_t(n);
-    st.call_needs_average = (n > 0) ? 1 : 0;
-    st.frames_in_call = 0;
-}
 
 __global__ void ofdm_reset_stream_kernel(StreamState* states, int stream) {
     // OFDM_Demod::Reset (ofdm_demodulator.cpp:277-289)
@@ -41,22 +31,34 @@ __global__ void ofdm_reset_stream_kernel(StreamState* states, int stream) {
     st.fine_time_offset = 0;
 }
 
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 struct Ofdm {
     dab_ofdm_params p{};
     int nfft = 0;
     int n_streams = 0;
     int device = 0;
-    bool raw_u8 = false;
+    int format = DAB_IQ_F32;
+    int sb = 8;                         // bytes per complex sample in the stream buffers
+    SampleFmt fmt{};
     bool debug_taps = false;
     size_t max_block = 0;
     size_t ring_samples = 0;
     size_t max_pitch = 1u << 30;        // cudaDeviceProp::memPitch bound for pitched copies (set at create)
-    int slots = 1;
+    int slots = 1;                      // frames a stream can complete in one call
+    int ring_slots = 2;                 // soft-bit buffers per stream (slots + 1: the frame being received owns one)
     size_t frame_bits = 0;
-    int syms_per_chunk = 25;
-    int frame_min_blocks = 3;           // DAB_B200_FRAME_MIN_BLOCKS: resident CTAs per SM the frame kernel is compiled for (3 or 4)
-    int frame_kernel_version = 3;       // DAB_B200_FRAME_KERNEL=2: the previous register-prefetch kernel (A/B runs)
+    int syms_per_chunk = 26;            // DAB_B200_SYMS_PER_CHUNK: target symbols per frame-kernel work item
+    int n_chunks = 3;                   // work items per dispatch
+    bool eager = false;                 // DAB_B200_EAGER=1: demodulate the symbols of a frame in the call they arrive in (see DESIGN.md:
+                                        // two half-size frame launches per step cost more than the window re-reads they save)
+    bool frame_owns_l1 = true;          // DAB_B200_FRAME_L1=0: the control kernel sums every UpdateSignalAverage window itself
     bool force_generic_kernel = false;  // DAB_B200_GENERIC_FRAME_KERNEL=1: run the generic-geometry frame kernel (tests)
+    bool dab_geometry = false;          // the v3 kernel applies
+    uint32_t call_index = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     // pipeline ways: the streams of a handle are split into `ways` contiguous groups, each sequenced on its own CUDA stream, so
@@ -82,7 +84,7 @@ struct Ofdm {
     DeviceBuffer<StreamState> states;
     DeviceBuffer<FrameDesc> descs, stage_descs;
     DeviceBuffer<dab_ofdm_frame_info> infos;
-    DeviceBuffer<int32_t> frames_in_call;
+    DeviceBuffer<int32_t> frames_in_call, frame_slots;
     DeviceBuffer<int8_t> bits;
     DeviceBuffer<int16_t> bin_to_pos, bin_to_carrier;
     DeviceBuffer<uint64_t> d_n;
@@ -93,19 +95,31 @@ struct Ofdm {
     std::vector<uint64_t> fed;       // samples handed to each stream so far
     std::vector<uint64_t> n_call;
     PinnedBuffer<uint64_t> h_n;
-    PinnedBuffer<int32_t> h_frames;
+    PinnedBuffer<int32_t> h_frames, h_frame_slots;
     PinnedBuffer<dab_ofdm_frame_info> h_infos;
     PinnedBuffer<int8_t> h_bits;
     dab_ofdm_frame_cb cb = nullptr;
     void* cb_user = nullptr;
     uint64_t launches = 0;
+    // host snapshot behind the scalar / small-array getters: refreshed at the end of every synchronous process call, read under
+    // snap_mtx only -- a GUI thread polling GetState() never waits for a Process() in flight on the reader thread
+    static constexpr int SNAP_ARRAYS_MAX_STREAMS = 4;   // response / frame-bit snapshots only for handles this small (the mirror class)
+    PinnedBuffer<StreamState> h_states;
+    PinnedBuffer<float> h_resp;         // [n_streams][2][nfft]: impulse response, coarse frequency response
+    std::mutex snap_mtx;
+    bool snap_valid = false;
+    std::vector<dab_ofdm_state> snap;
+    std::vector<int32_t> snap_pending_slot;
+    std::vector<float> snap_resp;
+    std::vector<int8_t> snap_bits;      // [n_streams][frame_bits]: last frame delivered through the callback
+    std::vector<uint8_t> snap_bits_valid;
     // optional per-kernel event timing (roofline measurement)
     bool timing = false;
     struct TimedLaunch { cudaEvent_t start, stop; int pass; bool is_frame; };
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
     dab_ofdm_kernel_times times{};
-    std::mutex mtx;
+    std::recursive_mutex mtx;
 };
 
 static cudaEvent_t take_event(Ofdm* o) {
@@ -198,74 +212,61 @@ static FrameGeom frame_geom(const Ofdm* o) {
     g.symbol_period = int(o->p.nb_symbol_period);
     g.cyclic_prefix = int(o->p.nb_cyclic_prefix);
     g.n_carriers = int(o->p.nb_data_carriers);
-    g.syms_per_chunk = o->syms_per_chunk;
-    g.n_chunks = (g.n_symbols - 1 + g.syms_per_chunk - 1) / g.syms_per_chunk;
+    g.fmt = o->fmt;
     g.bin_to_pos = o->bin_to_pos.ptr;
     g.bin_to_carrier = o->bin_to_carrier.ptr;
     g.twiddles = o->twiddles.ptr;
     return g;
 }
 
-template <int NFFT, bool RAW>
-static int launch_frame_t(Ofdm* o, cudaStream_t st, const FrameDesc* d_descs, int n_frames) {
+template <int NFFT, int SB>
+static int launch_frame_t(Ofdm* o, cudaStream_t st, const FrameDesc* d_descs, int n_items) {
     const FrameGeom g = frame_geom(o);
-    if (DabGeom<NFFT>::matches(g.symbol_period, g.cyclic_prefix, g.n_carriers) && !o->force_generic_kernel && o->frame_kernel_version >= 3) {
+    if (o->dab_geometry && !o->force_generic_kernel) {
         // the four DAB transmission modes, TMA-fed kernel with the separable PLL (ofdm_frame_v3.cuh)
-        constexpr size_t smem = FrameV3Smem<NFFT, RAW>::TOTAL_BYTES;
-        constexpr int GROUPS = FrameV3Smem<NFFT, RAW>::GROUPS;
-        const int n_items = n_frames * g.n_chunks;
+        constexpr size_t smem = FrameV3Smem<NFFT, SB>::TOTAL_BYTES;
+        constexpr int GROUPS = FrameV3Smem<NFFT, SB>::GROUPS;
         const int grid = (n_items + GROUPS - 1) / GROUPS;
         if (o->debug_taps) {
-            DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_v3_kernel<NFFT, RAW, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            ofdm_frame_v3_kernel<NFFT, RAW, true, 3><<<grid, FRAME_CTA_THREADS, smem, st>>>(g, d_descs, n_frames);
+            DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_v3_kernel<NFFT, SB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            ofdm_frame_v3_kernel<NFFT, SB, true><<<grid, FRAME_CTA_THREADS, smem, st>>>(g, d_descs, n_items);
         } else {
-            DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_v3_kernel<NFFT, RAW, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            ofdm_frame_v3_kernel<NFFT, RAW, false, 3><<<grid, FRAME_CTA_THREADS, smem, st>>>(g, d_descs, n_frames);
-        }
-        o->launches++;
-        DAB_CUDA_CHECK(cudaGetLastError());
-        return DAB_OK;
-    }
-    if (DabGeom<NFFT>::matches(g.symbol_period, g.cyclic_prefix, g.n_carriers) && !o->force_generic_kernel) {
-        // the four DAB transmission modes: geometry known at compile time
-        constexpr size_t smem = FrameDabSmem<NFFT>::TOTAL_BYTES;
-        constexpr int GROUPS = FrameDabSmem<NFFT>::GROUPS;
-        const int n_items = n_frames * g.n_chunks;
-        const int grid = (n_items + GROUPS - 1) / GROUPS;
-        if (o->frame_min_blocks == 3) {
-            DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_dab_kernel<NFFT, RAW, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            ofdm_frame_dab_kernel<NFFT, RAW, 3><<<grid, FRAME_CTA_THREADS, smem, st>>>(g, d_descs, n_frames);
-        } else if (o->frame_min_blocks == 2) {
-            DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_dab_kernel<NFFT, RAW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            ofdm_frame_dab_kernel<NFFT, RAW, 2><<<grid, FRAME_CTA_THREADS, smem, st>>>(g, d_descs, n_frames);
-        } else {
-            DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_dab_kernel<NFFT, RAW, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            ofdm_frame_dab_kernel<NFFT, RAW, 4><<<grid, FRAME_CTA_THREADS, smem, st>>>(g, d_descs, n_frames);
+            DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_v3_kernel<NFFT, SB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            ofdm_frame_v3_kernel<NFFT, SB, false><<<grid, FRAME_CTA_THREADS, smem, st>>>(g, d_descs, n_items);
         }
         o->launches++;
         DAB_CUDA_CHECK(cudaGetLastError());
         return DAB_OK;
     }
     const size_t smem = FrameSmem<NFFT>::total_bytes(g.n_carriers);
-    DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_kernel<NFFT, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_frame_kernel<NFFT, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     constexpr int GROUPS = FrameSmem<NFFT>::GROUPS;
-    const int n_items = n_frames * g.n_chunks;
     const int grid = (n_items + GROUPS - 1) / GROUPS;
-    ofdm_frame_kernel<NFFT, RAW><<<grid, FRAME_CTA_THREADS, smem, st>>>(g, d_descs, n_frames);
+    ofdm_frame_kernel<NFFT, SB><<<grid, FRAME_CTA_THREADS, smem, st>>>(g, d_descs, n_items);
     o->launches++;
     DAB_CUDA_CHECK(cudaGetLastError());
     return DAB_OK;
 }
 
-static int launch_frame(Ofdm* o, cudaStream_t st, const FrameDesc* d_descs, int n_frames, bool raw) {
-    if (n_frames <= 0) return DAB_OK;
+template <int SB>
+static int launch_frame_sb(Ofdm* o, cudaStream_t st, const FrameDesc* d_descs, int n_items) {
     switch (o->nfft) {
-    case 2048: return raw ? launch_frame_t<2048, true>(o, st, d_descs, n_frames) : launch_frame_t<2048, false>(o, st, d_descs, n_frames);
-    case 1024: return raw ? launch_frame_t<1024, true>(o, st, d_descs, n_frames) : launch_frame_t<1024, false>(o, st, d_descs, n_frames);
-    case 512: return raw ? launch_frame_t<512, true>(o, st, d_descs, n_frames) : launch_frame_t<512, false>(o, st, d_descs, n_frames);
-    case 256: return raw ? launch_frame_t<256, true>(o, st, d_descs, n_frames) : launch_frame_t<256, false>(o, st, d_descs, n_frames);
+    case 2048: return launch_frame_t<2048, SB>(o, st, d_descs, n_items);
+    case 1024: return launch_frame_t<1024, SB>(o, st, d_descs, n_items);
+    case 512: return launch_frame_t<512, SB>(o, st, d_descs, n_items);
+    case 256: return launch_frame_t<256, SB>(o, st, d_descs, n_items);
     }
     return set_error(DAB_ERR_INVALID, "unsupported FFT size %d", o->nfft);
+}
+
+static int launch_frame(Ofdm* o, cudaStream_t st, const FrameDesc* d_descs, int n_items) {
+    if (n_items <= 0) return DAB_OK;
+    switch (o->sb) {
+    case 8: return launch_frame_sb<8>(o, st, d_descs, n_items);
+    case 2: return launch_frame_sb<2>(o, st, d_descs, n_items);
+    case 4: return launch_frame_sb<4>(o, st, d_descs, n_items);
+    }
+    return set_error(DAB_ERR_INVALID, "unsupported sample size %d", o->sb);
 }
 
 static ControlGeom control_geom(const Ofdm* o) {
@@ -276,8 +277,17 @@ static ControlGeom control_geom(const Ofdm* o) {
     g.cyclic_prefix = int(o->p.nb_cyclic_prefix);
     g.n_carriers = int(o->p.nb_data_carriers);
     g.slots = o->slots;
+    g.ring_slots = o->ring_slots;
     g.n_streams = o->n_streams;
     g.stream0 = 0;
+    g.n_chunks = o->n_chunks;
+    g.syms_per_chunk = o->syms_per_chunk;
+    g.frame_passes = 0;
+    g.eager = o->eager ? 1 : 0;
+    // the generic-geometry kernel does not sum windows
+    g.frame_owns_l1 = (o->frame_owns_l1 && o->dab_geometry && !o->force_generic_kernel) ? 1 : 0;
+    g.l1_per_symbol = 2 * std::max(1, o->nfft / 16 / 32);   // two windows per sub-warp of a transform's thread group
+    g.call_index = o->call_index;
     g.frame_bits = o->frame_bits;
     if (o->ext_base) {
         g.mask = ~uint64_t(0);
@@ -290,6 +300,7 @@ static ControlGeom control_geom(const Ofdm* o) {
         g.stream_stride = o->ring_samples;
         g.samples = o->ring_iq.ptr;
     }
+    g.fmt = o->fmt;
     g.ring = o->null_ring.ptr;
     g.corr_explicit = o->corr_explicit.ptr;
     g.prs_fft_ref_conj = o->prs_fft_ref_conj.ptr;
@@ -300,6 +311,7 @@ static ControlGeom control_geom(const Ofdm* o) {
     g.descs = o->descs.ptr;
     g.infos = o->infos.ptr;
     g.frames_in_call = o->frames_in_call.ptr;
+    g.frame_slots = o->frame_slots.ptr;
     g.bits = o->bits.ptr;
     g.phase_err = o->phase_err.ptr;
     g.twiddles = o->twiddles.ptr;
@@ -307,33 +319,42 @@ static ControlGeom control_geom(const Ofdm* o) {
     g.l1_windows_stride = o->l1_windows_stride;
     g.fft_tap = o->debug_taps ? o->fft_tap.ptr : nullptr;
     g.vec_tap = o->debug_taps ? o->vec_tap.ptr : nullptr;
+    g.n_per_stream = nullptr;
+    g.n_uniform = 0;
     return g;
 }
 
-template <int NFFT, bool RAW>
-static int launch_control_t(Ofdm* o, cudaStream_t st, int stream0, int count, int pass) {
-    ControlGeom g = control_geom(o);
-    g.stream0 = stream0;
+template <int NFFT, int SB>
+static int launch_control_t(Ofdm* o, cudaStream_t st, const ControlGeom& g, int count, int pass) {
     const size_t smem = ControlSmem<NFFT>::bytes();
-    DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_control_kernel<NFFT, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    ofdm_control_kernel<NFFT, RAW><<<count, ControlSmem<NFFT>::THREADS, smem, st>>>(g, pass);
+    DAB_CUDA_CHECK(cudaFuncSetAttribute(ofdm_control_kernel<NFFT, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    ofdm_control_kernel<NFFT, SB><<<count, ControlSmem<NFFT>::THREADS, smem, st>>>(g, pass);
     o->launches++;
     DAB_CUDA_CHECK(cudaGetLastError());
     return DAB_OK;
 }
 
-static int launch_control(Ofdm* o, cudaStream_t st, int stream0, int count, int pass) {
-    const bool raw = o->raw_u8;
+template <int SB>
+static int launch_control_sb(Ofdm* o, cudaStream_t st, const ControlGeom& g, int count, int pass) {
     switch (o->nfft) {
-    case 2048: return raw ? launch_control_t<2048, true>(o, st, stream0, count, pass) : launch_control_t<2048, false>(o, st, stream0, count, pass);
-    case 1024: return raw ? launch_control_t<1024, true>(o, st, stream0, count, pass) : launch_control_t<1024, false>(o, st, stream0, count, pass);
-    case 512: return raw ? launch_control_t<512, true>(o, st, stream0, count, pass) : launch_control_t<512, false>(o, st, stream0, count, pass);
-    case 256: return raw ? launch_control_t<256, true>(o, st, stream0, count, pass) : launch_control_t<256, false>(o, st, stream0, count, pass);
+    case 2048: return launch_control_t<2048, SB>(o, st, g, count, pass);
+    case 1024: return launch_control_t<1024, SB>(o, st, g, count, pass);
+    case 512: return launch_control_t<512, SB>(o, st, g, count, pass);
+    case 256: return launch_control_t<256, SB>(o, st, g, count, pass);
     }
     return set_error(DAB_ERR_INVALID, "unsupported FFT size %d", o->nfft);
 }
 
-static size_t sample_bytes(const Ofdm* o) { return o->raw_u8 ? 2 : sizeof(float2); }
+static int launch_control(Ofdm* o, cudaStream_t st, const ControlGeom& g, int count, int pass) {
+    switch (o->sb) {
+    case 8: return launch_control_sb<8>(o, st, g, count, pass);
+    case 2: return launch_control_sb<2>(o, st, g, count, pass);
+    case 4: return launch_control_sb<4>(o, st, g, count, pass);
+    }
+    return set_error(DAB_ERR_INVALID, "unsupported sample size %d", o->sb);
+}
+
+static size_t sample_bytes(const Ofdm* o) { return size_t(o->sb); }
 
 // frame completions possible inside one call of n samples: consecutive frame ends are at least frame_cap - cp apart
 static int passes_for(const Ofdm* o, uint64_t n_max) {
@@ -355,41 +376,27 @@ static WayRange way_range(const Ofdm* o, int w, int ways) {
     return r;
 }
 
-// begin -> L1 windows -> (control -> frame)* -> control  for the streams of one way, in order on the way's CUDA stream
-static int issue_way_kernels(Ofdm* o, const WayRange& r, bool uniform, uint64_t n_uniform, uint64_t n_max, int passes) {
+// (control -> frame)* -> control  for the streams of one way, in order on the way's CUDA stream.  Control pass 0 opens the call
+// (OFDM_Demod::Process's entry); the frame kernel after pass p runs the work items pass p wrote; the last pass folds the call's
+// UpdateSignalAverage windows -- those the frame kernels summed on the way and those it sums itself -- into the running average.
+static int issue_way_kernels(Ofdm* o, const WayRange& r, bool uniform, uint64_t n_uniform, int passes) {
     const int count = r.hi - r.lo;
     cudaStream_t st = r.st;
-    const int threads = 128;
-    ofdm_begin_call_kernel<<<(count + threads - 1) / threads, threads, 0, st>>>(o->states.ptr + r.lo, uniform ? nullptr : o->d_n.ptr + r.lo, n_uniform, count);
-    o->launches++;
-    DAB_CUDA_CHECK(cudaGetLastError());
-    // UpdateSignalAverage's window averages for this call (default config: one 100-sample window every 500 samples): every slot
-    // of the window buffer that the current call can reach under ANY config (the kernel skips windows past the call's end);
-    // update_signal_average falls back to in-kernel evaluation beyond the buffer
-    {
-        const int max_windows = (n_max >= 1) ? o->l1_windows_stride : 0;
-        const int64_t tasks = int64_t(count) * ((max_windows + L1_WB - 1) / L1_WB);
-        const int grid = int(std::min<int64_t>((tasks + 7) / 8, 148 * 8));
-        ControlGeom g = control_geom(o);
-        g.stream0 = r.lo;
-        if (grid > 0) {
-            ScopedKernelTimer timer(o, st, DAB_OFDM_TIMING_PASSES - 1, false);
-            if (o->raw_u8) ofdm_l1_windows_kernel<true><<<grid, 256, 0, st>>>(g, count, max_windows);
-            else ofdm_l1_windows_kernel<false><<<grid, 256, 0, st>>>(g, count, max_windows);
-            o->launches++;
-            DAB_CUDA_CHECK(cudaGetLastError());
-        }
-    }
+    ControlGeom g = control_geom(o);
+    g.stream0 = r.lo;
+    g.frame_passes = passes;
+    g.n_per_stream = uniform ? nullptr : o->d_n.ptr;
+    g.n_uniform = n_uniform;
     for (int p = 0; p <= passes; p++) {
         int rc;
         {
             ScopedKernelTimer timer(o, st, p, false);
-            rc = launch_control(o, st, r.lo, count, p);
+            rc = launch_control(o, st, g, count, p);
         }
         if (rc != DAB_OK) return rc;
         if (p < passes) {
             ScopedKernelTimer timer(o, st, p, true);
-            rc = launch_frame(o, st, o->descs.ptr + size_t(p) * size_t(o->n_streams) + r.lo, count, o->raw_u8);
+            rc = launch_frame(o, st, o->descs.ptr + (size_t(p) * size_t(o->n_streams) + size_t(r.lo)) * size_t(o->n_chunks), count * o->n_chunks);
             if (rc != DAB_OK) return rc;
         }
     }
@@ -441,11 +448,12 @@ static int upload_blocks(Ofdm* o, const WayRange& r, const void* const* iq, size
 // One Process() call for every stream.  iq == nullptr: the n_call[s] new samples are already visible at [fed[s], fed[s] +
 // n_call[s]) (attached device streams).  Otherwise iq[s] is the caller's host block, copied into the stream ring first.
 //
-// The streams are split into pipeline ways.  Every way runs  upload -> begin -> L1 windows -> (control -> frame)* -> control ->
-// download of the frame counts  in order on its own CUDA stream (per-stream ordering is the reference's real-time order,
-// ofdm_control.cuh); different ways only share the GPU and the PCIe link, so one way's control passes (latency bound, ~1/4 of a
-// step when serialised) hide behind another way's frame kernel, and uploads, kernels and downloads of different ways overlap.
-static int run_call(Ofdm* o, bool uniform, uint64_t n_uniform, const void* const* iq) {
+// The streams are split into pipeline ways.  Every way runs  upload -> (control -> frame)* -> control -> download of the frame
+// counts  in order on its own CUDA stream (per-stream ordering is the reference's real-time order, ofdm_control.cuh); different
+// ways only share the GPU and the PCIe link, so one way's control passes (latency bound) hide behind another way's frame kernel,
+// and uploads, kernels and downloads of different ways overlap.
+static int run_call(Ofdm* o, bool uniform, uint64_t n_uniform, const void* const* iq, bool snapshot) {
+    NvtxRange nvtx_call("dab_ofdm call");
     uint64_t n_max = 0;
     if (uniform) {
         n_max = n_uniform;
@@ -459,12 +467,15 @@ static int run_call(Ofdm* o, bool uniform, uint64_t n_uniform, const void* const
     if (passes > o->slots) return set_error(DAB_ERR_CAPACITY, "call of %llu samples exceeds max_block_samples", (unsigned long long)n_max);
     const int ways = n_ways(o);
     const size_t sb = sample_bytes(o), ns = size_t(o->n_streams), slots = size_t(o->slots);
-    if (o->cb) {
+    if (o->cb || snapshot) {
         DAB_CUDA_CHECK(o->h_frames.reserve(ns));
+        DAB_CUDA_CHECK(o->h_frame_slots.reserve(ns * slots));
         DAB_CUDA_CHECK(o->h_infos.reserve(ns * slots));
     }
+    if (snapshot) DAB_CUDA_CHECK(o->h_states.reserve(ns));
     if (ways > 1) DAB_CUDA_CHECK(cudaEventRecord(o->fork_event, o->stream));
     for (int w = 0; w < ways; w++) {
+        NvtxRange nvtx_way("dab_ofdm way");
         const WayRange r = way_range(o, w, ways);
         if (ways > 1) DAB_CUDA_CHECK(cudaStreamWaitEvent(r.st, o->fork_event, 0));
         if (iq) {
@@ -478,16 +489,30 @@ static int run_call(Ofdm* o, bool uniform, uint64_t n_uniform, const void* const
                 DAB_CUDA_CHECK(cudaStreamWaitEvent(r.st, o->up_done[w], 0));
             }
         }
-        int rc = issue_way_kernels(o, r, uniform, n_uniform, n_max, passes);
+        int rc = issue_way_kernels(o, r, uniform, n_uniform, passes);
         if (rc != DAB_OK) return rc;
+        const size_t cnt = size_t(r.hi - r.lo);
         if (o->cb) {
-            const size_t cnt = size_t(r.hi - r.lo);
             DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_frames.ptr + r.lo, o->frames_in_call.ptr + r.lo, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, r.st));
+            DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_frame_slots.ptr + size_t(r.lo) * slots, o->frame_slots.ptr + size_t(r.lo) * slots, cnt * slots * sizeof(int32_t),
+                                           cudaMemcpyDeviceToHost, r.st));
             DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_infos.ptr + size_t(r.lo) * slots, o->infos.ptr + size_t(r.lo) * slots, cnt * slots * sizeof(dab_ofdm_frame_info),
                                            cudaMemcpyDeviceToHost, r.st));
         }
+        if (snapshot) {
+            DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_states.ptr + r.lo, o->states.ptr + r.lo, cnt * sizeof(StreamState), cudaMemcpyDeviceToHost, r.st));
+            if (o->n_streams <= Ofdm::SNAP_ARRAYS_MAX_STREAMS) {
+                const size_t nfft = size_t(o->nfft);
+                DAB_CUDA_CHECK(o->h_resp.reserve(ns * 2 * nfft));
+                for (int s = r.lo; s < r.hi; s++) {
+                    DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_resp.ptr + size_t(s) * 2 * nfft, o->impulse.ptr + size_t(s) * nfft, nfft * sizeof(float), cudaMemcpyDeviceToHost, r.st));
+                    DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_resp.ptr + size_t(s) * 2 * nfft + nfft, o->freq_resp.ptr + size_t(s) * nfft, nfft * sizeof(float), cudaMemcpyDeviceToHost, r.st));
+                }
+            }
+        }
         DAB_CUDA_CHECK(cudaEventRecord(o->counts_ready[w], r.st));
     }
+    o->call_index++;
     if (ways > 1) {
         o->ways_pending = true;
         // per-stream sample counts live in one device buffer that the next call overwrites from the handle's stream
@@ -508,44 +533,51 @@ static int run_callbacks(Ofdm* o, int w, int ways, size_t k) {
     const WayRange r = way_range(o, w, ways);
     const size_t slots = size_t(o->slots), fb = o->frame_bits;
     DAB_CUDA_CHECK(cudaEventSynchronize(o->bits_ready[w]));
+    const bool keep_bits = o->n_streams <= Ofdm::SNAP_ARRAYS_MAX_STREAMS;
     for (int s = r.lo; s < r.hi; s++)
-        for (int f = 0; f < o->h_frames.ptr[s]; f++, k++)
+        for (int f = 0; f < o->h_frames.ptr[s]; f++, k++) {
+            if (keep_bits) {  // GetFrameDataBits() between calls is served from this copy
+                std::lock_guard<std::mutex> snap_lock(o->snap_mtx);
+                o->snap_bits.resize(size_t(o->n_streams) * fb);
+                o->snap_bits_valid.resize(size_t(o->n_streams), 0);
+                memcpy(o->snap_bits.data() + size_t(s) * fb, o->h_bits.ptr + k * fb, fb);
+                o->snap_bits_valid[size_t(s)] = 1;
+            }
             o->cb(o->cb_user, s, o->h_bits.ptr + k * fb, fb, &o->h_infos.ptr[size_t(s) * slots + size_t(f)]);
+        }
     return DAB_OK;
 }
 
 // soft-bit callback delivery (CoordinatorThread's Notify, ofdm_demodulator.cpp:635), in stream then frame order.  Way by way:
-// as soon as a way's frame counts are on the host its soft bits are fetched (consecutive frames as one copy), and its
+// as soon as a way's frame counts are on the host its soft bits are fetched (consecutive streams as one strided copy), and its
 // callbacks run while the later ways are still uploading / computing.
 static int deliver(Ofdm* o) {
     if (!o->cb) return DAB_OK;
     const int ways = n_ways(o);
-    const size_t slots = size_t(o->slots), fb = o->frame_bits;
+    const size_t slots = size_t(o->slots), ring = size_t(o->ring_slots), fb = o->frame_bits;
     DAB_CUDA_CHECK(o->h_bits.reserve(size_t(o->n_streams) * slots * fb));
     std::vector<size_t> first_k(size_t(ways) + 1, 0);
     for (int w = 0; w < ways; w++) {
         const WayRange r = way_range(o, w, ways);
         DAB_CUDA_CHECK(cudaEventSynchronize(o->counts_ready[w]));
         size_t k = first_k[size_t(w)];
-        // device source of frame (s, f) is (s * slots + f) * fb, host destination (callback order: stream, then frame) is k * fb.
-        // Consecutive streams that completed the same number of frames c form a run whose frame f goes down as ONE pitched copy
-        // (rows of fb bytes, source pitch slots * fb, destination pitch c * fb): one copy per way in the steady state instead of
-        // one per stream -- 1024 separate 230 KB copies cost 6.7 ms of set-up per step, more than the transfer itself.
+        // device source of frame (s, f) is ((s * ring) + slot(s, f)) * fb, host destination (callback order: stream, then frame) is
+        // k * fb.  Consecutive streams that completed the same number of frames c into the same ring slots form a run whose frame f
+        // goes down as ONE pitched copy (rows of fb bytes, source pitch ring * fb, destination pitch c * fb): one copy per way in
+        // the steady state instead of one per stream -- 1024 separate 230 KB copies cost 6.7 ms of set-up per step, more than the
+        // transfer itself.
         cudaStream_t down = (ways > 1) ? o->down_stream : r.st;  // counts_ready[w] (synchronised above) follows the way's kernels
+        const int32_t* hs = o->h_frame_slots.ptr;
         for (int s0 = r.lo; s0 < r.hi;) {
             const int c = o->h_frames.ptr[s0];
             int s1 = s0 + 1;
-            while (s1 < r.hi && o->h_frames.ptr[s1] == c) s1++;
+            while (s1 < r.hi && o->h_frames.ptr[s1] == c && memcmp(hs + size_t(s1) * slots, hs + size_t(s0) * slots, size_t(c) * sizeof(int32_t)) == 0) s1++;
             if (c > 0) {
                 const size_t rows = size_t(s1 - s0);
                 for (int f = 0; f < c; f++) {
-                    const int8_t* src = o->bits.ptr + (size_t(s0) * slots + size_t(f)) * fb;
+                    const int8_t* src = o->bits.ptr + (size_t(s0) * ring + size_t(hs[size_t(s0) * slots + size_t(f)])) * fb;
                     int8_t* dst = o->h_bits.ptr + (k + size_t(f)) * fb;
-                    if (size_t(c) == slots && c == 1) {
-                        DAB_CUDA_CHECK(cudaMemcpyAsync(dst, src, rows * fb, cudaMemcpyDeviceToHost, down));
-                    } else {
-                        DAB_CUDA_CHECK(cudaMemcpy2DAsync(dst, size_t(c) * fb, src, slots * fb, fb, rows, cudaMemcpyDeviceToHost, down));
-                    }
+                    DAB_CUDA_CHECK(cudaMemcpy2DAsync(dst, size_t(c) * fb, src, ring * fb, fb, rows, cudaMemcpyDeviceToHost, down));
                 }
                 k += rows * size_t(c);
             }
@@ -566,6 +598,37 @@ static int deliver(Ofdm* o) {
     return join_ways(o);
 }
 
+static void fill_state(dab_ofdm_state* out, const StreamState& st) {
+    out->state = st.state;
+    out->fine_time_offset = st.fine_time_offset;
+    out->total_frames_read = st.total_frames_read;
+    out->total_frames_desync = st.total_frames_desync;
+    out->signal_average = st.l1_average;
+    out->fine_frequency_offset = st.freq_fine;
+    out->coarse_frequency_offset = st.freq_coarse;
+    out->reserved = 0;
+}
+
+// after a synchronous call: the states (and, for small handles, the sync responses) copied by run_call become the getter snapshot
+static void publish_snapshot(Ofdm* o) {
+    std::lock_guard<std::mutex> snap_lock(o->snap_mtx);
+    o->snap.resize(size_t(o->n_streams));
+    o->snap_pending_slot.resize(size_t(o->n_streams));
+    for (int s = 0; s < o->n_streams; s++) {
+        fill_state(&o->snap[size_t(s)], o->h_states.ptr[s]);
+        o->snap_pending_slot[size_t(s)] = o->h_states.ptr[s].pending_slot;
+    }
+    if (o->n_streams <= Ofdm::SNAP_ARRAYS_MAX_STREAMS && o->h_resp.ptr)
+        o->snap_resp.assign(o->h_resp.ptr, o->h_resp.ptr + size_t(o->n_streams) * 2 * size_t(o->nfft));
+    o->snap_valid = true;
+}
+
+static void invalidate_snapshot(Ofdm* o) {
+    std::lock_guard<std::mutex> snap_lock(o->snap_mtx);
+    o->snap_valid = false;
+    std::fill(o->snap_bits_valid.begin(), o->snap_bits_valid.end(), uint8_t(0));
+}
+
 static int init_states(Ofdm* o) {
     // the configuration is the caller's (OFDM_Demod::GetConfig() is mutable state of the object, not of a run): it survives a
     // re-initialisation of the stream states, e.g. attaching device-resident streams after dab_ofdm_set_config
@@ -583,8 +646,11 @@ static int init_states(Ofdm* o) {
     DAB_CUDA_CHECK(cudaMemcpy(o->states.ptr, init.data(), init.size() * sizeof(StreamState), cudaMemcpyHostToDevice));
     DAB_CUDA_CHECK(cudaMemset(o->null_ring.ptr, 0, o->null_ring.count * sizeof(float2)));
     DAB_CUDA_CHECK(cudaMemset(o->frames_in_call.ptr, 0, o->frames_in_call.count * sizeof(int32_t)));
+    DAB_CUDA_CHECK(cudaMemset(o->frame_slots.ptr, 0, o->frame_slots.count * sizeof(int32_t)));
     DAB_CUDA_CHECK(cudaMemset(o->descs.ptr, 0, o->descs.count * sizeof(FrameDesc)));
     std::fill(o->fed.begin(), o->fed.end(), 0);
+    o->call_index = 0;
+    invalidate_snapshot(o);
     return DAB_OK;
 }
 
@@ -593,6 +659,13 @@ static int create_impl(Ofdm* o, const dab_c32* prs, const int* mapper) {
     const size_t frame_cap = o->p.nb_frame_symbols * o->p.nb_symbol_period + o->p.nb_null_period;
     o->frame_bits = (o->p.nb_frame_symbols - 1) * ncarr * 2;
     o->slots = std::max(1, passes_for(o, o->max_block));
+    o->ring_slots = o->slots + 1;
+    o->dab_geometry = (o->nfft == 2048 && DabGeom<2048>::matches(int(o->p.nb_symbol_period), int(o->p.nb_cyclic_prefix), int(ncarr))) ||
+                      (o->nfft == 1024 && DabGeom<1024>::matches(int(o->p.nb_symbol_period), int(o->p.nb_cyclic_prefix), int(ncarr))) ||
+                      (o->nfft == 512 && DabGeom<512>::matches(int(o->p.nb_symbol_period), int(o->p.nb_cyclic_prefix), int(ncarr))) ||
+                      (o->nfft == 256 && DabGeom<256>::matches(int(o->p.nb_symbol_period), int(o->p.nb_cyclic_prefix), int(ncarr)));
+    // work items per dispatch: a whole frame in pieces of about syms_per_chunk symbols
+    o->n_chunks = std::max(1, std::min(FRAME_MAX_CHUNKS, int((o->p.nb_frame_symbols + size_t(o->syms_per_chunk) - 1) / size_t(o->syms_per_chunk))));
     size_t need = frame_cap + o->p.nb_null_period + o->p.nb_symbol_period + o->max_block + 1024;
     o->ring_samples = 1;
     while (o->ring_samples < need) o->ring_samples <<= 1;
@@ -645,12 +718,14 @@ static int create_impl(Ofdm* o, const dab_c32* prs, const int* mapper) {
     DAB_CUDA_CHECK(cudaMemset(o->impulse.ptr, 0, ns * nfft * sizeof(float)));
     DAB_CUDA_CHECK(cudaMemset(o->freq_resp.ptr, 0, ns * nfft * sizeof(float)));
     DAB_CUDA_CHECK(o->states.reserve(ns));
-    DAB_CUDA_CHECK(o->descs.reserve(ns * size_t(o->slots)));
+    DAB_CUDA_CHECK(o->descs.reserve(ns * size_t(o->slots) * size_t(o->n_chunks)));
     DAB_CUDA_CHECK(o->infos.reserve(ns * size_t(o->slots)));
     DAB_CUDA_CHECK(o->frames_in_call.reserve(ns));
-    DAB_CUDA_CHECK(o->bits.reserve(ns * size_t(o->slots) * o->frame_bits));
-    DAB_CUDA_CHECK(cudaMemset(o->bits.ptr, 0, ns * size_t(o->slots) * o->frame_bits));
-    DAB_CUDA_CHECK(o->phase_err.reserve(ns * size_t(o->slots) * o->p.nb_frame_symbols));
+    DAB_CUDA_CHECK(o->frame_slots.reserve(ns * size_t(o->slots)));
+    DAB_CUDA_CHECK(o->bits.reserve(ns * size_t(o->ring_slots) * o->frame_bits));
+    DAB_CUDA_CHECK(cudaMemset(o->bits.ptr, 0, ns * size_t(o->ring_slots) * o->frame_bits));
+    DAB_CUDA_CHECK(o->phase_err.reserve(ns * o->p.nb_frame_symbols));
+    DAB_CUDA_CHECK(cudaMemset(o->phase_err.ptr, 0, ns * o->p.nb_frame_symbols * sizeof(float)));
     DAB_CUDA_CHECK(o->bin_to_pos.reserve(nfft));
     DAB_CUDA_CHECK(o->bin_to_carrier.reserve(nfft));
     DAB_CUDA_CHECK(o->d_n.reserve(ns));
@@ -705,6 +780,31 @@ void dab_ofdm_default_config(dab_ofdm_config* c) {
     c->sync_impulse_peak_distance_probability = 0.15f;
 }
 
+static bool sample_format(int format, int* sb, SampleFmt* f) {
+    // examples/app_helpers/app_iq_readers.h:20-35: BIAS / MAX_AMPLITUDE per integer type (signed: 0 / max, unsigned: max/2 + 0.5 twice);
+    // a signed component is read as unsigned ^ sign bit, which raises the bias by 2^(bits-1)
+    f->flip = 0;
+    f->prmt = 0x3210;
+    f->bias = 0.0f;
+    f->scale = 1.0f;
+    switch (format) {
+    case DAB_IQ_F32: *sb = 8; return true;
+    case DAB_IQ_U8: *sb = 2; f->bias = 127.5f; f->scale = 1.0f / 127.5f; return true;
+    case DAB_IQ_S8: *sb = 2; f->flip = 0x80u; f->bias = 128.0f; f->scale = 1.0f / 127.0f; return true;
+    case DAB_IQ_S16LE: case DAB_IQ_S16BE: *sb = 4; f->flip = 0x8000u; f->bias = 32768.0f; f->scale = 1.0f / 32767.0f; break;
+    case DAB_IQ_U16LE: case DAB_IQ_U16BE: *sb = 4; f->bias = 32767.5f; f->scale = 1.0f / 32767.5f; break;
+    default: return false;
+    }
+    if (format == DAB_IQ_S16BE || format == DAB_IQ_U16BE) f->prmt = 0x2301;
+    return true;
+}
+
+size_t dab_iq_format_bytes(int format) {
+    int sb = 0;
+    SampleFmt f;
+    return sample_format(format, &sb, &f) ? size_t(sb) : 0;
+}
+
 dab_ofdm* dab_ofdm_create(const dab_ofdm_params* params, const dab_c32* prs_fft_ref, const int* carrier_mapper, const dab_ofdm_options* options,
                           int* status) {
     auto fail = [&](int rc) -> dab_ofdm* { if (status) *status = rc; return nullptr; };
@@ -717,6 +817,10 @@ dab_ofdm* dab_ofdm_create(const dab_ofdm_params* params, const dab_c32* prs_fft_
     if (params->nb_data_carriers >= nfft || params->nb_data_carriers % 8 != 0 || params->nb_frame_symbols < 2 ||
         params->nb_null_period < params->nb_cyclic_prefix)
         return fail(set_error(DAB_ERR_INVALID, "unsupported OFDM geometry"));
+    int sb = 0;
+    SampleFmt fmt;
+    if (!sample_format(options->sample_format, &sb, &fmt)) return fail(set_error(DAB_ERR_INVALID, "unknown sample_format %d", options->sample_format));
+    DeviceGuard guard;
     int rc = select_device(options->device);
     if (rc != DAB_OK) return fail(rc);
     auto* o = new Ofdm();
@@ -724,14 +828,16 @@ dab_ofdm* dab_ofdm_create(const dab_ofdm_params* params, const dab_c32* prs_fft_
     o->nfft = int(nfft);
     o->n_streams = options->n_streams;
     o->device = options->device;
-    o->raw_u8 = options->raw_u8_ingest != 0;
+    o->format = options->sample_format;
+    o->sb = sb;
+    o->fmt = fmt;
     o->debug_taps = options->keep_debug_taps != 0;
     o->max_block = options->max_block_samples ? options->max_block_samples : 262144;
     if (const char* e = getenv("DAB_B200_GENERIC_FRAME_KERNEL")) o->force_generic_kernel = (e[0] == '1');
     if (const char* e = getenv("DAB_B200_PIPELINE_WAYS")) { const int w = atoi(e); if (w >= 1 && w <= Ofdm::MAX_WAYS) o->ways = w; }
-    if (const char* e = getenv("DAB_B200_FRAME_KERNEL")) o->frame_kernel_version = atoi(e);
-    if (const char* e = getenv("DAB_B200_FRAME_MIN_BLOCKS")) { const int b = atoi(e); o->frame_min_blocks = (b >= 2 && b <= 4) ? b : 3; }
     if (const char* e = getenv("DAB_B200_SYMS_PER_CHUNK")) { const int c = atoi(e); if (c >= 1 && c <= 1024) o->syms_per_chunk = c; }
+    if (const char* e = getenv("DAB_B200_EAGER")) o->eager = (e[0] != '0');
+    if (const char* e = getenv("DAB_B200_FRAME_L1")) o->frame_owns_l1 = (e[0] != '0');
     rc = create_impl(o, prs_fft_ref, carrier_mapper);
     if (rc != DAB_OK) { delete o; return fail(rc); }
     if (status) *status = DAB_OK;
@@ -741,6 +847,7 @@ dab_ofdm* dab_ofdm_create(const dab_ofdm_params* params, const dab_c32* prs_fft_
 void dab_ofdm_destroy(dab_ofdm* h) {
     auto* o = reinterpret_cast<Ofdm*>(h);
     if (!o) return;
+    DeviceGuard guard;
     cudaSetDevice(o->device);
     cudaStreamSynchronize(o->stream);
     for (auto& t : o->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
@@ -759,10 +866,13 @@ void dab_ofdm_destroy(dab_ofdm* h) {
     delete o;
 }
 
-#define OFDM_HANDLE(h)                                          \
-    auto* o = reinterpret_cast<Ofdm*>(h);                       \
-    if (!o) return set_error(DAB_ERR_INVALID, "null handle");   \
-    std::lock_guard<std::mutex> lock(o->mtx);                   \
+// The handle's lock is recursive: the frame callback runs inside a process call and may call back into the same handle from the
+// same thread (see include/dab_b200.h).  The caller's current CUDA device is restored when the call returns.
+#define OFDM_HANDLE(h)                                              \
+    auto* o = reinterpret_cast<Ofdm*>(h);                           \
+    if (!o) return set_error(DAB_ERR_INVALID, "null handle");       \
+    std::lock_guard<std::recursive_mutex> lock(o->mtx);             \
+    DeviceGuard device_guard;                                       \
     DAB_CUDA_CHECK(cudaSetDevice(o->device))
 
 int dab_ofdm_set_cuda_stream(dab_ofdm* h, void* cuda_stream) {
@@ -795,14 +905,14 @@ int dab_ofdm_set_config(dab_ofdm* h, int stream, const dab_ofdm_config* cfg) {
     OFDM_HANDLE(h);
     { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     if (!cfg || stream < -1 || stream >= o->n_streams) return set_error(DAB_ERR_INVALID, "bad stream / config");
-    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
     const int lo = (stream < 0) ? 0 : stream, hi = (stream < 0) ? o->n_streams : stream + 1;
-    for (int s = lo; s < hi; s++) {
-        if (size_t(s) < o->cfgs.size()) o->cfgs[size_t(s)] = *cfg;
-        DAB_CUDA_CHECK(cudaMemcpy(reinterpret_cast<char*>(o->states.ptr + s) + offsetof(StreamState, cfg), cfg, sizeof(*cfg), cudaMemcpyHostToDevice));
-    }
-    // the precomputed window averages of UpdateSignalAverage (ofdm_l1_windows_kernel) must cover a whole call under this
-    // configuration too, otherwise every stream evaluates its windows inside the control kernel
+    for (int s = lo; s < hi; s++) o->cfgs[size_t(s)] = *cfg;
+    // one strided copy into the cfg member of every selected stream state
+    DAB_CUDA_CHECK(cudaMemcpy2DAsync(reinterpret_cast<char*>(o->states.ptr + lo) + offsetof(StreamState, cfg), sizeof(StreamState), &o->cfgs[size_t(lo)],
+                                     sizeof(dab_ofdm_config), sizeof(dab_ofdm_config), size_t(hi - lo), cudaMemcpyHostToDevice, o->stream));
+    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
+    // the window buffer the frame kernel writes UpdateSignalAverage's window averages to must hold a whole call under this
+    // configuration too, otherwise the control kernel sums every window itself
     if (cfg->signal_l1_nb_samples > 0 && cfg->signal_l1_nb_decimate > 0) {
         const size_t step = size_t(cfg->signal_l1_nb_samples) * size_t(cfg->signal_l1_nb_decimate);
         const size_t need = std::min<size_t>(o->max_block / step + 2, size_t(1) << 20);
@@ -816,42 +926,51 @@ int dab_ofdm_set_config(dab_ofdm* h, int stream, const dab_ofdm_config* cfg) {
 
 int dab_ofdm_get_config(dab_ofdm* h, int stream, dab_ofdm_config* cfg) {
     OFDM_HANDLE(h);
-    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     if (!cfg || stream < 0 || stream >= o->n_streams) return set_error(DAB_ERR_INVALID, "bad stream / config");
-    DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
-    DAB_CUDA_CHECK(cudaMemcpy(cfg, reinterpret_cast<char*>(o->states.ptr + stream) + offsetof(StreamState, cfg), sizeof(*cfg), cudaMemcpyDeviceToHost));
+    *cfg = o->cfgs[size_t(stream)];   // the device copies are only ever written from this host copy
     return DAB_OK;
 }
 
-static int ingest_and_run(Ofdm* o, const void* const* iq, const size_t* n, bool raw) {
+static int ingest_and_run(Ofdm* o, const void* const* iq, const size_t* n, int format) {
     if (o->ext_base) return set_error(DAB_ERR_INVALID, "handle is attached to device-resident streams; use dab_ofdm_advance");
-    if (raw != o->raw_u8) return set_error(DAB_ERR_INVALID, "handle was created with raw_u8_ingest = %d", int(o->raw_u8));
+    if (format >= 0 && format != o->format) return set_error(DAB_ERR_INVALID, "handle was created with sample_format = %d", o->format);
     for (int s = 0; s < o->n_streams; s++) {
         const size_t ns = n[s];
         if (ns > o->max_block) return set_error(DAB_ERR_CAPACITY, "stream %d: block of %zu samples exceeds max_block_samples %zu", s, ns, o->max_block);
         if (ns > 0 && !iq[s]) return set_error(DAB_ERR_INVALID, "stream %d: null sample pointer", s);
         o->n_call[size_t(s)] = ns;
     }
-    int rc = run_call(o, false, 0, iq);
+    int rc = run_call(o, false, 0, iq, true);
     if (rc != DAB_OK) return rc;
     // the caller's span (possibly pageable memory, staged by the driver) must have been consumed before the call returns:
     // deliver() waits for every way's frame counts, which follow the way's upload; without a callback wait here
-    if (o->cb) return deliver(o);
-    const int ways = n_ways(o);
-    for (int w = 0; w < ways; w++) DAB_CUDA_CHECK(cudaEventSynchronize(o->counts_ready[w]));
+    if (o->cb) {
+        rc = deliver(o);
+        if (rc != DAB_OK) return rc;
+    } else {
+        const int ways = n_ways(o);
+        for (int w = 0; w < ways; w++) DAB_CUDA_CHECK(cudaEventSynchronize(o->counts_ready[w]));
+    }
+    publish_snapshot(o);
     return DAB_OK;
 }
 
 int dab_ofdm_process_batch(dab_ofdm* h, const dab_c32* const* iq, const size_t* n) {
     OFDM_HANDLE(h);
     if (!iq || !n) return set_error(DAB_ERR_INVALID, "null argument");
-    return ingest_and_run(o, reinterpret_cast<const void* const*>(iq), n, false);
+    return ingest_and_run(o, reinterpret_cast<const void* const*>(iq), n, DAB_IQ_F32);
 }
 
 int dab_ofdm_process_batch_u8(dab_ofdm* h, const uint8_t* const* iq_u8, const size_t* n) {
     OFDM_HANDLE(h);
     if (!iq_u8 || !n) return set_error(DAB_ERR_INVALID, "null argument");
-    return ingest_and_run(o, reinterpret_cast<const void* const*>(iq_u8), n, true);
+    return ingest_and_run(o, reinterpret_cast<const void* const*>(iq_u8), n, DAB_IQ_U8);
+}
+
+int dab_ofdm_process_batch_raw(dab_ofdm* h, const void* const* iq, const size_t* n) {
+    OFDM_HANDLE(h);
+    if (!iq || !n) return set_error(DAB_ERR_INVALID, "null argument");
+    return ingest_and_run(o, iq, n, -1);
 }
 
 int dab_ofdm_process(dab_ofdm* h, int stream, const dab_c32* iq, size_t n) {
@@ -861,7 +980,7 @@ int dab_ofdm_process(dab_ofdm* h, int stream, const dab_c32* iq, size_t n) {
     std::vector<size_t> ns(size_t(o->n_streams), 0);
     ptrs[size_t(stream)] = iq;
     ns[size_t(stream)] = n;
-    return ingest_and_run(o, ptrs.data(), ns.data(), false);
+    return ingest_and_run(o, ptrs.data(), ns.data(), DAB_IQ_F32);
 }
 
 int dab_ofdm_attach_device_streams(dab_ofdm* h, const dab_c32* d_iq, size_t stride_samples, size_t total_samples) {
@@ -883,7 +1002,8 @@ static int advance_impl(Ofdm* o, const size_t* n, size_t n_uniform) {
         if (o->fed[size_t(s)] + ns > o->ext_total) return set_error(DAB_ERR_CAPACITY, "stream %d: advance past the end of the attached buffer", s);
         o->n_call[size_t(s)] = ns;
     }
-    int rc = run_call(o, n == nullptr, n_uniform, nullptr);
+    invalidate_snapshot(o);   // asynchronous: the getters synchronise on demand
+    int rc = run_call(o, n == nullptr, n_uniform, nullptr, false);
     if (rc != DAB_OK) return rc;
     if (n != nullptr) DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));  // the pinned staging copy of n[] is reused by the next call
     return deliver(o);
@@ -905,8 +1025,16 @@ int dab_ofdm_device_bits(dab_ofdm* h, const int8_t** d_bits, size_t* n_bits, int
     { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     if (d_bits) *d_bits = o->bits.ptr;
     if (n_bits) *n_bits = o->frame_bits;
-    if (slots_per_stream) *slots_per_stream = o->slots;
+    if (slots_per_stream) *slots_per_stream = o->ring_slots;
     if (d_frames_in_call) *d_frames_in_call = o->frames_in_call.ptr;
+    return DAB_OK;
+}
+
+int dab_ofdm_device_frame_slots(dab_ofdm* h, const int32_t** d_frame_slots, int* max_frames_per_call) {
+    OFDM_HANDLE(h);
+    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
+    if (d_frame_slots) *d_frame_slots = o->frame_slots.ptr;
+    if (max_frames_per_call) *max_frames_per_call = o->slots;
     return DAB_OK;
 }
 
@@ -914,6 +1042,7 @@ int dab_ofdm_reset(dab_ofdm* h, int stream) {
     OFDM_HANDLE(h);
     { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     if (stream < 0 || stream >= o->n_streams) return set_error(DAB_ERR_INVALID, "stream %d out of range", stream);
+    invalidate_snapshot(o);
     ofdm_reset_stream_kernel<<<1, 1, 0, o->stream>>>(o->states.ptr, stream);
     o->launches++;
     DAB_CUDA_CHECK(cudaGetLastError());
@@ -921,20 +1050,22 @@ int dab_ofdm_reset(dab_ofdm* h, int stream) {
 }
 
 int dab_ofdm_get_state(dab_ofdm* h, int stream, dab_ofdm_state* out) {
+    auto* o0 = reinterpret_cast<Ofdm*>(h);
+    if (!o0) return set_error(DAB_ERR_INVALID, "null handle");
+    if (!out || stream < 0 || stream >= o0->n_streams) return set_error(DAB_ERR_INVALID, "bad stream / output");
+    {   // fast path: the snapshot of the last synchronous call -- no GPU work, and no wait for a call in flight on another thread
+        std::lock_guard<std::mutex> snap_lock(o0->snap_mtx);
+        if (o0->snap_valid) {
+            *out = o0->snap[size_t(stream)];
+            return DAB_OK;
+        }
+    }
     OFDM_HANDLE(h);
     { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
-    if (!out || stream < 0 || stream >= o->n_streams) return set_error(DAB_ERR_INVALID, "bad stream / output");
     StreamState st;
     DAB_CUDA_CHECK(cudaMemcpyAsync(&st, o->states.ptr + stream, sizeof(st), cudaMemcpyDeviceToHost, o->stream));
     DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
-    out->state = st.state;
-    out->fine_time_offset = st.fine_time_offset;
-    out->total_frames_read = st.total_frames_read;
-    out->total_frames_desync = st.total_frames_desync;
-    out->signal_average = st.l1_average;
-    out->fine_frequency_offset = st.freq_fine;
-    out->coarse_frequency_offset = st.freq_coarse;
-    out->reserved = 0;
+    fill_state(out, st);
     return DAB_OK;
 }
 
@@ -968,28 +1099,44 @@ static int copy_out(Ofdm* o, void* dst, const void* d_src, size_t bytes) {
     return DAB_OK;
 }
 
-int dab_ofdm_get_impulse_response(dab_ofdm* h, int stream, float* out, size_t nb_fft) {
+// which = 0: impulse response, 1: coarse frequency response
+static int get_response(dab_ofdm* h, int stream, float* out, size_t nb_fft, int which) {
+    auto* o0 = reinterpret_cast<Ofdm*>(h);
+    if (!o0) return set_error(DAB_ERR_INVALID, "null handle");
+    if (!out || stream < 0 || stream >= o0->n_streams || nb_fft != size_t(o0->nfft)) return set_error(DAB_ERR_INVALID, "bad argument");
+    {
+        std::lock_guard<std::mutex> snap_lock(o0->snap_mtx);
+        if (o0->snap_valid && o0->snap_resp.size() == size_t(o0->n_streams) * 2 * nb_fft) {
+            memcpy(out, o0->snap_resp.data() + (size_t(stream) * 2 + size_t(which)) * nb_fft, nb_fft * sizeof(float));
+            return DAB_OK;
+        }
+    }
     OFDM_HANDLE(h);
     { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
-    if (!out || stream < 0 || stream >= o->n_streams || nb_fft != size_t(o->nfft)) return set_error(DAB_ERR_INVALID, "bad argument");
-    return copy_out(o, out, o->impulse.ptr + size_t(stream) * nb_fft, nb_fft * sizeof(float));
+    return copy_out(o, out, (which ? o->freq_resp.ptr : o->impulse.ptr) + size_t(stream) * nb_fft, nb_fft * sizeof(float));
 }
 
-int dab_ofdm_get_coarse_frequency_response(dab_ofdm* h, int stream, float* out, size_t nb_fft) {
-    OFDM_HANDLE(h);
-    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
-    if (!out || stream < 0 || stream >= o->n_streams || nb_fft != size_t(o->nfft)) return set_error(DAB_ERR_INVALID, "bad argument");
-    return copy_out(o, out, o->freq_resp.ptr + size_t(stream) * nb_fft, nb_fft * sizeof(float));
-}
+int dab_ofdm_get_impulse_response(dab_ofdm* h, int stream, float* out, size_t nb_fft) { return get_response(h, stream, out, nb_fft, 0); }
+
+int dab_ofdm_get_coarse_frequency_response(dab_ofdm* h, int stream, float* out, size_t nb_fft) { return get_response(h, stream, out, nb_fft, 1); }
 
 int dab_ofdm_get_frame_data_bits(dab_ofdm* h, int stream, int8_t* out, size_t n_bits) {
+    auto* o0 = reinterpret_cast<Ofdm*>(h);
+    if (!o0) return set_error(DAB_ERR_INVALID, "null handle");
+    if (!out || stream < 0 || stream >= o0->n_streams || n_bits != o0->frame_bits) return set_error(DAB_ERR_INVALID, "bad argument");
+    {
+        std::lock_guard<std::mutex> snap_lock(o0->snap_mtx);
+        if (size_t(stream) < o0->snap_bits_valid.size() && o0->snap_bits_valid[size_t(stream)]) {
+            memcpy(out, o0->snap_bits.data() + size_t(stream) * n_bits, n_bits);
+            return DAB_OK;
+        }
+    }
     OFDM_HANDLE(h);
     { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
-    if (!out || stream < 0 || stream >= o->n_streams || n_bits != o->frame_bits) return set_error(DAB_ERR_INVALID, "bad argument");
     StreamState st;
     int rc = copy_out(o, &st, o->states.ptr + stream, sizeof(st));
     if (rc != DAB_OK) return rc;
-    return copy_out(o, out, o->bits.ptr + (size_t(stream) * size_t(o->slots) + size_t(st.pending_slot)) * o->frame_bits, n_bits);
+    return copy_out(o, out, o->bits.ptr + (size_t(stream) * size_t(o->ring_slots) + size_t(st.pending_slot)) * o->frame_bits, n_bits);
 }
 
 int dab_ofdm_get_correlation_time_buffer(dab_ofdm* h, int stream, dab_c32* out, size_t n) {
@@ -997,7 +1144,7 @@ int dab_ofdm_get_correlation_time_buffer(dab_ofdm* h, int stream, dab_c32* out, 
     { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     const size_t cap = o->p.nb_null_period + o->p.nb_symbol_period;
     if (!out || stream < 0 || stream >= o->n_streams || n != cap) return set_error(DAB_ERR_INVALID, "bad argument (n must be nb_null_period + nb_symbol_period)");
-    if (o->raw_u8) return set_error(DAB_ERR_INVALID, "not available with raw_u8_ingest");
+    if (o->format != DAB_IQ_F32) return set_error(DAB_ERR_INVALID, "not available with a raw sample_format");
     StreamState st;
     int rc = copy_out(o, &st, o->states.ptr + stream, sizeof(st));
     if (rc != DAB_OK) return rc;
@@ -1071,11 +1218,13 @@ int dab_ofdm_demod_frames_device(dab_ofdm* h, const dab_c32* d_frames, size_t fr
                                  float* d_phase_error) {
     OFDM_HANDLE(h);
     if (!d_frames || !freq_offset || !d_bits || n_frames < 0) return set_error(DAB_ERR_INVALID, "null argument");
-    if (o->raw_u8) return set_error(DAB_ERR_INVALID, "stage-level entry takes complex float frames");
+    if (o->format != DAB_IQ_F32) return set_error(DAB_ERR_INVALID, "stage-level entry takes complex float frames");
     if (n_frames == 0) return DAB_OK;
-    std::vector<FrameDesc> descs(static_cast<size_t>(n_frames));
+    const int S = int(o->p.nb_frame_symbols), parts = o->n_chunks;
+    std::vector<FrameDesc> descs(static_cast<size_t>(n_frames) * size_t(parts));
     for (int f = 0; f < n_frames; f++) {
-        FrameDesc& d = descs[size_t(f)];
+        FrameDesc d;
+        memset(&d, 0, sizeof(d));
         d.src = reinterpret_cast<const float2*>(d_frames) + size_t(f) * frame_stride;
         d.mask = ~uint64_t(0);
         d.limit = o->p.nb_frame_symbols * o->p.nb_symbol_period;
@@ -1084,12 +1233,18 @@ int dab_ofdm_demod_frames_device(dab_ofdm* h, const dab_c32* d_frames, size_t fr
         d.valid = 1;
         d.bits = d_bits + size_t(f) * o->frame_bits;
         d.phase_err = d_phase_error ? d_phase_error + size_t(f) * o->p.nb_frame_symbols : nullptr;
-        d.fft_tap = nullptr;
-        d.vec_tap = nullptr;
+        d.l1_w_hi = -1;
+        int b = 0;
+        for (int c = 0; c < parts; c++) {
+            d.s_begin = b;
+            d.s_end = b + S / parts + (c < S % parts ? 1 : 0);
+            b = d.s_end;
+            descs[size_t(f) * size_t(parts) + size_t(c)] = d;
+        }
     }
-    DAB_CUDA_CHECK(o->stage_descs.reserve(size_t(n_frames)));
+    DAB_CUDA_CHECK(o->stage_descs.reserve(descs.size()));
     DAB_CUDA_CHECK(cudaMemcpyAsync(o->stage_descs.ptr, descs.data(), descs.size() * sizeof(FrameDesc), cudaMemcpyHostToDevice, o->stream));
-    int rc = launch_frame(o, o->stream, o->stage_descs.ptr, n_frames, false);
+    int rc = launch_frame(o, o->stream, o->stage_descs.ptr, int(descs.size()));
     // `descs` is a local: the upload must have left it before we return
     DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
     return rc;

@@ -8,12 +8,23 @@
 // ofdm_demodulator.cpp:608-618) is applied before frame k+1's PRS synchronisation.  A control pass therefore stops at a
 // frame dispatch; the host launches  control -> frame kernel -> control ...  and the next control pass first folds the
 // frame kernel's per-symbol phase errors into the fine frequency offset, then continues with the remaining samples.
+//
+// What the frame kernel is handed is a RANGE of symbols of a frame (FrameDesc): once a frame's PRS is synchronised its net
+// frequency offset is fixed (the only update in between is the previous frame's, which precedes the sync), so its symbols can be
+// demodulated in the call they arrive in instead of all at once when the frame completes.  Every sample then passes through
+// shared memory in the call that delivered it, and the frame kernel sums that call's UpdateSignalAverage windows
+// (ofdm_demodulator.cpp:934-950) on the way; the control kernel only evaluates the windows no item covered (NULL symbol,
+// the unfinished symbol at the end of a block, streams that are not locked) and folds all of them into the running average in
+// window order at the end of the call -- or earlier, the moment FindNullPowerDip needs the value.
 #pragma once
 #include "ofdm_device.cuh"
 #include "ofdm_frame.cuh"
-#include "ofdm_frame_dab.cuh"
+#include "ofdm_frame_v3.cuh"
 
 namespace dabb200 {
+
+constexpr int CTRL_MAX_OWNED = 8;    // UpdateSignalAverage window ranges per call that frame-kernel items may own (one per dispatch)
+constexpr int FRAME_MAX_CHUNKS = 4;  // work items one dispatch is split into (load balance: a frame is 76 - 153 symbols long)
 
 struct StreamState {
     // --- mirrors of the OFDM_Demod members (ofdm_demodulator.h:58-75)
@@ -36,28 +47,43 @@ struct StreamState {
     int64_t corr_base;       // absolute sample index of correlation-buffer element 0
     // --- OFDM_Frame_Buffer (ofdm_frame_buffer.h): virtual, [frame_start, frame_start + frame_cap)
     int64_t frame_start;
+    float frame_freq;        // net PLL frequency of the frame being received (fixed once its PRS is synchronised)
+    int32_t symbols_done;    // symbols [0, symbols_done) of that frame are demodulated or queued for the frame kernel
+    int32_t frame_slot;      // soft-bit buffer (ring slot) the frame is written to
     // --- cursor / current Process() call
     int64_t consumed;        // absolute index of the next unread sample
     int64_t call_begin;
     int64_t call_end;
-    int32_t call_needs_average;  // UpdateSignalAverage still to run for this call
+    int32_t avg_pending;         // UpdateSignalAverage of this call not folded into l1_average yet (see fold_average)
     int32_t pipeline_pending;    // a frame was dispatched; its phase errors still have to update the fine offset
-    int32_t pending_slot;        // output slot of that frame
-    int32_t frames_in_call;      // frames dispatched during this call
+    int32_t pending_slot;        // soft-bit ring slot of the most recently completed frame
+    int32_t frames_in_call;      // frames completed during this call
+    int32_t syncs_in_call;       // frames whose PRS was synchronised during this call (ring slot choice)
+    int32_t own_n;               // window ranges of this call owned by frame-kernel items
+    int32_t own_lo[CTRL_MAX_OWNED], own_hi[CTRL_MAX_OWNED];
     dab_ofdm_config cfg;
     dab_ofdm_frame_info pending_info;
 };
 
 struct ControlGeom {
     int n_symbols, symbol_period, null_period, cyclic_prefix, n_carriers;
-    int slots;               // output slots per stream and call
+    int slots;               // frames a stream can complete per call
+    int ring_slots;          // soft-bit buffers per stream: slots + 1 (the frame being received has one too)
     int n_streams;           // streams of the handle (row length of descs)
     int stream0;             // first stream this launch covers (launches are split into pipeline ways, see run_call)
+    int n_chunks;            // work items per dispatch (<= FRAME_MAX_CHUNKS)
+    int syms_per_chunk;      // target symbols per work item
+    int frame_passes;        // control passes of this call that are followed by a frame-kernel launch
+    int eager;               // 1: symbols of a frame still being received are demodulated in the call they arrive in
+    int frame_owns_l1;       // 1: the frame kernel sums the UpdateSignalAverage windows inside the symbols it reads
+    int l1_per_symbol;       // ... at most this many per symbol
+    uint32_t call_index;     // calls made on this handle so far (soft-bit ring slot choice)
     size_t frame_bits;
     uint64_t mask;           // stream index mask (ring size - 1 or ~0)
     uint64_t limit;          // samples addressable per stream (ring size, or the attached buffer's length)
     size_t stream_stride;    // samples between consecutive streams' bases
     const void* samples;     // base of stream 0
+    SampleFmt fmt;
     float2* ring;            // [n_streams][null_period] null-power-dip ring
     float2* corr_explicit;   // [n_streams][null_period] cold-start copy of the ring into the correlation buffer
     const float2* prs_fft_ref_conj;   // [NFFT]  conj(PRS)                               (ofdm_demodulator.cpp:130-132)
@@ -65,16 +91,19 @@ struct ControlGeom {
     float* impulse_response;          // [n_streams][NFFT]
     float* freq_response;             // [n_streams][NFFT]
     StreamState* states;
-    FrameDesc* descs;        // [slots][n_streams]
+    FrameDesc* descs;        // [frame_passes][n_streams][n_chunks]
     dab_ofdm_frame_info* infos;  // [n_streams][slots]
     int32_t* frames_in_call;     // [n_streams]
-    int8_t* bits;            // [n_streams][slots][frame_bits]
-    float* phase_err;        // [n_streams][slots][n_symbols]
+    int32_t* frame_slots;        // [n_streams][slots]: ring slot of the f-th frame completed in this call
+    int8_t* bits;            // [n_streams][ring_slots][frame_bits]
+    float* phase_err;        // [n_streams][n_symbols]
     const float2* twiddles;  // precomputed FFT twiddles (fft_twiddle_init_kernel)
-    float* l1_windows;       // [n_streams][l1_windows_stride] window averages of the current call (ofdm_l1_windows_kernel)
+    float* l1_windows;       // [n_streams][l1_windows_stride] window averages of the current call summed by the frame kernel
     int l1_windows_stride;
     float2* fft_tap;         // optional [n_streams][n_symbols * NFFT]
     float2* vec_tap;         // optional [n_streams][(n_symbols-1) * n_carriers]
+    const uint64_t* n_per_stream;  // samples of this call per stream, nullptr: n_uniform
+    uint64_t n_uniform;
 };
 
 constexpr int CTRL_L1_BATCH = 1024;  // windows whose L1 averages are computed in parallel before the sequential scan
@@ -82,7 +111,10 @@ constexpr int CTRL_L1_BATCH = 1024;  // windows whose L1 averages are computed i
 template <int NFFT>
 struct ControlSmem {
     using G = FftGeom<NFFT>;
-    static constexpr int THREADS = (G::T < 32) ? 32 : G::T;
+    // at least four warps whatever the FFT size: the transforms use the first N/16 threads, the L1 window scans (FindNullPowerDip
+    // walks whole blocks while a stream is unlocked) use all of them -- with one warp per stream a 1024-stream Mode II / III step
+    // spent 0.5 ms in the scans of the unlocked streams (profiles/r02a_mode_probe_baseline.txt)
+    static constexpr int THREADS = (G::T < 128) ? 128 : G::T;
     // `nat` (natural-order spectrum between two transforms) aliases exchange 1 and the L1 window batch aliases the (contiguous) exchanges: both
     // are only alive while no transform is in flight (every hand-over is separated by a CTA barrier)
     static_assert(G::E1_SIZE >= NFFT, "nat must fit into exchange 1");
@@ -100,7 +132,7 @@ __device__ __forceinline__ ArgMax argmax_combine(ArgMax a, ArgMax b) {
     return take_b ? b : a;
 }
 
-template <int NFFT, bool RAW_U8>
+template <int NFFT, int SB>
 struct Control {
     using G = FftGeom<NFFT>;
     static constexpr int T = G::T;
@@ -114,20 +146,19 @@ struct Control {
     float2* red;
     const void* src;
 
-    __device__ float2 sample(int64_t abs_index) const { return load_sample<RAW_U8>(src, uint64_t(abs_index) & geo.mask); }
+    __device__ float2 sample(int64_t abs_index) const { return load_sample<SB>(src, uint64_t(abs_index) & geo.mask, geo.fmt); }
     // element i of the reference's correlation buffer (null + PRS)
     __device__ float2 corr_at(int i) const {
         if (uint32_t(i) < st.corr_explicit_len) return geo.corr_explicit[size_t(stream) * geo.null_period + i];
         return sample(st.corr_base + i);
     }
 
-    // ---- CalculateL1Average (ofdm_demodulator.cpp:922-932) of `count` windows of K samples, window w at first + w * step
-    // L1 averages of `count` windows of K samples, window w starting at first + w * step, into l1buf.  A warp takes 8 windows at
-    // a time and walks them together, so that 8 independent loads are in flight per lane: one window after the other costs a
-    // full memory latency per window (~1 us), which made a single unlocked stream (FindNullPowerDip scans whole blocks) or a
-    // non-default signal_l1 configuration (more windows than the precomputed buffer holds) the long pole of a 1024-stream step
-    // (1.5 - 2.3 ms).  Per window the additions keep their order (lane-strided partial sums, then the butterfly).
-    __device__ void l1_windows(int64_t first, int step, int K, int count) {
+    // ---- CalculateL1Average (ofdm_demodulator.cpp:922-932) of `count` windows of K samples, window w starting at first + w * step,
+    // into out[0 .. count).  A warp takes 8 windows at a time and walks them together, so that 8 independent loads are in flight
+    // per lane: one window after the other costs a full memory latency per window (~1 us), which made a single unlocked stream
+    // (FindNullPowerDip scans whole blocks) the long pole of a 1024-stream step.  Per window the additions keep their order
+    // (lane-strided partial sums, then the butterfly): the frame kernel sums its windows the same way.  No barrier inside.
+    __device__ void l1_windows(float* out, int64_t first, int step, int K, int count) {
         constexpr int U = 8;
         const int lane = tid & 31, warp = tid >> 5, n_warps = THREADS / 32;
         for (int w = warp * U; w < count; w += n_warps * U) {
@@ -135,27 +166,35 @@ struct Control {
             float acc[U];
 #pragma unroll
             for (int u = 0; u < U; u++) acc[u] = 0.0f;
-            for (int i = lane; i < K; i += 32) {
-                float2 v[U];
+            // four strides of 32 samples per round: with the default 100-sample windows every load of the 8 windows is issued
+            // before the first addition (one memory round trip per 8 windows instead of four)
+            for (int i0 = lane; i0 < K; i0 += 128) {
+                float2 v[4][U];
 #pragma unroll
-                for (int u = 0; u < U; u++) v[u] = (w + u < count) ? sample(base + int64_t(u) * step + i) : make_float2(0.0f, 0.0f);
+                for (int q = 0; q < 4; q++)
 #pragma unroll
-                for (int u = 0; u < U; u++) acc[u] += fabsf(v[u].x) + fabsf(v[u].y);
+                    for (int u = 0; u < U; u++)
+                        v[q][u] = (w + u < count && i0 + 32 * q < K) ? sample(base + int64_t(u) * step + i0 + 32 * q) : make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+#pragma unroll
+                    for (int u = 0; u < U; u++) acc[u] += fabsf(v[q][u].x) + fabsf(v[q][u].y);
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 float a = acc[u];
 #pragma unroll
                 for (int d = 16; d >= 1; d >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, d);
-                if (lane == 0 && w + u < count) l1buf[w + u] = a / float(K);
+                if (lane == 0 && w + u < count) out[w + u] = a / float(K);
             }
         }
-        __syncthreads();
     }
 
-    // ---- UpdateSignalAverage (ofdm_demodulator.cpp:934-950): the per-window L1 averages of this call were computed by
-    // ofdm_l1_windows_kernel (all streams, all windows in parallel); only the sequential exponential average is left
-    __device__ void update_signal_average() {
+    // ---- UpdateSignalAverage (ofdm_demodulator.cpp:934-950) of the current call, folded into l1_average in window order.  The
+    // window averages come from the frame kernel where one of its items had the samples in shared memory (own_lo/own_hi, recorded
+    // at dispatch; those launches have completed: a dispatch ends its control pass) and are summed here otherwise.  Runs once per
+    // call: at the end of the stream's last active pass, or the moment FindNullPowerDip needs the average.
+    __device__ void fold_average() {
         const int64_t N = st.call_end - st.call_begin;
         const int K = st.cfg.signal_l1_nb_samples;
         if (N >= K && K > 0) {
@@ -165,12 +204,16 @@ struct Control {
             const float* win = geo.l1_windows + size_t(stream) * geo.l1_windows_stride;
             for (int64_t w0 = 0; w0 < n_windows; w0 += CTRL_L1_BATCH) {
                 const int count = int(min(int64_t(CTRL_L1_BATCH), n_windows - w0));
-                if (w0 + count <= geo.l1_windows_stride) {
-                    for (int w = tid; w < count; w += THREADS) l1buf[w] = win[w0 + w];
-                    __syncthreads();
-                } else {
-                    l1_windows(st.call_begin + w0 * L, L, K, count);  // window buffer too small for this call: compute here
+                int64_t cursor = w0;
+                for (int r = 0; r < st.own_n && cursor < w0 + count; r++) {
+                    const int64_t lo = max(int64_t(st.own_lo[r]), cursor), hi = min(int64_t(st.own_hi[r]), w0 + count - 1);
+                    if (hi < lo) continue;
+                    if (lo > cursor) l1_windows(l1buf + (cursor - w0), st.call_begin + cursor * L, L, K, int(lo - cursor));
+                    for (int64_t w = lo + tid; w <= hi; w += THREADS) l1buf[w - w0] = win[w];
+                    cursor = hi + 1;
                 }
+                if (cursor < w0 + count) l1_windows(l1buf + (cursor - w0), st.call_begin + cursor * L, L, K, int(w0 + count - cursor));
+                __syncthreads();
                 if (tid == 0) {
                     const float beta = st.cfg.signal_l1_update_beta;
                     float avg = st.l1_average;
@@ -180,12 +223,19 @@ struct Control {
                 __syncthreads();
             }
         }
-        if (tid == 0) st.call_needs_average = 0;
+        if (tid == 0) {
+            st.avg_pending = 0;
+            // every frame of this call reports the average of the whole block, as the reference's Process() has it before the first
+            // frame is dispatched
+            for (int f = 0; f < st.frames_in_call; f++) geo.infos[size_t(stream) * geo.slots + f].signal_average = st.l1_average;
+            st.pending_info.signal_average = st.l1_average;
+        }
         __syncthreads();
     }
 
     // ---- FindNullPowerDip (ofdm_demodulator.cpp:291-347)
     __device__ void find_null_power_dip() {
+        if (st.avg_pending) fold_average();  // the thresholds use the average over the whole block (UpdateSignalAverage runs first)
         const int64_t c0 = st.consumed;
         const int64_t N = st.call_end - c0;
         const int K = st.cfg.signal_l1_nb_samples;
@@ -196,7 +246,8 @@ struct Control {
         __syncthreads();
         for (int64_t w0 = 0; w0 < n_windows; w0 += CTRL_L1_BATCH) {
             const int count = int(min(int64_t(CTRL_L1_BATCH), n_windows - w0));
-            l1_windows(c0 + w0 * K, K, K, count);
+            l1_windows(l1buf, c0 + w0 * K, K, K, count);
+            __syncthreads();
             if (tid == 0) {
                 const float start_thresh = st.l1_average * st.cfg.null_l1_thresh_null_start;
                 const float end_thresh = st.l1_average * st.cfg.null_l1_thresh_null_end;
@@ -473,139 +524,179 @@ struct Control {
                 st.corr_length = 0;
                 st.fine_time_offset = offset;
                 st.state = DAB_OFDM_READING_SYMBOLS;
+                // from here to the end of the frame nothing changes the frequency offsets (the previous frame's fine update came
+                // before this synchronisation): the frame kernel may start on the symbols as they arrive
+                st.frame_freq = st.freq_coarse + st.freq_fine;
+                st.symbols_done = 0;
+                st.frame_slot = choose_slot_thread0();
+                st.syncs_in_call++;
                 st.pending_info.frame_start = st.frame_start;
                 st.pending_info.fine_time_offset = offset;
+                st.pending_info.coarse_offset = st.freq_coarse;
+                st.pending_info.fine_offset_used = st.freq_fine;
             }
         }
         __syncthreads();
     }
 
-    // ---- the fine-frequency half of CoordinatorThread (ofdm_demodulator.cpp:606-618, 632) for the frame dispatched before
-    __device__ void finish_pipeline() {
-        // the per-symbol phase errors arrive with one parallel load; the sum keeps the reference's symbol order
-        const float* pe = geo.phase_err + (size_t(stream) * geo.slots + st.pending_slot) * geo.n_symbols;
-        for (int s = tid; s < geo.n_symbols; s += THREADS) l1buf[s] = pe[s];
-        __syncthreads();
-        if (tid != 0) return;
-        float total = 0.0f;
-        for (int s = 0; s < geo.n_symbols; s++) total += l1buf[s];
-        const float avg = total / float(geo.n_symbols);
-        const float two_pi = 3.14159265358979323846f * 2.0f;
-        const float fine_error = (1.0f / float(NFFT)) * avg / two_pi;  // CalculateFineFrequencyError :821-823
-        update_fine_thread0(-st.cfg.sync_fine_freq_update_beta * fine_error);
-        st.pending_info.fine_offset_after = st.freq_fine;
-        st.total_frames_read++;
-        geo.infos[size_t(stream) * geo.slots + st.pending_slot] = st.pending_info;
-        st.pipeline_pending = 0;
+    // Soft-bit ring slot for the frame whose PRS was just synchronised.  The j-th synchronisation of call c takes slot (c + j) mod R
+    // unless a frame completed earlier in this call still sits there: streams that complete one frame per call (the batched steady
+    // state) then all use the same slot in the same call, and their frames leave the device as one strided copy.
+    __device__ int choose_slot_thread0() {
+        const int R = geo.ring_slots;
+        int cand = int((geo.call_index + uint32_t(st.syncs_in_call)) % uint32_t(R));
+        for (int k = 0; k < R; k++) {
+            bool busy = false;
+            for (int f = 0; f < st.frames_in_call; f++) busy = busy || (geo.frame_slots[size_t(stream) * geo.slots + f] == cand);
+            if (!busy) break;
+            cand = (cand + 1) % R;
+        }
+        return cand;
     }
 
-    // ---- ReadSymbols (ofdm_demodulator.cpp:550-577): returns true when a frame was dispatched
-    __device__ bool read_symbols_thread0() {
-        const int64_t frame_cap = int64_t(geo.n_symbols) * geo.symbol_period + geo.null_period;
-        const int64_t frame_end = st.frame_start + frame_cap;
-        const int64_t take = min(st.call_end - st.consumed, frame_end - st.consumed);
-        st.consumed += take;
-        if (st.consumed != frame_end) return false;
-        // the trailing NULL symbol becomes the head of the next correlation buffer (:557-562)
-        st.corr_base = frame_end - geo.null_period;
-        st.corr_length = uint32_t(geo.null_period);
-        st.corr_explicit_len = 0;
-        // hand the frame to the frame kernel (SignalStart, :572)
-        const int slot = st.frames_in_call;
+    // ---- the fine-frequency half of CoordinatorThread (ofdm_demodulator.cpp:606-618, 632) for the frame that just completed
+    __device__ void finish_pipeline() {
+        // the per-symbol phase errors arrive with one parallel load; the sum keeps the reference's symbol order
+        const float* pe = geo.phase_err + size_t(stream) * geo.n_symbols;
+        for (int s = tid; s < geo.n_symbols; s += THREADS) l1buf[s] = pe[s];
+        __syncthreads();
+        if (tid == 0) {
+            float total = 0.0f;
+            for (int s = 0; s < geo.n_symbols; s++) total += l1buf[s];
+            const float avg = total / float(geo.n_symbols);
+            const float two_pi = 3.14159265358979323846f * 2.0f;
+            const float fine_error = (1.0f / float(NFFT)) * avg / two_pi;  // CalculateFineFrequencyError :821-823
+            update_fine_thread0(-st.cfg.sync_fine_freq_update_beta * fine_error);
+            st.pending_info.fine_offset_after = st.freq_fine;
+            st.total_frames_read++;
+            geo.infos[size_t(stream) * geo.slots + (st.frames_in_call - 1)] = st.pending_info;
+            st.pipeline_pending = 0;
+        }
+        __syncthreads();
+    }
+
+    // Hands symbols [st.symbols_done, s_end) of the frame being received to the frame kernel launched after this pass, split into
+    // up to n_chunks work items, and lets those items own the UpdateSignalAverage windows inside the samples they read.
+    __device__ void dispatch_thread0(int pass, int s_end) {
+        const int s_lo = st.symbols_done;
+        const int n_new = s_end - s_lo;
+        const int SP = geo.symbol_period;
+        int parts = (n_new + geo.syms_per_chunk - 1) / geo.syms_per_chunk;
+        parts = max(1, min(parts, geo.n_chunks));
+        // window ownership: windows [w_lo, w_hi] of this call lie inside the samples the items load
+        const int K = st.cfg.signal_l1_nb_samples;
+        const int L = K * st.cfg.signal_l1_nb_decimate;
+        const int64_t N = st.call_end - st.call_begin;
+        int64_t n_windows = 0;
+        if (K > 0 && L > 0 && N >= K) n_windows = (N - K + L - 1) / L;
+        // the frame kernel sums at most l1_per_symbol windows per symbol (two per sub-warp) of at most L1_PREFIX + 1 samples
+        const bool can_own = geo.frame_owns_l1 && st.avg_pending && n_windows > 0 && K - 1 <= L1_PREFIX && st.own_n < CTRL_MAX_OWNED &&
+                             n_windows <= int64_t(geo.l1_windows_stride) && (SP + K - 1) / L + 1 <= geo.l1_per_symbol;
+        int64_t own_lo = -1, own_hi = -2;
         FrameDesc d;
         d.src = src;
         d.mask = geo.mask;
         d.limit = geo.limit;
         d.start = st.frame_start;
-        d.freq = st.freq_coarse + st.freq_fine;
+        d.freq = st.frame_freq;
         d.valid = 1;
-        d.bits = geo.bits + (size_t(stream) * geo.slots + slot) * geo.frame_bits;
-        d.phase_err = geo.phase_err + (size_t(stream) * geo.slots + slot) * geo.n_symbols;
+        d.bits = geo.bits + (size_t(stream) * geo.ring_slots + st.frame_slot) * geo.frame_bits;
+        d.phase_err = geo.phase_err + size_t(stream) * geo.n_symbols;
         d.fft_tap = geo.fft_tap ? geo.fft_tap + size_t(stream) * geo.n_symbols * NFFT : nullptr;
         d.vec_tap = geo.vec_tap ? geo.vec_tap + size_t(stream) * (geo.n_symbols - 1) * geo.n_carriers : nullptr;
-        geo.descs[size_t(slot) * geo.n_streams + stream] = d;
-        st.pending_info.coarse_offset = st.freq_coarse;
-        st.pending_info.fine_offset_used = st.freq_fine;
+        d.l1_origin = st.call_begin;
+        d.l1_k = K;
+        d.l1_step = L;
+        FrameDesc* out = geo.descs + (size_t(pass) * geo.n_streams + stream) * geo.n_chunks;
+        int b = s_lo;
+        for (int c = 0; c < parts; c++) {
+            const int e = b + n_new / parts + (c < n_new % parts ? 1 : 0);
+            d.s_begin = b;
+            d.s_end = e;
+            d.l1_out = nullptr;
+            d.l1_w_lo = 0;
+            d.l1_w_hi = -1;
+            if (can_own) {
+                // first item of the dispatch: windows that begin inside its first loaded symbol (and inside this call); later items:
+                // windows that end after their reference symbol (the previous item takes those ending in it)
+                const int64_t first_loaded = st.frame_start + int64_t(max(b - 1, 0)) * SP;
+                const int64_t lo_abs = (c == 0) ? max(first_loaded, st.call_begin) : st.frame_start + int64_t(b) * SP - K + 1;
+                const int64_t hi_abs = st.frame_start + int64_t(e) * SP - K;   // last admissible window start
+                const int64_t rel_lo = max(lo_abs - st.call_begin, int64_t(0));
+                const int64_t w_lo = (rel_lo + L - 1) / L;
+                int64_t w_hi = (hi_abs >= st.call_begin) ? (hi_abs - st.call_begin) / L : -1;
+                w_hi = min(w_hi, n_windows - 1);
+                if (w_hi >= w_lo) {
+                    d.l1_out = geo.l1_windows + size_t(stream) * geo.l1_windows_stride;
+                    d.l1_w_lo = int(w_lo);
+                    d.l1_w_hi = int(w_hi);
+                    if (own_lo < 0) own_lo = w_lo;
+                    own_hi = w_hi;
+                }
+            }
+            out[c] = d;
+            b = e;
+        }
+        if (own_hi >= own_lo && own_lo >= 0) {
+            st.own_lo[st.own_n] = int(own_lo);
+            st.own_hi[st.own_n] = int(own_hi);
+            st.own_n++;
+        }
+        st.symbols_done = s_end;
+    }
+
+    // ---- ReadSymbols (ofdm_demodulator.cpp:550-577): returns true when the pass has to stop for the frame kernel
+    __device__ bool read_symbols_thread0(int pass, bool& dispatched) {
+        const int S = geo.n_symbols;
+        const int64_t frame_cap = int64_t(S) * geo.symbol_period + geo.null_period;
+        const int64_t frame_end = st.frame_start + frame_cap;
+        const int64_t take = min(st.call_end - st.consumed, frame_end - st.consumed);
+        st.consumed += take;
+        const bool may_dispatch = pass < geo.frame_passes;
+        if (st.consumed != frame_end) {
+            // the block ends inside the frame: the symbols that are complete can be demodulated now
+            if (geo.eager && may_dispatch) {
+                const int avail = int(min(int64_t(S), (st.consumed - st.frame_start) / geo.symbol_period));
+                if (avail > st.symbols_done) {
+                    dispatch_thread0(pass, avail);
+                    dispatched = true;
+                }
+            }
+            return false;
+        }
+        // the trailing NULL symbol becomes the head of the next correlation buffer (:557-562)
+        st.corr_base = frame_end - geo.null_period;
+        st.corr_length = uint32_t(geo.null_period);
+        st.corr_explicit_len = 0;
+        // the frame is complete (SignalStart, :572): whatever the frame kernel has not seen yet goes out now
+        const bool need_kernel = st.symbols_done < S;
+        if (need_kernel) {
+            dispatch_thread0(pass, S);
+            dispatched = true;
+        }
+        const int f = st.frames_in_call;
+        geo.frame_slots[size_t(stream) * geo.slots + f] = st.frame_slot;
         st.pending_info.signal_average = st.l1_average;
         st.pending_info.total_desync = st.total_frames_desync;
-        st.pending_slot = slot;
+        st.pending_info.slot = st.frame_slot;
+        st.pending_slot = st.frame_slot;
         st.pipeline_pending = 1;
-        st.frames_in_call = slot + 1;
+        st.frames_in_call = f + 1;
         st.state = DAB_OFDM_READING_NULL_AND_PRS;
-        return true;
+        return need_kernel;
     }
 };
 
-// CalculateL1Average (ofdm_demodulator.cpp:922-932) for every window UpdateSignalAverage (:934-950) visits in the current call:
-// window w of stream s covers samples [call_begin + w L, + K).  One warp per group of L1_WB windows, every load of the group
-// issued before the first use (the access pattern -- 800 bytes out of every 4000 -- is DRAM-latency bound otherwise).
-constexpr int L1_WB = 4;
-template <bool RAW_U8>
-__global__ void __launch_bounds__(256) ofdm_l1_windows_kernel(ControlGeom geo, int n_streams, int max_windows) {
-    const int lane = threadIdx.x & 31;
-    const int warps_per_block = blockDim.x >> 5;
-    const int groups = (max_windows + L1_WB - 1) / L1_WB;
-    const int total = n_streams * groups;
-    for (int task = blockIdx.x * warps_per_block + (threadIdx.x >> 5); task < total; task += gridDim.x * warps_per_block) {
-        const int stream = geo.stream0 + task / groups, w0 = (task % groups) * L1_WB;
-        const StreamState* st = geo.states + stream;
-        const int K = st->cfg.signal_l1_nb_samples;
-        const int L = K * st->cfg.signal_l1_nb_decimate;
-        const int64_t call_begin = st->call_begin;
-        const int64_t N = st->call_end - call_begin;
-        if (K <= 0 || L <= 0 || N < K) continue;
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(geo.samples) + size_t(stream) * geo.stream_stride * (RAW_U8 ? 2 : 8);
-        // window b: samples [first, first + K) of the stream; `flat` when it does not wrap around the ring
-        bool live[L1_WB], flat[L1_WB];
-        uint64_t first[L1_WB];
-        float acc[L1_WB];
-#pragma unroll
-        for (int b = 0; b < L1_WB; b++) {
-            live[b] = (w0 + b < max_windows) && (int64_t(w0 + b) * L < N - K);  // loop condition i < M of the reference
-            first[b] = uint64_t(call_begin + int64_t(w0 + b) * L) & geo.mask;
-            flat[b] = (geo.mask == ~uint64_t(0)) || (first[b] + uint64_t(K) <= geo.mask + 1);
-            acc[b] = 0.0f;
-        }
-        for (int i0 = 0; i0 < K; i0 += 128) {
-            float2 v[L1_WB][4];
-#pragma unroll
-            for (int b = 0; b < L1_WB; b++) {
-                const unsigned char* p = src + first[b] * (RAW_U8 ? 2 : 8);
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int i = i0 + lane + 32 * q;
-                    v[b][q] = make_float2(0.0f, 0.0f);
-                    if (live[b] && i < K) {
-                        if (flat[b]) v[b][q] = load_sample_ptr<RAW_U8>(p + i * (RAW_U8 ? 2 : 8));
-                        else v[b][q] = load_sample<RAW_U8>(src, (first[b] + uint64_t(i)) & geo.mask);
-                    }
-                }
-            }
-#pragma unroll
-            for (int b = 0; b < L1_WB; b++)
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (i0 + lane + 32 * q < K) acc[b] += fabsf(v[b][q].x) + fabsf(v[b][q].y);
-        }
-#pragma unroll
-        for (int b = 0; b < L1_WB; b++) {
-            float a = acc[b];
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, d);
-            if (lane == 0 && live[b]) geo.l1_windows[size_t(stream) * geo.l1_windows_stride + w0 + b] = a / float(K);
-        }
-    }
-}
-
-// pass: index of this control pass within the call (0 = first).  Frame slot `pass` is the one a dispatch in this pass fills.
-template <int NFFT, bool RAW_U8>
+// pass: index of this control pass within the call (0 = first; it also opens the call: OFDM_Demod::Process's entry,
+// ofdm_demodulator.cpp:235-243).  Passes below geo.frame_passes are followed by a frame-kernel launch over the items they wrote.
+template <int NFFT, int SB>
 __global__ void __launch_bounds__(ControlSmem<NFFT>::THREADS, 4)
 ofdm_control_kernel(ControlGeom geo, int pass) {
     using G = FftGeom<NFFT>;
-    using C = Control<NFFT, RAW_U8>;
+    using C = Control<NFFT, SB>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ StreamState st;
-    __shared__ int stop_flag;
+    __shared__ int stop_flag, dispatched_flag;
     const int stream = geo.stream0 + blockIdx.x, tid = threadIdx.x;
 
     float2* tw1 = reinterpret_cast<float2*>(smem_raw);
@@ -619,22 +710,36 @@ ofdm_control_kernel(ControlGeom geo, int pass) {
     if (tid == 0) {
         st = geo.states[stream];
         stop_flag = 0;
-        // descriptor of the slot this pass may fill starts out invalid
-        if (pass < geo.slots) geo.descs[size_t(pass) * geo.n_streams + stream].valid = 0;
+        dispatched_flag = 0;
+        if (pass == 0) {
+            const uint64_t n = geo.n_per_stream ? geo.n_per_stream[stream] : geo.n_uniform;
+            st.call_begin = st.call_end;
+            st.call_end = st.call_begin + int64_t(n);
+            st.avg_pending = (n > 0) ? 1 : 0;
+            st.frames_in_call = 0;
+            st.syncs_in_call = 0;
+            st.own_n = 0;
+        }
     }
+    // the work items this pass may fill start out invalid
+    if (pass < geo.frame_passes && tid < geo.n_chunks) geo.descs[(size_t(pass) * geo.n_streams + stream) * geo.n_chunks + tid].valid = 0;
     __syncthreads();
-    // nothing to do: no frame waiting for its fine update and no unread samples
-    if (!st.pipeline_pending && st.consumed >= st.call_end) return;
+    // nothing to do: no frame waiting for its fine update, no unread samples, the signal average of the call is folded
+    if (!st.pipeline_pending && st.consumed >= st.call_end && !st.avg_pending) {
+        if (pass == 0 && tid == 0) {
+            geo.states[stream] = st;
+            geo.frames_in_call[stream] = 0;
+        }
+        return;
+    }
 
     __shared__ int tw_loaded;  // the twiddle tables are only staged when a synchronisation stage actually runs
     if (tid == 0) tw_loaded = 0;
-    const void* src = RAW_U8 ? static_cast<const void*>(reinterpret_cast<const uchar2*>(geo.samples) + size_t(stream) * geo.stream_stride)
-                             : static_cast<const void*>(reinterpret_cast<const float2*>(geo.samples) + size_t(stream) * geo.stream_stride);
+    const void* src = reinterpret_cast<const unsigned char*>(geo.samples) + size_t(stream) * geo.stream_stride * size_t(SB);
     C ctl{geo, st, stream, tid, tw1, tw2, e1, e2, nat, l1buf, red, src};
 
     if (st.pipeline_pending) ctl.finish_pipeline();
     __syncthreads();
-    if (st.call_needs_average) ctl.update_signal_average();
 
     // OFDM_Demod::Process main loop (ofdm_demodulator.cpp:245-274)
     while (st.consumed < st.call_end && !stop_flag) {
@@ -664,13 +769,19 @@ ofdm_control_kernel(ControlGeom geo, int pass) {
             break;
         case DAB_OFDM_READING_SYMBOLS:
             if (tid == 0) {
-                if (ctl.read_symbols_thread0()) stop_flag = 1;  // wait for the frame kernel before touching the next PRS
+                bool dispatched = false;
+                if (ctl.read_symbols_thread0(pass, dispatched)) stop_flag = 1;  // wait for the frame kernel before touching the next PRS
+                if (dispatched) dispatched_flag = 1;
             }
             __syncthreads();
+            // a frame whose symbols were all demodulated as they arrived needs no kernel: its fine-frequency update runs right here
+            if (st.pipeline_pending && !stop_flag) ctl.finish_pipeline();
             break;
         }
     }
     __syncthreads();
+    // the call is over for this stream and every item it dispatched has run: fold UpdateSignalAverage
+    if (st.avg_pending && st.consumed >= st.call_end && !dispatched_flag && !st.pipeline_pending) ctl.fold_average();
     if (tid == 0) {
         geo.states[stream] = st;
         geo.frames_in_call[stream] = st.frames_in_call;

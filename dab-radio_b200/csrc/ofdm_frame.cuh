@@ -14,18 +14,73 @@
 
 namespace dabb200 {
 
+// How the stream buffers hold a sample (examples/app_helpers/app_iq_readers.h:17-88): complex float, or a raw
+// integer pair straight from the front end, dequantised on the way into the registers as the reference's QuantisedIQ<T>::to_c32 +
+// scale does:  value = (float(raw) - BIAS) * (1 / MAX_AMPLITUDE).  The kernels are compiled per sample SIZE (8 / 2 / 4 bytes); which
+// integer type a 2- or 4-byte sample is (signedness, byte order) is a runtime parameter: a signed value is read as
+// unsigned ^ sign bit with the bias raised by 2^(bits-1) (exact in fp32), a big-endian 16-bit pair costs one PRMT.
+struct SampleFmt {
+    uint32_t flip;   // xor mask on the unsigned component: 0 (unsigned), 0x80 (s8), 0x8000 (s16)
+    uint32_t prmt;   // byte selector for the 4-byte formats: 0x3210 little endian, 0x2301 big endian
+    float bias;      // u8 127.5, s8 128, u16 32767.5, s16 32768
+    float scale;     // 1 / MAX_AMPLITUDE: u8 1/127.5, s8 1/127, u16 1/32767.5, s16 1/32767
+};
+
+// SB = bytes per complex sample: 8 (float2), 2 (u8 / s8 pair), 4 (u16 / s16 pair)
+template <int SB>
+__device__ __forceinline__ float2 decode_sample(uint32_t raw, const SampleFmt& f) {
+    uint32_t i, q;
+    if (SB == 2) {
+        i = raw & 0xFFu;
+        q = (raw >> 8) & 0xFFu;
+    } else {
+        raw = __byte_perm(raw, 0u, f.prmt);
+        i = raw & 0xFFFFu;
+        q = raw >> 16;
+    }
+    return make_float2((float(i ^ f.flip) - f.bias) * f.scale, (float(q ^ f.flip) - f.bias) * f.scale);
+}
+
+template <int SB>
+__device__ __forceinline__ float2 load_sample_ptr(const void* p, const SampleFmt& f) {
+    if (SB == 2) return decode_sample<2>(uint32_t(__ldg(reinterpret_cast<const unsigned short*>(p))), f);
+    if (SB == 4) return decode_sample<4>(__ldg(reinterpret_cast<const unsigned int*>(p)), f);
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
+template <int SB>
+__device__ __forceinline__ float2 load_sample(const void* src, uint64_t index, const SampleFmt& f) {
+    return load_sample_ptr<SB>(reinterpret_cast<const unsigned char*>(src) + index * uint64_t(SB), f);
+}
+
+// One work item of the frame kernels: symbols [s_begin, s_end) of one transmission frame of one stream.  The item writes the
+// cyclic-prefix phase error of each of its symbols and the soft-bit rows s - 1 (DQPSK of symbols s - 1 and s) for s >= 1; for
+// s_begin > 0 it transforms symbol s_begin - 1 once more as the differential reference.  A frame is covered by any tiling of
+// [0, S) into items -- chunks of a frame that completed in this Process() call, or the symbols that arrived so far of a frame
+// still being received (ofdm_control.cuh decides).
 struct FrameDesc {
-    const void* src;       // float2 (or uchar2 for raw-u8 ingest) sample base of the stream
+    const void* src;       // sample base of the stream (SampleFmt layout)
     uint64_t mask;         // index mask: ring size - 1, or ~0 for a linear buffer
-    int64_t start;         // sample index of the PRS cyclic-prefix start
+    uint64_t limit;        // samples addressable from src without wrapping (ring size, or the length of a linear buffer):
+                           // bounds the 16-byte-granular bulk copies of the v3 kernel
+    int64_t start;         // sample index of the PRS cyclic-prefix start (symbol 0 of the frame)
     float freq;            // net PLL frequency (coarse + fine), cycles / sample
-    int32_t valid;         // 0: nothing to do for this frame slot
-    int8_t* bits;          // out: (S-1) * 2 * ncarr soft bits
+    int32_t valid;         // 0: nothing to do for this item
+    int32_t s_begin, s_end;
+    int8_t* bits;          // out: (S-1) * 2 * ncarr soft bits of the frame
     float* phase_err;      // out: S cyclic-prefix phase errors (radians), one per symbol
     float2* fft_tap;       // optional GUI tap: S * NFFT spectra (natural bin order), else nullptr
     float2* vec_tap;       // optional GUI tap: (S-1) * ncarr DQPSK vectors (carrier order), else nullptr
-    uint64_t limit;        // samples addressable from src without wrapping (ring size, or the length of a linear buffer):
-                           // bounds the 16-byte-granular bulk copies of the v3 kernel
+    // UpdateSignalAverage (ofdm_demodulator.cpp:934-950) windows this item computes while their samples sit in shared memory:
+    // window w covers samples [l1_origin + w * l1_step, + l1_k); the item owns w in [l1_w_lo, l1_w_hi] whose last sample lies in
+    // one of its symbols after l1_after (absolute sample index; the windows ending earlier belong to the previous item)
+    float* l1_out;         // [window] averages of the current call, nullptr: none
+    int64_t l1_origin;
+    int64_t l1_after;
+    int32_t l1_k, l1_step;
+    int32_t l1_w_lo, l1_w_hi;
 };
 
 struct FrameGeom {
@@ -33,26 +88,24 @@ struct FrameGeom {
     int symbol_period;
     int cyclic_prefix;
     int n_carriers;
-    int syms_per_chunk;    // DQPSK outputs per work item
-    int n_chunks;          // ceil((S-1) / syms_per_chunk)
+    SampleFmt fmt;
     const int16_t* bin_to_pos;      // [NFFT]: de-interleaved soft-bit position of FFT bin k, -1 for DC / guard bins
     const int16_t* bin_to_carrier;  // [NFFT]: carrier index (DQPSK vector order) of bin k, -1 if unused
     const float2* twiddles;         // [TW1_SIZE + TW2_SIZE] precomputed FFT twiddles
 };
 
-template <bool RAW_U8>
-__device__ __forceinline__ float2 load_sample(const void* src, uint64_t index) {
-    if (RAW_U8) {
-        // examples/app_helpers/app_iq_readers.h:17-69: (u8 - 127.5) * (1 / 127.5)
-        const uchar2 q = __ldg(reinterpret_cast<const uchar2*>(src) + index);
-        const float scale = 1.0f / 127.5f;
-        return make_float2((float(q.x) - 127.5f) * scale, (float(q.y) - 127.5f) * scale);
-    }
-    float2 v;
-    const float2* p = reinterpret_cast<const float2*>(src) + index;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-    return v;
-}
+// The DAB transmission-mode geometry (the four modes of dab_ofdm_params_ref.cpp:10-57 share cp = 63 N / 256, symbol = N + cp,
+// carriers = 3 N / 4): what the v3 kernel is specialised for.
+template <int NFFT>
+struct DabGeom {
+    static constexpr int CP = 63 * NFFT / 256;
+    static constexpr int SP = NFFT + CP;
+    static constexpr int NCARR = 3 * NFFT / 4;
+    static constexpr int HALF = NCARR / 2;
+    static constexpr int TAIL0 = NFFT - CP;              // FFT-window index pairing with cyclic-prefix sample 0
+    static __host__ __device__ constexpr bool matches(int sp, int cp, int ncarr) { return sp == SP && cp == CP && ncarr == NCARR; }
+    static __host__ __device__ constexpr bool bin_used(int k) { return (k >= 1 && k <= HALF) || (k >= NFFT - HALF && k < NFFT); }
+};
 
 constexpr int FRAME_CTA_THREADS = 128;
 
@@ -69,9 +122,12 @@ struct FrameSmem {
     }
 };
 
-template <int NFFT, bool RAW_U8>
+// Generic-geometry frame kernel: any OFDM_Params the reference API accepts (cp <= nfft / 4, carriers a multiple of 8).  The four
+// DAB transmission modes run ofdm_frame_v3_kernel instead; DAB_B200_GENERIC_FRAME_KERNEL=1 routes them here too (cross-check in
+// tests/test_ofdm_gpu.py).  It does not compute UpdateSignalAverage windows (the control kernel evaluates them itself then).
+template <int NFFT, int SB>
 __global__ void __launch_bounds__(FRAME_CTA_THREADS, 4)
-ofdm_frame_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_frames) {
+ofdm_frame_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_items) {
     using G = FftGeom<NFFT>;
     using SM = FrameSmem<NFFT>;
     constexpr int T = G::T;
@@ -80,6 +136,7 @@ ofdm_frame_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_fram
     constexpr int RED_WIDTH = (T < 32) ? T : 32;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int n_loop_s;
     float2* tw1 = reinterpret_cast<float2*>(smem_raw);
     float2* tw2 = tw1 + G::TW1_SIZE;
     const int group = threadIdx.x / T, t = threadIdx.x % T;
@@ -89,23 +146,17 @@ ofdm_frame_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_fram
     int8_t* stage = reinterpret_cast<int8_t*>(e2 + G::E2_SIZE);
     float2* red = reinterpret_cast<float2*>(stage + SM::stage_bytes(geo.n_carriers));
 
-    const int n_items = n_frames * geo.n_chunks;
     const int item = blockIdx.x * GROUPS + group;
-    const int frame = (item < n_items) ? item / geo.n_chunks : 0;
-    const int chunk = (item < n_items) ? item % geo.n_chunks : 0;
-    const FrameDesc desc = descs[frame];
-    const bool active = (item < n_items) && desc.valid != 0;
-    // a CTA without any frame to demodulate (streams that completed no frame in this pass) leaves at once
-    if (GROUPS == 1) {
-        if (!active) return;
-    } else {
-        if (!__syncthreads_or(active ? 1 : 0)) return;
-    }
+    const FrameDesc desc = descs[(item < n_items) ? item : 0];
+    const bool active = (item < n_items) && desc.valid != 0 && desc.s_end > desc.s_begin;
+    // a CTA without any symbol to demodulate leaves at once
+    if (threadIdx.x == 0) n_loop_s = 0;
+    if (!__syncthreads_or(active ? 1 : 0)) return;
+    const int s_load0 = max(desc.s_begin - 1, 0);   // first symbol transformed: the differential reference (or the PRS itself)
+    if (active && t == 0) atomicMax(&n_loop_s, desc.s_end - s_load0);
     fft_load_twiddles<NFFT>(tw1, geo.twiddles, threadIdx.x, FRAME_CTA_THREADS);
 
-    const int S = geo.n_symbols, sp = geo.symbol_period, cp = geo.cyclic_prefix, ncarr = geo.n_carriers;
-    const int s_first = chunk * geo.syms_per_chunk;                  // first symbol whose DQPSK output this item owns
-    const int s_out_end = min(s_first + geo.syms_per_chunk, S - 1);  // one past the last owned output symbol
+    const int sp = geo.symbol_period, cp = geo.cyclic_prefix, ncarr = geo.n_carriers;
 
     // soft-bit positions of my 16 output bins (fixed for the whole kernel), two int16 per register
     uint32_t pos_pack[8];
@@ -122,24 +173,26 @@ ofdm_frame_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_fram
     for (int r = 0; r < 16; r++) prev[r] = make_float2(0.0f, 0.0f);
     int staged = -1;  // output symbol sitting in `stage` (group-uniform), not yet written to HBM
 
-    __syncthreads();  // twiddle tables ready
+    __syncthreads();  // twiddle tables and the CTA's loop count ready
+    const int n_loop = n_loop_s;
 
-    for (int si = 0; si <= geo.syms_per_chunk; si++) {
-        const int s = s_first + si;
-        const bool sym_active = active && (s <= s_out_end);  // s_out_end <= S - 1
+    for (int si = 0; si < n_loop; si++) {
+        const int s = s_load0 + si;
+        const bool sym_active = active && (s < desc.s_end);
+        const bool own = sym_active && (s >= desc.s_begin);
         float2 v[16];
         float2 corr = make_float2(0.0f, 0.0f);
         if (sym_active) {
             const uint64_t sym0 = uint64_t(desc.start + int64_t(s) * sp);
             const PllSymbol pll = pll_symbol(desc.freq, s * sp, sp);
-            // FFT window (cyclic prefix removed, ofdm_demodulator.cpp:705) and the prefix itself: coalesced 8-byte loads
+            // FFT window (cyclic prefix removed, ofdm_demodulator.cpp:705) and the prefix itself: coalesced loads
 #pragma unroll
-            for (int j = 0; j < 16; j++) v[j] = load_sample<RAW_U8>(desc.src, (sym0 + uint64_t(cp + t + T * j)) & desc.mask);
+            for (int j = 0; j < 16; j++) v[j] = load_sample<SB>(desc.src, (sym0 + uint64_t(cp + t + T * j)) & desc.mask, geo.fmt);
             float2 head[4];
 #pragma unroll
             for (int j = 12; j < 16; j++) {
                 const int w = t + T * j;
-                head[j - 12] = (w >= tail0) ? load_sample<RAW_U8>(desc.src, (sym0 + uint64_t(w - tail0)) & desc.mask) : make_float2(0.0f, 0.0f);
+                head[j - 12] = (w >= tail0) ? load_sample<SB>(desc.src, (sym0 + uint64_t(w - tail0)) & desc.mask, geo.fmt) : make_float2(0.0f, 0.0f);
             }
 #pragma unroll
             for (int j = 0; j < 16; j++) v[j] = pll_rotate(pll, v[j], cp + t + T * j);
@@ -164,7 +217,7 @@ ofdm_frame_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_fram
         fft_pass1<NFFT>(v, t, e1, tw1);
         __syncthreads();  // ---- barrier A: exchange 1 complete, correlation partials visible, previous staging complete
 
-        if (sym_active && t == 0 && desc.phase_err != nullptr && (s < s_out_end || s == S - 1)) {
+        if (own && t == 0 && desc.phase_err != nullptr) {
             float2 tot = corr;
             if (WARPS_PER_GROUP > 1) {
                 tot = red[0];
@@ -184,7 +237,7 @@ ofdm_frame_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_fram
         __syncthreads();  // ---- barrier B: exchange 2 complete, staging buffer free
         fft_pass3<NFFT>(v, t, e2);
 
-        if (sym_active && desc.fft_tap != nullptr && (s < s_out_end || s == S - 1)) {
+        if (own && desc.fft_tap != nullptr) {
 #pragma unroll
             for (int r = 0; r < 16; r++) desc.fft_tap[size_t(s) * NFFT + fft_out_bin<NFFT>(t, r)] = v[r];
         }

@@ -149,7 +149,7 @@ struct Viterbi {
     int max_smem_optin = 0;
     int oneshot_slot = -1;  // schedule slot reused by dab_viterbi_decode_one
     uint64_t launches = 0;
-    std::mutex mtx;
+    std::recursive_mutex mtx;   // recursive: dab_viterbi_decode_one holds it across its schedule slot write and the decode
 };
 
 static int upload_schedules(Viterbi* v) {
@@ -317,7 +317,7 @@ int dab_viterbi_add_schedule(dab_viterbi* h, const dab_vit_schedule* s) {
     DevSchedule d;
     int rc = digest_schedule(s, &d);
     if (rc != DAB_OK) return rc;
-    std::lock_guard<std::mutex> lock(v->mtx);
+    std::lock_guard<std::recursive_mutex> lock(v->mtx);
     if (v->schedules.size() >= DAB_VIT_MAX_SCHEDULES) return set_error(DAB_ERR_CAPACITY, "more than %d schedules", DAB_VIT_MAX_SCHEDULES);
     v->schedules.push_back(d);
     v->schedules_dirty = true;
@@ -336,7 +336,8 @@ int dab_viterbi_decode_jobs_device(dab_viterbi* h, const int8_t* d_soft, size_t 
     auto* v = reinterpret_cast<Viterbi*>(h);
     if (!v) return set_error(DAB_ERR_INVALID, "null handle");
     if (n_jobs < 0 || (n_jobs > 0 && (!d_soft || !d_jobs || !d_out))) return set_error(DAB_ERR_INVALID, "null buffer");
-    std::lock_guard<std::mutex> lock(v->mtx);
+    std::lock_guard<std::recursive_mutex> lock(v->mtx);
+    DeviceGuard device_guard;
     DAB_CUDA_CHECK(cudaSetDevice(v->device));
     return launch(v, d_soft, soft_bytes, d_jobs, nullptr, n_jobs, max_steps, d_out, out_bytes, d_path_error, d_job_status);
 }
@@ -347,7 +348,8 @@ int dab_viterbi_decode_batch_device(dab_viterbi* h, const int8_t* d_soft, size_t
     if (!v) return set_error(DAB_ERR_INVALID, "null handle");
     if (n_jobs < 0 || (n_jobs > 0 && (!d_soft || !jobs || !d_out))) return set_error(DAB_ERR_INVALID, "null buffer");
     if (n_jobs == 0) return DAB_OK;
-    std::lock_guard<std::mutex> lock(v->mtx);
+    std::lock_guard<std::recursive_mutex> lock(v->mtx);
+    DeviceGuard device_guard;
     DAB_CUDA_CHECK(cudaSetDevice(v->device));
     int bad = -1;
     const uint32_t max_steps = max_steps_of(v, jobs, n_jobs, &bad);
@@ -366,7 +368,8 @@ int dab_viterbi_decode_batch(dab_viterbi* h, const int8_t* soft, size_t soft_byt
     if (!v) return set_error(DAB_ERR_INVALID, "null handle");
     if (n_jobs < 0 || (n_jobs > 0 && (!soft || !jobs || !out))) return set_error(DAB_ERR_INVALID, "null buffer");
     if (n_jobs == 0) return DAB_OK;
-    std::lock_guard<std::mutex> lock(v->mtx);
+    std::lock_guard<std::recursive_mutex> lock(v->mtx);
+    DeviceGuard device_guard;
     DAB_CUDA_CHECK(cudaSetDevice(v->device));
     int bad = -1;
     const uint32_t max_steps = max_steps_of(v, jobs, n_jobs, &bad);
@@ -401,8 +404,9 @@ int dab_viterbi_decode_one(dab_viterbi* h, const dab_vit_schedule* s, const int8
     DevSchedule d;
     int rc = digest_schedule(s, &d);
     if (rc != DAB_OK) return rc;
+    // the one-shot schedule slot is shared by every decode_one on this handle: hold the lock until the decode that reads it is done
+    std::lock_guard<std::recursive_mutex> lock(v->mtx);
     {
-        std::lock_guard<std::mutex> lock(v->mtx);
         if (v->oneshot_slot < 0) {
             if (v->schedules.size() >= DAB_VIT_MAX_SCHEDULES) return set_error(DAB_ERR_CAPACITY, "no schedule slot left");
             v->schedules.push_back(d);
@@ -426,7 +430,8 @@ int dab_viterbi_prepare_jobs(dab_viterbi* h, const dab_vit_job* jobs, int n_jobs
     auto* v = reinterpret_cast<Viterbi*>(h);
     if (!v) return set_error(DAB_ERR_INVALID, "null handle");
     if (!jobs || n_jobs <= 0) return set_error(DAB_ERR_INVALID, "empty job list");
-    std::lock_guard<std::mutex> lock(v->mtx);
+    std::lock_guard<std::recursive_mutex> lock(v->mtx);
+    DeviceGuard device_guard;
     DAB_CUDA_CHECK(cudaSetDevice(v->device));
     int bad = -1;
     const uint32_t max_steps = max_steps_of(v, jobs, n_jobs, &bad);
@@ -451,8 +456,9 @@ int dab_viterbi_decode_prepared(dab_viterbi* h, int plan, const int8_t* d_soft, 
     auto* v = reinterpret_cast<Viterbi*>(h);
     if (!v) return set_error(DAB_ERR_INVALID, "null handle");
     if (!d_soft || !d_out) return set_error(DAB_ERR_INVALID, "null buffer");
-    std::lock_guard<std::mutex> lock(v->mtx);
+    std::lock_guard<std::recursive_mutex> lock(v->mtx);
     if (plan < 1 || size_t(plan) >= v->prepared.size() || !v->prepared[size_t(plan)]->used) return set_error(DAB_ERR_INVALID, "unknown job plan %d", plan);
+    DeviceGuard device_guard;
     DAB_CUDA_CHECK(cudaSetDevice(v->device));
     Viterbi::Prepared* p = v->prepared[size_t(plan)].get();
     int rc = upload_schedules(v);
@@ -464,8 +470,9 @@ int dab_viterbi_decode_prepared(dab_viterbi* h, int plan, const int8_t* d_soft, 
 int dab_viterbi_release_jobs(dab_viterbi* h, int plan) {
     auto* v = reinterpret_cast<Viterbi*>(h);
     if (!v) return set_error(DAB_ERR_INVALID, "null handle");
-    std::lock_guard<std::mutex> lock(v->mtx);
+    std::lock_guard<std::recursive_mutex> lock(v->mtx);
     if (plan < 1 || size_t(plan) >= v->prepared.size() || !v->prepared[size_t(plan)]->used) return set_error(DAB_ERR_INVALID, "unknown job plan %d", plan);
+    DeviceGuard device_guard;
     DAB_CUDA_CHECK(cudaSetDevice(v->device));
     DAB_CUDA_CHECK(cudaStreamSynchronize(v->stream));
     v->prepared[size_t(plan)].reset(new Viterbi::Prepared());
@@ -475,6 +482,7 @@ int dab_viterbi_release_jobs(dab_viterbi* h, int plan) {
 int dab_viterbi_sync(dab_viterbi* h) {
     auto* v = reinterpret_cast<Viterbi*>(h);
     if (!v) return set_error(DAB_ERR_INVALID, "null handle");
+    DeviceGuard device_guard;
     DAB_CUDA_CHECK(cudaSetDevice(v->device));
     DAB_CUDA_CHECK(cudaStreamSynchronize(v->stream));
     return DAB_OK;

@@ -31,12 +31,17 @@ class OfdmDemodBatch:
     """n_streams independent OFDM demodulators of one DAB transmission mode on one GPU."""
 
     def __init__(self, mode, n_streams=1, device=0, max_block_samples=0, keep_debug_taps=False, raw_u8=False, params=None, prs=None,
-                 mapper=None):
+                 mapper=None, sample_format=None):
         self.L = capi.load()
         self.params = params if params is not None else ofdm_params(mode)
         prs = prs if prs is not None else prs_reference(mode)
         mapper = mapper if mapper is not None else mapper_reference(mode)
-        opts = capi.OfdmOptions(n_streams, device, max_block_samples, 1 if keep_debug_taps else 0, 1 if raw_u8 else 0)
+        fmt = capi.IQ_U8 if raw_u8 else capi.IQ_F32
+        if sample_format is not None:
+            fmt = capi.IQ_FORMATS[sample_format] if isinstance(sample_format, str) else int(sample_format)
+        self.sample_format = fmt
+        self.sample_bytes = int(self.L.dab_iq_format_bytes(fmt))
+        opts = capi.OfdmOptions(n_streams, device, max_block_samples, 1 if keep_debug_taps else 0, fmt)
         status = C.c_int(0)
         prs = np.ascontiguousarray(prs, np.complex64)
         mapper = np.ascontiguousarray(mapper, np.int32)
@@ -80,6 +85,13 @@ class OfdmDemodBatch:
         ns = (C.c_size_t * self.n_streams)(*[0 if a is None else a.size // 2 for a in arrs])
         capi.check(self.L.dab_ofdm_process_batch_u8(self.h, ptrs, ns))
 
+    def process_batch_raw(self, blocks):
+        """blocks: per stream a byte array (np.uint8) of raw samples in the handle's sample_format, or None"""
+        arrs = [None if b is None else np.ascontiguousarray(b).view(np.uint8) for b in blocks]
+        ptrs = (C.c_void_p * self.n_streams)(*[None if a is None else a.ctypes.data for a in arrs])
+        ns = (C.c_size_t * self.n_streams)(*[0 if a is None else a.size // self.sample_bytes for a in arrs])
+        capi.check(self.L.dab_ofdm_process_batch_raw(self.h, ptrs, ns))
+
     def process_batch_ptrs(self, ptrs, ns):
         """raw host pointers (ints) and sample counts: used by bench.py with pinned torch tensors"""
         p = (C.c_void_p * self.n_streams)(*ptrs)
@@ -114,6 +126,13 @@ class OfdmDemodBatch:
         d_bits, n_bits, slots, d_frames = C.c_void_p(), C.c_size_t(), C.c_int(), C.c_void_p()
         capi.check(self.L.dab_ofdm_device_bits(self.h, C.byref(d_bits), C.byref(n_bits), C.byref(slots), C.byref(d_frames)))
         return d_bits.value, int(n_bits.value), int(slots.value), d_frames.value
+
+    def device_frame_slots(self):
+        """(device pointer to int32 frame_slots[n_streams][max_frames], max_frames): ring slot of the f-th frame a stream completed
+        in the last call"""
+        d_slots, max_frames = C.c_void_p(), C.c_int()
+        capi.check(self.L.dab_ofdm_device_frame_slots(self.h, C.byref(d_slots), C.byref(max_frames)))
+        return d_slots.value, int(max_frames.value)
 
     def demod_frames_device(self, d_frames, frame_stride, n_frames, freq_offsets, d_bits, d_phase_err):
         f = np.ascontiguousarray(freq_offsets, np.float32)

@@ -118,20 +118,43 @@ typedef struct {
     float coarse_offset;      /* used by this frame's PLL */
     float fine_offset_used;   /* used by this frame's PLL */
     float fine_offset_after;  /* after this frame's cyclic-prefix update */
-    float signal_average;
+    float signal_average;     /* GetSignalAverage() after the Process() call that completed the frame */
+    int32_t slot;             /* soft-bit buffer of the frame on the device (dab_ofdm_device_bits) */
+    int32_t reserved;
 } dab_ofdm_frame_info;
+
+/* How a stream's samples are stored (examples/app_helpers/app_iq_readers.h:17-35,76-88,109-110,130-135: raw_u8, raw_s8,
+ * raw_s16l/b, raw_u16l/b).  Raw integer pairs are uploaded as they come from the front end and dequantised on the device as
+ * QuantisedIQ<T>::to_c32 does: (float(raw) - BIAS) * (1 / MAX_AMPLITUDE). */
+typedef enum {
+    DAB_IQ_F32 = 0,    /* std::complex<float> */
+    DAB_IQ_U8 = 1,     /* (u8 - 127.5) / 127.5 */
+    DAB_IQ_S8 = 2,     /* s8 / 127 */
+    DAB_IQ_S16LE = 3,  /* s16 / 32767 */
+    DAB_IQ_S16BE = 4,
+    DAB_IQ_U16LE = 5,  /* (u16 - 32767.5) / 32767.5 */
+    DAB_IQ_U16BE = 6
+} dab_iq_format;
+/* bytes per complex sample of a format (8, 2 or 4); 0 for an unknown format */
+DAB_API size_t dab_iq_format_bytes(int format);
 
 typedef struct {
     int n_streams;             /* >= 1 */
     int device;                /* CUDA ordinal */
     size_t max_block_samples;  /* largest n passed to a process call (0 => 262144) */
     int keep_debug_taps;       /* 1: also store frame FFT / DQPSK vectors for the GUI getters (doubles HBM writes) */
-    int raw_u8_ingest;         /* 1: the stream rings hold raw uint8 IQ (dab_ofdm_process_batch_u8), dequantised on device */
+    int sample_format;         /* dab_iq_format of the stream buffers; DAB_IQ_U8 (= 1, the former raw_u8_ingest flag) and the other
+                                  raw formats are fed through dab_ofdm_process_batch_raw and dequantised on the device */
 } dab_ofdm_options;
 
 /* Replaces On_OFDM_Frame().Attach(...) (ofdm_demodulator.h:140).  `bits` is owned by the library and valid only during the
  * call, like the reference's span over m_pipeline_out_bits (ofdm_demodulator.cpp:110,635).  Called on the thread that
- * invoked the process/sync entry point, in frame order per stream. */
+ * invoked the process/sync entry point, in frame order per stream.
+ * Re-entrancy: the callback runs inside the process call, which holds the handle's (recursive) lock.  It may call any
+ * dab_ofdm_* function on the same handle from the same thread (GetState(), Reset() from an On_OFDM_Frame observer, as the
+ * reference allows); other threads calling process / advance on the handle wait until the call returns.  The scalar getters
+ * (dab_ofdm_get_state) and dab_ofdm_get_impulse_response / _coarse_frequency_response / _frame_data_bits are served from a host
+ * snapshot taken at the end of the last synchronous process call and never wait for a call in flight on another thread. */
 typedef void (*dab_ofdm_frame_cb)(void* user, int stream, const int8_t* bits, size_t n_bits, const dab_ofdm_frame_info* info);
 
 /* A ready-made dab_ofdm_frame_cb for throughput measurements from languages whose own callbacks are slow (bench.py's e2e leg
@@ -163,6 +186,8 @@ DAB_API int dab_ofdm_process(dab_ofdm* h, int stream, const dab_c32* iq, size_t 
 DAB_API int dab_ofdm_process_batch(dab_ofdm* h, const dab_c32* const* iq, const size_t* n);
 /* raw 8-bit IQ (examples/app_helpers/app_iq_readers.h:17-69): sample = (u8 - 127.5) / 127.5, dequantised on the device */
 DAB_API int dab_ofdm_process_batch_u8(dab_ofdm* h, const uint8_t* const* iq_u8, const size_t* n);
+/* any raw format: iq[s] points at n[s] samples in the handle's sample_format (options->sample_format) */
+DAB_API int dab_ofdm_process_batch_raw(dab_ofdm* h, const void* const* iq, const size_t* n);
 
 /* Device-resident streams (the batched B200 path): d_iq points at n_streams rows of `stride_samples` samples already in
  * HBM.  The demodulator then reads the rows in place -- no ring copy.  dab_ofdm_advance(h, n) is one Process() call of n[s]
@@ -175,9 +200,13 @@ DAB_API int dab_ofdm_attach_device_streams(dab_ofdm* h, const dab_c32* d_iq, siz
 DAB_API int dab_ofdm_join(dab_ofdm* h);
 DAB_API int dab_ofdm_advance(dab_ofdm* h, const size_t* n);
 DAB_API int dab_ofdm_advance_uniform(dab_ofdm* h, size_t n);
-/* device pointer / geometry of the soft-bit output of the most recent process/advance call:
- * bits[stream][slot][n_bits], frames_in_call[stream] = how many slots are valid */
+/* Device pointer / geometry of the soft-bit output: every stream owns slots_per_stream soft-bit buffers of n_bits bytes,
+ * bits[stream][slot][n_bits], used in rotation (a frame is written while its symbols arrive, over several calls if the blocks are
+ * short).  The frames a stream COMPLETED in the most recent process/advance call are frames_in_call[stream] many; the f-th of them
+ * sits in slot frame_slots[stream * max_frames_per_call + f] (dab_ofdm_device_frame_slots; also dab_ofdm_frame_info::slot).  Streams
+ * that complete one frame per call -- the batched steady state -- all use the same slot in the same call. */
 DAB_API int dab_ofdm_device_bits(dab_ofdm* h, const int8_t** d_bits, size_t* n_bits, int* slots_per_stream, const int32_t** d_frames_in_call);
+DAB_API int dab_ofdm_device_frame_slots(dab_ofdm* h, const int32_t** d_frame_slots, int* max_frames_per_call);
 
 DAB_API int dab_ofdm_reset(dab_ofdm* h, int stream);           /* OFDM_Demod::Reset() */
 DAB_API int dab_ofdm_get_state(dab_ofdm* h, int stream, dab_ofdm_state* out);
@@ -206,7 +235,7 @@ typedef struct {
 DAB_API int dab_ofdm_set_kernel_timing(dab_ofdm* h, int enable);                    /* also clears the accumulators */
 DAB_API int dab_ofdm_get_kernel_times(dab_ofdm* h, dab_ofdm_kernel_times* out);     /* synchronises the stream */
 
-/* Stage-level entry used by the parity tests and the roofline measurement: demodulate already aligned frames.
+/* Stage-level entry used by the parity tests and the roofline measurement: demodulate already aligned frames (complex float).
  * d_frames: n_frames rows of frame_stride samples, row = PRS + data symbols (nb_frame_symbols * nb_symbol_period samples);
  * freq_offset[n_frames] (host); d_bits: n_frames * frame_bits; d_phase_error: n_frames * nb_frame_symbols floats (per symbol). */
 DAB_API int dab_ofdm_demod_frames_device(dab_ofdm* h, const dab_c32* d_frames, size_t frame_stride, int n_frames,
@@ -327,6 +356,11 @@ DAB_API int dab_ensemble_subchannel_schedule(const dab_subchannel* sub, dab_vit_
  * stream s is decoded iff d_frames_in_call == NULL or d_frames_in_call[s] > slot.  Asynchronous on the handle's stream. */
 DAB_API int dab_ensemble_decode_frames_device(dab_ensemble* h, const int8_t* d_bits, size_t stream_stride,
                                               const int32_t* d_frames_in_call, int slot);
+/* The f-th frame each stream completed in the demodulator's last call, straight from its soft-bit ring (dab_ofdm_device_bits +
+ * dab_ofdm_device_frame_slots): stream s is decoded iff d_frames_in_call[s] > f, and its frame starts at
+ * d_bits + s * stream_stride + d_frame_slots[s * frame_slots_stride + f] * slot_stride. */
+DAB_API int dab_ensemble_decode_frames_indexed(dab_ensemble* h, const int8_t* d_bits, size_t stream_stride, size_t slot_stride,
+                                               const int32_t* d_frames_in_call, const int32_t* d_frame_slots, int frame_slots_stride, int f);
 /* The same from host memory: bits[n_streams][nb_frame_bits]; present[n_streams] (optional) = 0 skips a stream. */
 DAB_API int dab_ensemble_decode_frames(dab_ensemble* h, const int8_t* bits, const uint8_t* present);
 
