@@ -376,13 +376,13 @@ def run_ours(args):
                  "fib_valid": n_streams * res.nb_cifs * res.nb_fibs_per_cif, "msc_nbytes": n_streams * res.nb_cifs * res.max_subchannels * 4}
         h_out = {k: torch.empty(v, dtype=torch.uint8).pin_memory() for k, v in sizes.items()}
         p, n = d.pointer_arrays([host[s].data_ptr() for s in range(n_streams)], [FRAME_LEN] * n_streams)
-        _, max_frames = d.device_frame_slots()
+        d_bits, n_bits, slots, d_fic = d.device_bits()
 
         def step():
             d.process_batch_prepared(p, n, True)
             d.join()
-            for f in range(max_frames):
-                dec.decode_ofdm_frames(d, f)
+            for slot in range(slots):
+                dec.decode_frames_device(d_bits + slot * n_bits, slots * n_bits, d_fic, slot)
             r = dec.device_results()
             for k in sizes:
                 (err,) = cudart.cudaMemcpyAsync(h_out[k].data_ptr(), getattr(r, k), sizes[k], cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost,

@@ -66,11 +66,11 @@ class OfdmFrameInfo(C.Structure):
     _fields_ = [
         ("frame_start", C.c_int64), ("fine_time_offset", C.c_int32), ("total_desync", C.c_int32),
         ("coarse_offset", C.c_float), ("fine_offset_used", C.c_float), ("fine_offset_after", C.c_float),
-        ("signal_average", C.c_float), ("slot", C.c_int32), ("reserved", C.c_int32),
+        ("signal_average", C.c_float),
     ]
 
     def asdict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 # dab_iq_format
@@ -134,7 +134,7 @@ EXPORTED_SYMBOLS = (
     "dab_get_mapper_reference", "dab_get_puncture_code",
     "dab_ofdm_create", "dab_ofdm_destroy", "dab_ofdm_set_cuda_stream", "dab_ofdm_set_frame_callback", "dab_ofdm_set_config",
     "dab_ofdm_get_config", "dab_ofdm_default_config", "dab_ofdm_process", "dab_ofdm_process_batch", "dab_ofdm_process_batch_u8",
-    "dab_ofdm_process_batch_raw", "dab_iq_format_bytes", "dab_ofdm_device_frame_slots", "dab_ensemble_decode_frames_indexed",
+    "dab_ofdm_process_batch_raw", "dab_iq_format_bytes",
     "dab_ofdm_attach_device_streams", "dab_ofdm_advance", "dab_ofdm_advance_uniform", "dab_ofdm_device_bits", "dab_ofdm_reset",
     "dab_ofdm_get_state", "dab_ofdm_sync", "dab_ofdm_join", "dab_ofdm_count_frames_cb", "dab_ofdm_frame_bits", "dab_ofdm_get_params", "dab_ofdm_get_impulse_response",
     "dab_ofdm_get_coarse_frequency_response", "dab_ofdm_get_correlation_time_buffer", "dab_ofdm_get_frame_data_bits", "dab_ofdm_get_frame_fft", "dab_ofdm_get_frame_data_vec",
@@ -185,7 +185,6 @@ def load():
     L.dab_ofdm_process_batch_raw.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
     L.dab_iq_format_bytes.argtypes = [i32]
     L.dab_iq_format_bytes.restype = sz
-    L.dab_ofdm_device_frame_slots.argtypes = [vp, C.POINTER(vp), ip]
     L.dab_ofdm_attach_device_streams.argtypes = [vp, vp, sz, sz]
     L.dab_ofdm_advance.argtypes = [vp, C.POINTER(sz)]
     L.dab_ofdm_advance_uniform.argtypes = [vp, sz]
@@ -251,7 +250,6 @@ def _bind_ensemble(L):
     L.dab_ensemble_subchannel_schedule.argtypes = [C.POINTER(Subchannel), C.POINTER(VitSchedule), C.POINTER(C.c_uint32)]
     L.dab_ensemble_decode_frames_device.argtypes = [vp, vp, sz, vp, i32]
     L.dab_ensemble_decode_frames.argtypes = [vp, vp, vp]
-    L.dab_ensemble_decode_frames_indexed.argtypes = [vp, vp, sz, sz, vp, vp, i32, i32]
     L.dab_ensemble_device_results.argtypes = [vp, C.POINTER(EnsembleResults)]
     L.dab_ensemble_read_fic.argtypes = [vp, i32, vp, vp, vp]
     L.dab_ensemble_read_msc.argtypes = [vp, i32, i32, i32, vp, sz, C.POINTER(C.c_int32), C.POINTER(u64)]

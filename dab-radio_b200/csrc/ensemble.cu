@@ -52,18 +52,7 @@ struct EnsGeom {
     int fib_group_bytes;    // nb_fib_cif_bits / 24
     int msc_cif_bytes;      // nb_cif_bits / 8
     int aligned16;          // the caller's frame rows allow 16-byte loads
-    // frames taken straight from the demodulator's soft-bit ring (dab_ensemble_decode_frames_indexed): stream s's frame starts
-    // frame_slots[s * frame_slots_stride + slot] * slot_stride bytes into its row; nullptr: at the row start
-    const int32_t* frame_slots;
-    int frame_slots_stride;
-    size_t slot_stride;
 };
-
-__device__ __forceinline__ const int8_t* ens_frame(const EnsGeom& g, const int8_t* bits, size_t stream_stride, int slot, int s) {
-    const int8_t* row = ens_frame(g, bits, stream_stride, slot, s);
-    if (g.frame_slots != nullptr) row += size_t(g.frame_slots[size_t(s) * g.frame_slots_stride + slot]) * g.slot_stride;
-    return row;
-}
 
 __device__ __forceinline__ bool stream_has_frame(const int32_t* frames_in_call, int slot, int s) {
     return frames_in_call == nullptr || frames_in_call[s] > slot;
@@ -77,7 +66,7 @@ ens_push_kernel(EnsGeom g, const int8_t* __restrict__ bits, size_t stream_stride
     const int s = blockIdx.z, c = blockIdx.y, t = threadIdx.x;
     if (!stream_has_frame(frames_in_call, slot, s)) return;
     const int p0 = blockIdx.x * ENS_CHUNK, pos = p0 + t;
-    const int8_t* src = ens_frame(g, bits, stream_stride, slot, s) + size_t(g.nb_fic_bits) + size_t(c) * size_t(g.nb_cif_bits);
+    const int8_t* src = bits + size_t(s) * stream_stride + size_t(g.nb_fic_bits) + size_t(c) * size_t(g.nb_cif_bits);
     if (pos < g.plane_len) {
         uint32_t w[4];
         if (g.aligned16) {
@@ -191,7 +180,7 @@ ens_viterbi_kernel(EnsGeom g, const int8_t* __restrict__ bits, size_t stream_str
     uint8_t* out;
     SubDesc sd{};
     if (is_fic) {
-        soft = ens_frame(g, bits, stream_stride, slot, s) + size_t(c) * size_t(g.nb_fib_cif_bits);
+        soft = bits + size_t(s) * stream_stride + size_t(c) * size_t(g.nb_fib_cif_bits);
         out = o.fib_bytes + (size_t(s) * g.nb_cifs + c) * size_t(g.fib_group_bytes);
     } else {
         if (k >= g.max_subs) return;
@@ -262,7 +251,7 @@ ens_viterbi_lanes_kernel(EnsGeom g, const int8_t* __restrict__ bits, size_t stre
     uint8_t* out = o.fib_bytes;
     if (active) {
         if (is_fic) {
-            soft = ens_frame(g, bits, stream_stride, slot, s) + size_t(c) * size_t(g.nb_fib_cif_bits);
+            soft = bits + size_t(s) * stream_stride + size_t(c) * size_t(g.nb_fib_cif_bits);
             out = o.fib_bytes + (size_t(s) * g.nb_cifs + c) * size_t(g.fib_group_bytes);
         } else {
             active = false;
@@ -492,19 +481,14 @@ static int upload_tables(Ensemble* e) {
     return DAB_OK;
 }
 
-static int decode_device(Ensemble* e, const int8_t* d_bits, size_t stream_stride, const int32_t* d_frames_in_call, int slot,
-                         const int32_t* d_frame_slots = nullptr, int frame_slots_stride = 0, size_t slot_stride = 0) {
+static int decode_device(Ensemble* e, const int8_t* d_bits, size_t stream_stride, const int32_t* d_frames_in_call, int slot) {
     const EnsGeom base = e->g;
     if (e->tables_dirty) {
         int rc = upload_tables(e);
         if (rc != DAB_OK) return rc;
     }
     EnsGeom g = base;
-    g.frame_slots = d_frame_slots;
-    g.frame_slots_stride = frame_slots_stride;
-    g.slot_stride = slot_stride;
-    g.aligned16 = (reinterpret_cast<uintptr_t>(d_bits) % 16 == 0 && stream_stride % 16 == 0 && slot_stride % 16 == 0 && g.nb_fic_bits % 16 == 0 &&
-                   g.nb_cif_bits % 16 == 0) ? 1 : 0;
+    g.aligned16 = (reinterpret_cast<uintptr_t>(d_bits) % 16 == 0 && stream_stride % 16 == 0 && g.nb_fic_bits % 16 == 0 && g.nb_cif_bits % 16 == 0) ? 1 : 0;
     const bool has_msc = g.nb_cif_bits > 0 && e->jobs_per_cif > (g.fic_enabled ? 1 : 0);
     if (has_msc) {
         const dim3 grid(unsigned((g.plane_len + ENS_CHUNK - 1) / ENS_CHUNK), unsigned(g.nb_cifs), unsigned(g.n_streams));
@@ -753,19 +737,6 @@ int dab_ensemble_decode_frames_device(dab_ensemble* h, const int8_t* d_bits, siz
     DeviceGuard device_guard;
     DAB_CUDA_CHECK(cudaSetDevice(e->device));
     return decode_device(e, d_bits, stream_stride, d_frames_in_call, slot);
-}
-
-int dab_ensemble_decode_frames_indexed(dab_ensemble* h, const int8_t* d_bits, size_t stream_stride, size_t slot_stride, const int32_t* d_frames_in_call,
-                                       const int32_t* d_frame_slots, int frame_slots_stride, int f) {
-    auto* e = reinterpret_cast<Ensemble*>(h);
-    if (!e) return set_error(DAB_ERR_INVALID, "null handle");
-    if (!d_bits || !d_frame_slots || f < 0 || f >= frame_slots_stride) return set_error(DAB_ERR_INVALID, "bad frame index / null buffer");
-    if (slot_stride < size_t(e->params.nb_fic_bits) + size_t(e->params.nb_cifs) * size_t(e->params.nb_cif_bits) || stream_stride < slot_stride)
-        return set_error(DAB_ERR_INVALID, "slot stride %zu is shorter than one frame", slot_stride);
-    std::lock_guard<std::mutex> lock(e->mtx);
-    DeviceGuard device_guard;
-    DAB_CUDA_CHECK(cudaSetDevice(e->device));
-    return decode_device(e, d_bits, stream_stride, d_frames_in_call, f, d_frame_slots, frame_slots_stride, slot_stride);
 }
 
 int dab_ensemble_decode_frames(dab_ensemble* h, const int8_t* bits, const uint8_t* present) {

@@ -48,17 +48,15 @@ struct Ofdm {
     size_t max_block = 0;
     size_t ring_samples = 0;
     size_t max_pitch = 1u << 30;        // cudaDeviceProp::memPitch bound for pitched copies (set at create)
-    int slots = 1;                      // frames a stream can complete in one call
-    int ring_slots = 2;                 // soft-bit buffers per stream (slots + 1: the frame being received owns one)
+    int slots = 1;                      // frames a stream can complete in one call = soft-bit buffers per stream
     size_t frame_bits = 0;
     int syms_per_chunk = 26;            // DAB_B200_SYMS_PER_CHUNK: target symbols per frame-kernel work item
-    int n_chunks = 3;                   // work items per dispatch
-    bool eager = false;                 // DAB_B200_EAGER=1: demodulate the symbols of a frame in the call they arrive in (see DESIGN.md:
-                                        // two half-size frame launches per step cost more than the window re-reads they save)
-    bool frame_owns_l1 = true;          // DAB_B200_FRAME_L1=0: the control kernel sums every UpdateSignalAverage window itself
+    int n_chunks = 3;                   // work items per frame
+    bool l1_side_kernel = true;         // DAB_B200_L1_SIDE=0: the control kernel sums every UpdateSignalAverage window itself
+    int l1_grid = 148 * 8;              // DAB_B200_L1_GRID: CTAs of the window kernel (grid-stride loop)
+    int l1_prio = 2;                    // DAB_B200_L1_PRIO: 0 lowest, 1 highest, 2 default stream priority (profiles/r02_step_probes.md)
     bool force_generic_kernel = false;  // DAB_B200_GENERIC_FRAME_KERNEL=1: run the generic-geometry frame kernel (tests)
     bool dab_geometry = false;          // the v3 kernel applies
-    uint32_t call_index = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     // pipeline ways: the streams of a handle are split into `ways` contiguous groups, each sequenced on its own CUDA stream, so
@@ -70,6 +68,9 @@ struct Ofdm {
     cudaEvent_t counts_ready[MAX_WAYS] = {};
     cudaEvent_t bits_ready[MAX_WAYS] = {};
     cudaEvent_t up_done[MAX_WAYS] = {};
+    // UpdateSignalAverage's window kernel runs beside the frame kernel on a side stream per way (ofdm_control.cuh)
+    cudaStream_t l1_stream[MAX_WAYS] = {};
+    cudaEvent_t call_open[MAX_WAYS] = {}, l1_done[MAX_WAYS] = {};
     // host-buffer path: all uploads on one stream and all soft-bit downloads on another, each in way order, so that the PCIe
     // link serves the ways first-in first-out (copies queued on the way streams themselves share the link and all finish last)
     cudaStream_t up_stream = nullptr, down_stream = nullptr;
@@ -84,7 +85,7 @@ struct Ofdm {
     DeviceBuffer<StreamState> states;
     DeviceBuffer<FrameDesc> descs, stage_descs;
     DeviceBuffer<dab_ofdm_frame_info> infos;
-    DeviceBuffer<int32_t> frames_in_call, frame_slots;
+    DeviceBuffer<int32_t> frames_in_call;
     DeviceBuffer<int8_t> bits;
     DeviceBuffer<int16_t> bin_to_pos, bin_to_carrier;
     DeviceBuffer<uint64_t> d_n;
@@ -95,7 +96,7 @@ struct Ofdm {
     std::vector<uint64_t> fed;       // samples handed to each stream so far
     std::vector<uint64_t> n_call;
     PinnedBuffer<uint64_t> h_n;
-    PinnedBuffer<int32_t> h_frames, h_frame_slots;
+    PinnedBuffer<int32_t> h_frames;
     PinnedBuffer<dab_ofdm_frame_info> h_infos;
     PinnedBuffer<int8_t> h_bits;
     dab_ofdm_frame_cb cb = nullptr;
@@ -277,17 +278,11 @@ static ControlGeom control_geom(const Ofdm* o) {
     g.cyclic_prefix = int(o->p.nb_cyclic_prefix);
     g.n_carriers = int(o->p.nb_data_carriers);
     g.slots = o->slots;
-    g.ring_slots = o->ring_slots;
     g.n_streams = o->n_streams;
     g.stream0 = 0;
     g.n_chunks = o->n_chunks;
-    g.syms_per_chunk = o->syms_per_chunk;
     g.frame_passes = 0;
-    g.eager = o->eager ? 1 : 0;
-    // the generic-geometry kernel does not sum windows
-    g.frame_owns_l1 = (o->frame_owns_l1 && o->dab_geometry && !o->force_generic_kernel) ? 1 : 0;
-    g.l1_per_symbol = 2 * std::max(1, o->nfft / 16 / 32);   // two windows per sub-warp of a transform's thread group
-    g.call_index = o->call_index;
+    g.l1_ready = 0;
     g.frame_bits = o->frame_bits;
     if (o->ext_base) {
         g.mask = ~uint64_t(0);
@@ -311,7 +306,6 @@ static ControlGeom control_geom(const Ofdm* o) {
     g.descs = o->descs.ptr;
     g.infos = o->infos.ptr;
     g.frames_in_call = o->frames_in_call.ptr;
-    g.frame_slots = o->frame_slots.ptr;
     g.bits = o->bits.ptr;
     g.phase_err = o->phase_err.ptr;
     g.twiddles = o->twiddles.ptr;
@@ -377,9 +371,10 @@ static WayRange way_range(const Ofdm* o, int w, int ways) {
 }
 
 // (control -> frame)* -> control  for the streams of one way, in order on the way's CUDA stream.  Control pass 0 opens the call
-// (OFDM_Demod::Process's entry); the frame kernel after pass p runs the work items pass p wrote; the last pass folds the call's
-// UpdateSignalAverage windows -- those the frame kernels summed on the way and those it sums itself -- into the running average.
-static int issue_way_kernels(Ofdm* o, const WayRange& r, bool uniform, uint64_t n_uniform, int passes) {
+// (OFDM_Demod::Process's entry); the frame kernel after pass p runs the work items pass p wrote.  UpdateSignalAverage's window
+// averages are summed by ofdm_l1_windows_kernel on the way's side stream between pass 0 and pass 1, i.e. while the frame kernel
+// runs; the stream's last pass folds them into the running average.
+static int issue_way_kernels(Ofdm* o, int w, const WayRange& r, bool uniform, uint64_t n_uniform, uint64_t n_max, int passes) {
     const int count = r.hi - r.lo;
     cudaStream_t st = r.st;
     ControlGeom g = control_geom(o);
@@ -394,11 +389,36 @@ static int issue_way_kernels(Ofdm* o, const WayRange& r, bool uniform, uint64_t 
             rc = launch_control(o, st, g, count, p);
         }
         if (rc != DAB_OK) return rc;
+        if (p == 0 && passes > 0 && o->l1_side_kernel) {
+            // every slot of the window buffer that this call can reach under ANY config (the kernel skips windows past the call's
+            // end; fold_average sums the windows beyond the buffer itself)
+            const int max_windows = (n_max >= 1) ? o->l1_windows_stride : 0;
+            const int64_t tasks = int64_t(count) * ((max_windows + L1_WB - 1) / L1_WB);
+            const int grid = int(std::min<int64_t>((tasks + 1) / 2, o->l1_grid));
+            if (grid > 0) {
+                cudaStream_t side = o->l1_stream[w];
+                DAB_CUDA_CHECK(cudaEventRecord(o->call_open[w], st));
+                DAB_CUDA_CHECK(cudaStreamWaitEvent(side, o->call_open[w], 0));
+                {
+                    ScopedKernelTimer timer(o, side, DAB_OFDM_TIMING_PASSES - 1, false);
+                    switch (o->sb) {
+                    case 8: ofdm_l1_windows_kernel<8><<<grid, L1_CTA_THREADS, 0, side>>>(g, count, max_windows); break;
+                    case 2: ofdm_l1_windows_kernel<2><<<grid, L1_CTA_THREADS, 0, side>>>(g, count, max_windows); break;
+                    default: ofdm_l1_windows_kernel<4><<<grid, L1_CTA_THREADS, 0, side>>>(g, count, max_windows); break;
+                    }
+                    o->launches++;
+                    DAB_CUDA_CHECK(cudaGetLastError());
+                }
+                DAB_CUDA_CHECK(cudaEventRecord(o->l1_done[w], side));
+                g.l1_ready = 1;   // for the passes from here on, which wait for l1_done below
+            }
+        }
         if (p < passes) {
             ScopedKernelTimer timer(o, st, p, true);
             rc = launch_frame(o, st, o->descs.ptr + (size_t(p) * size_t(o->n_streams) + size_t(r.lo)) * size_t(o->n_chunks), count * o->n_chunks);
             if (rc != DAB_OK) return rc;
         }
+        if (p == 0 && g.l1_ready) DAB_CUDA_CHECK(cudaStreamWaitEvent(st, o->l1_done[w], 0));
     }
     return DAB_OK;
 }
@@ -469,7 +489,6 @@ static int run_call(Ofdm* o, bool uniform, uint64_t n_uniform, const void* const
     const size_t sb = sample_bytes(o), ns = size_t(o->n_streams), slots = size_t(o->slots);
     if (o->cb || snapshot) {
         DAB_CUDA_CHECK(o->h_frames.reserve(ns));
-        DAB_CUDA_CHECK(o->h_frame_slots.reserve(ns * slots));
         DAB_CUDA_CHECK(o->h_infos.reserve(ns * slots));
     }
     if (snapshot) DAB_CUDA_CHECK(o->h_states.reserve(ns));
@@ -489,13 +508,11 @@ static int run_call(Ofdm* o, bool uniform, uint64_t n_uniform, const void* const
                 DAB_CUDA_CHECK(cudaStreamWaitEvent(r.st, o->up_done[w], 0));
             }
         }
-        int rc = issue_way_kernels(o, r, uniform, n_uniform, passes);
+        int rc = issue_way_kernels(o, w, r, uniform, n_uniform, n_max, passes);
         if (rc != DAB_OK) return rc;
         const size_t cnt = size_t(r.hi - r.lo);
         if (o->cb) {
             DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_frames.ptr + r.lo, o->frames_in_call.ptr + r.lo, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, r.st));
-            DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_frame_slots.ptr + size_t(r.lo) * slots, o->frame_slots.ptr + size_t(r.lo) * slots, cnt * slots * sizeof(int32_t),
-                                           cudaMemcpyDeviceToHost, r.st));
             DAB_CUDA_CHECK(cudaMemcpyAsync(o->h_infos.ptr + size_t(r.lo) * slots, o->infos.ptr + size_t(r.lo) * slots, cnt * slots * sizeof(dab_ofdm_frame_info),
                                            cudaMemcpyDeviceToHost, r.st));
         }
@@ -512,7 +529,6 @@ static int run_call(Ofdm* o, bool uniform, uint64_t n_uniform, const void* const
         }
         DAB_CUDA_CHECK(cudaEventRecord(o->counts_ready[w], r.st));
     }
-    o->call_index++;
     if (ways > 1) {
         o->ways_pending = true;
         // per-stream sample counts live in one device buffer that the next call overwrites from the handle's stream
@@ -554,30 +570,32 @@ static int run_callbacks(Ofdm* o, int w, int ways, size_t k) {
 static int deliver(Ofdm* o) {
     if (!o->cb) return DAB_OK;
     const int ways = n_ways(o);
-    const size_t slots = size_t(o->slots), ring = size_t(o->ring_slots), fb = o->frame_bits;
+    const size_t slots = size_t(o->slots), fb = o->frame_bits;
     DAB_CUDA_CHECK(o->h_bits.reserve(size_t(o->n_streams) * slots * fb));
     std::vector<size_t> first_k(size_t(ways) + 1, 0);
     for (int w = 0; w < ways; w++) {
         const WayRange r = way_range(o, w, ways);
         DAB_CUDA_CHECK(cudaEventSynchronize(o->counts_ready[w]));
         size_t k = first_k[size_t(w)];
-        // device source of frame (s, f) is ((s * ring) + slot(s, f)) * fb, host destination (callback order: stream, then frame) is
-        // k * fb.  Consecutive streams that completed the same number of frames c into the same ring slots form a run whose frame f
-        // goes down as ONE pitched copy (rows of fb bytes, source pitch ring * fb, destination pitch c * fb): one copy per way in
-        // the steady state instead of one per stream -- 1024 separate 230 KB copies cost 6.7 ms of set-up per step, more than the
-        // transfer itself.
+        // device source of frame (s, f) is (s * slots + f) * fb, host destination (callback order: stream, then frame) is k * fb.
+        // Consecutive streams that completed the same number of frames c form a run whose frame f goes down as ONE pitched copy
+        // (rows of fb bytes, source pitch slots * fb, destination pitch c * fb): one copy per way in the steady state instead of
+        // one per stream -- 1024 separate 230 KB copies cost 6.7 ms of set-up per step, more than the transfer itself.
         cudaStream_t down = (ways > 1) ? o->down_stream : r.st;  // counts_ready[w] (synchronised above) follows the way's kernels
-        const int32_t* hs = o->h_frame_slots.ptr;
         for (int s0 = r.lo; s0 < r.hi;) {
             const int c = o->h_frames.ptr[s0];
             int s1 = s0 + 1;
-            while (s1 < r.hi && o->h_frames.ptr[s1] == c && memcmp(hs + size_t(s1) * slots, hs + size_t(s0) * slots, size_t(c) * sizeof(int32_t)) == 0) s1++;
+            while (s1 < r.hi && o->h_frames.ptr[s1] == c) s1++;
             if (c > 0) {
                 const size_t rows = size_t(s1 - s0);
                 for (int f = 0; f < c; f++) {
-                    const int8_t* src = o->bits.ptr + (size_t(s0) * ring + size_t(hs[size_t(s0) * slots + size_t(f)])) * fb;
+                    const int8_t* src = o->bits.ptr + (size_t(s0) * slots + size_t(f)) * fb;
                     int8_t* dst = o->h_bits.ptr + (k + size_t(f)) * fb;
-                    DAB_CUDA_CHECK(cudaMemcpy2DAsync(dst, size_t(c) * fb, src, ring * fb, fb, rows, cudaMemcpyDeviceToHost, down));
+                    if (size_t(c) == slots && c == 1) {
+                        DAB_CUDA_CHECK(cudaMemcpyAsync(dst, src, rows * fb, cudaMemcpyDeviceToHost, down));
+                    } else {
+                        DAB_CUDA_CHECK(cudaMemcpy2DAsync(dst, size_t(c) * fb, src, slots * fb, fb, rows, cudaMemcpyDeviceToHost, down));
+                    }
                 }
                 k += rows * size_t(c);
             }
@@ -646,10 +664,8 @@ static int init_states(Ofdm* o) {
     DAB_CUDA_CHECK(cudaMemcpy(o->states.ptr, init.data(), init.size() * sizeof(StreamState), cudaMemcpyHostToDevice));
     DAB_CUDA_CHECK(cudaMemset(o->null_ring.ptr, 0, o->null_ring.count * sizeof(float2)));
     DAB_CUDA_CHECK(cudaMemset(o->frames_in_call.ptr, 0, o->frames_in_call.count * sizeof(int32_t)));
-    DAB_CUDA_CHECK(cudaMemset(o->frame_slots.ptr, 0, o->frame_slots.count * sizeof(int32_t)));
     DAB_CUDA_CHECK(cudaMemset(o->descs.ptr, 0, o->descs.count * sizeof(FrameDesc)));
     std::fill(o->fed.begin(), o->fed.end(), 0);
-    o->call_index = 0;
     invalidate_snapshot(o);
     return DAB_OK;
 }
@@ -659,12 +675,11 @@ static int create_impl(Ofdm* o, const dab_c32* prs, const int* mapper) {
     const size_t frame_cap = o->p.nb_frame_symbols * o->p.nb_symbol_period + o->p.nb_null_period;
     o->frame_bits = (o->p.nb_frame_symbols - 1) * ncarr * 2;
     o->slots = std::max(1, passes_for(o, o->max_block));
-    o->ring_slots = o->slots + 1;
     o->dab_geometry = (o->nfft == 2048 && DabGeom<2048>::matches(int(o->p.nb_symbol_period), int(o->p.nb_cyclic_prefix), int(ncarr))) ||
                       (o->nfft == 1024 && DabGeom<1024>::matches(int(o->p.nb_symbol_period), int(o->p.nb_cyclic_prefix), int(ncarr))) ||
                       (o->nfft == 512 && DabGeom<512>::matches(int(o->p.nb_symbol_period), int(o->p.nb_cyclic_prefix), int(ncarr))) ||
                       (o->nfft == 256 && DabGeom<256>::matches(int(o->p.nb_symbol_period), int(o->p.nb_cyclic_prefix), int(ncarr)));
-    // work items per dispatch: a whole frame in pieces of about syms_per_chunk symbols
+    // work items per frame: pieces of about syms_per_chunk symbols
     o->n_chunks = std::max(1, std::min(FRAME_MAX_CHUNKS, int((o->p.nb_frame_symbols + size_t(o->syms_per_chunk) - 1) / size_t(o->syms_per_chunk))));
     size_t need = frame_cap + o->p.nb_null_period + o->p.nb_symbol_period + o->max_block + 1024;
     o->ring_samples = 1;
@@ -697,12 +712,17 @@ static int create_impl(Ofdm* o, const dab_c32* prs, const int* mapper) {
 
     DAB_CUDA_CHECK(cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking));
     o->stream = o->own_stream;
+    int prio_low = 0, prio_high = 0;
+    DAB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
     for (int w = 0; w < Ofdm::MAX_WAYS; w++) {
         DAB_CUDA_CHECK(cudaStreamCreateWithFlags(&o->way_stream[w], cudaStreamNonBlocking));
         DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->way_done[w], cudaEventDisableTiming));
         DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->counts_ready[w], cudaEventDisableTiming));
         DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->bits_ready[w], cudaEventDisableTiming));
         DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->up_done[w], cudaEventDisableTiming));
+        DAB_CUDA_CHECK(cudaStreamCreateWithPriority(&o->l1_stream[w], cudaStreamNonBlocking, o->l1_prio == 1 ? prio_high : (o->l1_prio == 0 ? prio_low : 0)));
+        DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->call_open[w], cudaEventDisableTiming));
+        DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->l1_done[w], cudaEventDisableTiming));
     }
     DAB_CUDA_CHECK(cudaStreamCreateWithFlags(&o->up_stream, cudaStreamNonBlocking));
     DAB_CUDA_CHECK(cudaStreamCreateWithFlags(&o->down_stream, cudaStreamNonBlocking));
@@ -721,9 +741,8 @@ static int create_impl(Ofdm* o, const dab_c32* prs, const int* mapper) {
     DAB_CUDA_CHECK(o->descs.reserve(ns * size_t(o->slots) * size_t(o->n_chunks)));
     DAB_CUDA_CHECK(o->infos.reserve(ns * size_t(o->slots)));
     DAB_CUDA_CHECK(o->frames_in_call.reserve(ns));
-    DAB_CUDA_CHECK(o->frame_slots.reserve(ns * size_t(o->slots)));
-    DAB_CUDA_CHECK(o->bits.reserve(ns * size_t(o->ring_slots) * o->frame_bits));
-    DAB_CUDA_CHECK(cudaMemset(o->bits.ptr, 0, ns * size_t(o->ring_slots) * o->frame_bits));
+    DAB_CUDA_CHECK(o->bits.reserve(ns * size_t(o->slots) * o->frame_bits));
+    DAB_CUDA_CHECK(cudaMemset(o->bits.ptr, 0, ns * size_t(o->slots) * o->frame_bits));
     DAB_CUDA_CHECK(o->phase_err.reserve(ns * o->p.nb_frame_symbols));
     DAB_CUDA_CHECK(cudaMemset(o->phase_err.ptr, 0, ns * o->p.nb_frame_symbols * sizeof(float)));
     DAB_CUDA_CHECK(o->bin_to_pos.reserve(nfft));
@@ -836,8 +855,9 @@ dab_ofdm* dab_ofdm_create(const dab_ofdm_params* params, const dab_c32* prs_fft_
     if (const char* e = getenv("DAB_B200_GENERIC_FRAME_KERNEL")) o->force_generic_kernel = (e[0] == '1');
     if (const char* e = getenv("DAB_B200_PIPELINE_WAYS")) { const int w = atoi(e); if (w >= 1 && w <= Ofdm::MAX_WAYS) o->ways = w; }
     if (const char* e = getenv("DAB_B200_SYMS_PER_CHUNK")) { const int c = atoi(e); if (c >= 1 && c <= 1024) o->syms_per_chunk = c; }
-    if (const char* e = getenv("DAB_B200_EAGER")) o->eager = (e[0] != '0');
-    if (const char* e = getenv("DAB_B200_FRAME_L1")) o->frame_owns_l1 = (e[0] != '0');
+    if (const char* e = getenv("DAB_B200_L1_SIDE")) o->l1_side_kernel = (e[0] != '0');
+    if (const char* e = getenv("DAB_B200_L1_GRID")) { const int g = atoi(e); if (g >= 1) o->l1_grid = g; }
+    if (const char* e = getenv("DAB_B200_L1_PRIO")) o->l1_prio = atoi(e);
     rc = create_impl(o, prs_fft_ref, carrier_mapper);
     if (rc != DAB_OK) { delete o; return fail(rc); }
     if (status) *status = DAB_OK;
@@ -858,6 +878,9 @@ void dab_ofdm_destroy(dab_ofdm* h) {
         if (o->counts_ready[w]) cudaEventDestroy(o->counts_ready[w]);
         if (o->bits_ready[w]) cudaEventDestroy(o->bits_ready[w]);
         if (o->up_done[w]) cudaEventDestroy(o->up_done[w]);
+        if (o->l1_stream[w]) { cudaStreamSynchronize(o->l1_stream[w]); cudaStreamDestroy(o->l1_stream[w]); }
+        if (o->call_open[w]) cudaEventDestroy(o->call_open[w]);
+        if (o->l1_done[w]) cudaEventDestroy(o->l1_done[w]);
     }
     if (o->up_stream) { cudaStreamSynchronize(o->up_stream); cudaStreamDestroy(o->up_stream); }
     if (o->down_stream) { cudaStreamSynchronize(o->down_stream); cudaStreamDestroy(o->down_stream); }
@@ -1025,16 +1048,8 @@ int dab_ofdm_device_bits(dab_ofdm* h, const int8_t** d_bits, size_t* n_bits, int
     { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     if (d_bits) *d_bits = o->bits.ptr;
     if (n_bits) *n_bits = o->frame_bits;
-    if (slots_per_stream) *slots_per_stream = o->ring_slots;
+    if (slots_per_stream) *slots_per_stream = o->slots;
     if (d_frames_in_call) *d_frames_in_call = o->frames_in_call.ptr;
-    return DAB_OK;
-}
-
-int dab_ofdm_device_frame_slots(dab_ofdm* h, const int32_t** d_frame_slots, int* max_frames_per_call) {
-    OFDM_HANDLE(h);
-    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
-    if (d_frame_slots) *d_frame_slots = o->frame_slots.ptr;
-    if (max_frames_per_call) *max_frames_per_call = o->slots;
     return DAB_OK;
 }
 
@@ -1136,7 +1151,7 @@ int dab_ofdm_get_frame_data_bits(dab_ofdm* h, int stream, int8_t* out, size_t n_
     StreamState st;
     int rc = copy_out(o, &st, o->states.ptr + stream, sizeof(st));
     if (rc != DAB_OK) return rc;
-    return copy_out(o, out, o->bits.ptr + (size_t(stream) * size_t(o->ring_slots) + size_t(st.pending_slot)) * o->frame_bits, n_bits);
+    return copy_out(o, out, o->bits.ptr + (size_t(stream) * size_t(o->slots) + size_t(st.pending_slot)) * o->frame_bits, n_bits);
 }
 
 int dab_ofdm_get_correlation_time_buffer(dab_ofdm* h, int stream, dab_c32* out, size_t n) {
@@ -1233,7 +1248,6 @@ int dab_ofdm_demod_frames_device(dab_ofdm* h, const dab_c32* d_frames, size_t fr
         d.valid = 1;
         d.bits = d_bits + size_t(f) * o->frame_bits;
         d.phase_err = d_phase_error ? d_phase_error + size_t(f) * o->p.nb_frame_symbols : nullptr;
-        d.l1_w_hi = -1;
         int b = 0;
         for (int c = 0; c < parts; c++) {
             d.s_begin = b;

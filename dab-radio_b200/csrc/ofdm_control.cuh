@@ -9,13 +9,11 @@
 // frame dispatch; the host launches  control -> frame kernel -> control ...  and the next control pass first folds the
 // frame kernel's per-symbol phase errors into the fine frequency offset, then continues with the remaining samples.
 //
-// What the frame kernel is handed is a RANGE of symbols of a frame (FrameDesc): once a frame's PRS is synchronised its net
-// frequency offset is fixed (the only update in between is the previous frame's, which precedes the sync), so its symbols can be
-// demodulated in the call they arrive in instead of all at once when the frame completes.  Every sample then passes through
-// shared memory in the call that delivered it, and the frame kernel sums that call's UpdateSignalAverage windows
-// (ofdm_demodulator.cpp:934-950) on the way; the control kernel only evaluates the windows no item covered (NULL symbol,
-// the unfinished symbol at the end of a block, streams that are not locked) and folds all of them into the running average in
-// window order at the end of the call -- or earlier, the moment FindNullPowerDip needs the value.
+// UpdateSignalAverage (ofdm_demodulator.cpp:934-950) runs first in the reference's Process(); here its value is only needed when a
+// stream searches for the NULL symbol or when the call is over, so it is folded lazily: the window averages of every stream are
+// computed by ofdm_l1_windows_kernel on a side stream WHILE the frame kernel runs (it is DRAM-latency bound and fits into the
+// registers the frame kernel leaves free on every SM), and the last control pass of the call folds them into the running average
+// in window order.  A stream that needs the average earlier (FindNullPowerDip) sums its windows itself.
 #pragma once
 #include "ofdm_device.cuh"
 #include "ofdm_frame.cuh"
@@ -23,8 +21,7 @@
 
 namespace dabb200 {
 
-constexpr int CTRL_MAX_OWNED = 8;    // UpdateSignalAverage window ranges per call that frame-kernel items may own (one per dispatch)
-constexpr int FRAME_MAX_CHUNKS = 4;  // work items one dispatch is split into (load balance: a frame is 76 - 153 symbols long)
+constexpr int FRAME_MAX_CHUNKS = 4;  // work items a frame is split into (load balance: a frame is 76 - 153 symbols long)
 
 struct StreamState {
     // --- mirrors of the OFDM_Demod members (ofdm_demodulator.h:58-75)
@@ -47,37 +44,26 @@ struct StreamState {
     int64_t corr_base;       // absolute sample index of correlation-buffer element 0
     // --- OFDM_Frame_Buffer (ofdm_frame_buffer.h): virtual, [frame_start, frame_start + frame_cap)
     int64_t frame_start;
-    float frame_freq;        // net PLL frequency of the frame being received (fixed once its PRS is synchronised)
-    int32_t symbols_done;    // symbols [0, symbols_done) of that frame are demodulated or queued for the frame kernel
-    int32_t frame_slot;      // soft-bit buffer (ring slot) the frame is written to
     // --- cursor / current Process() call
     int64_t consumed;        // absolute index of the next unread sample
     int64_t call_begin;
     int64_t call_end;
     int32_t avg_pending;         // UpdateSignalAverage of this call not folded into l1_average yet (see fold_average)
     int32_t pipeline_pending;    // a frame was dispatched; its phase errors still have to update the fine offset
-    int32_t pending_slot;        // soft-bit ring slot of the most recently completed frame
+    int32_t pending_slot;        // output slot of the most recently completed frame
     int32_t frames_in_call;      // frames completed during this call
-    int32_t syncs_in_call;       // frames whose PRS was synchronised during this call (ring slot choice)
-    int32_t own_n;               // window ranges of this call owned by frame-kernel items
-    int32_t own_lo[CTRL_MAX_OWNED], own_hi[CTRL_MAX_OWNED];
     dab_ofdm_config cfg;
     dab_ofdm_frame_info pending_info;
 };
 
 struct ControlGeom {
     int n_symbols, symbol_period, null_period, cyclic_prefix, n_carriers;
-    int slots;               // frames a stream can complete per call
-    int ring_slots;          // soft-bit buffers per stream: slots + 1 (the frame being received has one too)
+    int slots;               // frames a stream can complete per call = soft-bit buffers per stream
     int n_streams;           // streams of the handle (row length of descs)
     int stream0;             // first stream this launch covers (launches are split into pipeline ways, see run_call)
-    int n_chunks;            // work items per dispatch (<= FRAME_MAX_CHUNKS)
-    int syms_per_chunk;      // target symbols per work item
+    int n_chunks;            // work items per frame (<= FRAME_MAX_CHUNKS)
     int frame_passes;        // control passes of this call that are followed by a frame-kernel launch
-    int eager;               // 1: symbols of a frame still being received are demodulated in the call they arrive in
-    int frame_owns_l1;       // 1: the frame kernel sums the UpdateSignalAverage windows inside the symbols it reads
-    int l1_per_symbol;       // ... at most this many per symbol
-    uint32_t call_index;     // calls made on this handle so far (soft-bit ring slot choice)
+    int l1_ready;            // 1: l1_windows holds the window averages of this call (ofdm_l1_windows_kernel has completed)
     size_t frame_bits;
     uint64_t mask;           // stream index mask (ring size - 1 or ~0)
     uint64_t limit;          // samples addressable per stream (ring size, or the attached buffer's length)
@@ -94,11 +80,10 @@ struct ControlGeom {
     FrameDesc* descs;        // [frame_passes][n_streams][n_chunks]
     dab_ofdm_frame_info* infos;  // [n_streams][slots]
     int32_t* frames_in_call;     // [n_streams]
-    int32_t* frame_slots;        // [n_streams][slots]: ring slot of the f-th frame completed in this call
-    int8_t* bits;            // [n_streams][ring_slots][frame_bits]
+    int8_t* bits;            // [n_streams][slots][frame_bits]
     float* phase_err;        // [n_streams][n_symbols]
     const float2* twiddles;  // precomputed FFT twiddles (fft_twiddle_init_kernel)
-    float* l1_windows;       // [n_streams][l1_windows_stride] window averages of the current call summed by the frame kernel
+    float* l1_windows;       // [n_streams][l1_windows_stride] window averages of the current call (ofdm_l1_windows_kernel)
     int l1_windows_stride;
     float2* fft_tap;         // optional [n_streams][n_symbols * NFFT]
     float2* vec_tap;         // optional [n_streams][(n_symbols-1) * n_carriers]
@@ -191,9 +176,9 @@ struct Control {
     }
 
     // ---- UpdateSignalAverage (ofdm_demodulator.cpp:934-950) of the current call, folded into l1_average in window order.  The
-    // window averages come from the frame kernel where one of its items had the samples in shared memory (own_lo/own_hi, recorded
-    // at dispatch; those launches have completed: a dispatch ends its control pass) and are summed here otherwise.  Runs once per
-    // call: at the end of the stream's last active pass, or the moment FindNullPowerDip needs the average.
+    // window averages come from ofdm_l1_windows_kernel when it has completed (geo.l1_ready: the passes after the first frame
+    // launch) and are summed here otherwise.  Runs once per call: in the stream's last pass, or the moment FindNullPowerDip needs
+    // the average.
     __device__ void fold_average() {
         const int64_t N = st.call_end - st.call_begin;
         const int K = st.cfg.signal_l1_nb_samples;
@@ -204,15 +189,11 @@ struct Control {
             const float* win = geo.l1_windows + size_t(stream) * geo.l1_windows_stride;
             for (int64_t w0 = 0; w0 < n_windows; w0 += CTRL_L1_BATCH) {
                 const int count = int(min(int64_t(CTRL_L1_BATCH), n_windows - w0));
-                int64_t cursor = w0;
-                for (int r = 0; r < st.own_n && cursor < w0 + count; r++) {
-                    const int64_t lo = max(int64_t(st.own_lo[r]), cursor), hi = min(int64_t(st.own_hi[r]), w0 + count - 1);
-                    if (hi < lo) continue;
-                    if (lo > cursor) l1_windows(l1buf + (cursor - w0), st.call_begin + cursor * L, L, K, int(lo - cursor));
-                    for (int64_t w = lo + tid; w <= hi; w += THREADS) l1buf[w - w0] = win[w];
-                    cursor = hi + 1;
+                if (geo.l1_ready && w0 + count <= geo.l1_windows_stride) {
+                    for (int w = tid; w < count; w += THREADS) l1buf[w] = win[w0 + w];
+                } else {
+                    l1_windows(l1buf, st.call_begin + w0 * L, L, K, count);
                 }
-                if (cursor < w0 + count) l1_windows(l1buf + (cursor - w0), st.call_begin + cursor * L, L, K, int(w0 + count - cursor));
                 __syncthreads();
                 if (tid == 0) {
                     const float beta = st.cfg.signal_l1_update_beta;
@@ -524,37 +505,14 @@ struct Control {
                 st.corr_length = 0;
                 st.fine_time_offset = offset;
                 st.state = DAB_OFDM_READING_SYMBOLS;
-                // from here to the end of the frame nothing changes the frequency offsets (the previous frame's fine update came
-                // before this synchronisation): the frame kernel may start on the symbols as they arrive
-                st.frame_freq = st.freq_coarse + st.freq_fine;
-                st.symbols_done = 0;
-                st.frame_slot = choose_slot_thread0();
-                st.syncs_in_call++;
                 st.pending_info.frame_start = st.frame_start;
                 st.pending_info.fine_time_offset = offset;
-                st.pending_info.coarse_offset = st.freq_coarse;
-                st.pending_info.fine_offset_used = st.freq_fine;
             }
         }
         __syncthreads();
     }
 
-    // Soft-bit ring slot for the frame whose PRS was just synchronised.  The j-th synchronisation of call c takes slot (c + j) mod R
-    // unless a frame completed earlier in this call still sits there: streams that complete one frame per call (the batched steady
-    // state) then all use the same slot in the same call, and their frames leave the device as one strided copy.
-    __device__ int choose_slot_thread0() {
-        const int R = geo.ring_slots;
-        int cand = int((geo.call_index + uint32_t(st.syncs_in_call)) % uint32_t(R));
-        for (int k = 0; k < R; k++) {
-            bool busy = false;
-            for (int f = 0; f < st.frames_in_call; f++) busy = busy || (geo.frame_slots[size_t(stream) * geo.slots + f] == cand);
-            if (!busy) break;
-            cand = (cand + 1) % R;
-        }
-        return cand;
-    }
-
-    // ---- the fine-frequency half of CoordinatorThread (ofdm_demodulator.cpp:606-618, 632) for the frame that just completed
+    // ---- the fine-frequency half of CoordinatorThread (ofdm_demodulator.cpp:606-618, 632) for the frame dispatched before
     __device__ void finish_pipeline() {
         // the per-symbol phase errors arrive with one parallel load; the sum keeps the reference's symbol order
         const float* pe = geo.phase_err + size_t(stream) * geo.n_symbols;
@@ -569,123 +527,121 @@ struct Control {
             update_fine_thread0(-st.cfg.sync_fine_freq_update_beta * fine_error);
             st.pending_info.fine_offset_after = st.freq_fine;
             st.total_frames_read++;
-            geo.infos[size_t(stream) * geo.slots + (st.frames_in_call - 1)] = st.pending_info;
+            geo.infos[size_t(stream) * geo.slots + st.pending_slot] = st.pending_info;
             st.pipeline_pending = 0;
         }
         __syncthreads();
     }
 
-    // Hands symbols [st.symbols_done, s_end) of the frame being received to the frame kernel launched after this pass, split into
-    // up to n_chunks work items, and lets those items own the UpdateSignalAverage windows inside the samples they read.
-    __device__ void dispatch_thread0(int pass, int s_end) {
-        const int s_lo = st.symbols_done;
-        const int n_new = s_end - s_lo;
-        const int SP = geo.symbol_period;
-        int parts = (n_new + geo.syms_per_chunk - 1) / geo.syms_per_chunk;
-        parts = max(1, min(parts, geo.n_chunks));
-        // window ownership: windows [w_lo, w_hi] of this call lie inside the samples the items load
-        const int K = st.cfg.signal_l1_nb_samples;
-        const int L = K * st.cfg.signal_l1_nb_decimate;
-        const int64_t N = st.call_end - st.call_begin;
-        int64_t n_windows = 0;
-        if (K > 0 && L > 0 && N >= K) n_windows = (N - K + L - 1) / L;
-        // the frame kernel sums at most l1_per_symbol windows per symbol (two per sub-warp) of at most L1_PREFIX + 1 samples
-        const bool can_own = geo.frame_owns_l1 && st.avg_pending && n_windows > 0 && K - 1 <= L1_PREFIX && st.own_n < CTRL_MAX_OWNED &&
-                             n_windows <= int64_t(geo.l1_windows_stride) && (SP + K - 1) / L + 1 <= geo.l1_per_symbol;
-        int64_t own_lo = -1, own_hi = -2;
-        FrameDesc d;
-        d.src = src;
-        d.mask = geo.mask;
-        d.limit = geo.limit;
-        d.start = st.frame_start;
-        d.freq = st.frame_freq;
-        d.valid = 1;
-        d.bits = geo.bits + (size_t(stream) * geo.ring_slots + st.frame_slot) * geo.frame_bits;
-        d.phase_err = geo.phase_err + size_t(stream) * geo.n_symbols;
-        d.fft_tap = geo.fft_tap ? geo.fft_tap + size_t(stream) * geo.n_symbols * NFFT : nullptr;
-        d.vec_tap = geo.vec_tap ? geo.vec_tap + size_t(stream) * (geo.n_symbols - 1) * geo.n_carriers : nullptr;
-        d.l1_origin = st.call_begin;
-        d.l1_k = K;
-        d.l1_step = L;
-        FrameDesc* out = geo.descs + (size_t(pass) * geo.n_streams + stream) * geo.n_chunks;
-        int b = s_lo;
-        for (int c = 0; c < parts; c++) {
-            const int e = b + n_new / parts + (c < n_new % parts ? 1 : 0);
-            d.s_begin = b;
-            d.s_end = e;
-            d.l1_out = nullptr;
-            d.l1_w_lo = 0;
-            d.l1_w_hi = -1;
-            if (can_own) {
-                // first item of the dispatch: windows that begin inside its first loaded symbol (and inside this call); later items:
-                // windows that end after their reference symbol (the previous item takes those ending in it)
-                const int64_t first_loaded = st.frame_start + int64_t(max(b - 1, 0)) * SP;
-                const int64_t lo_abs = (c == 0) ? max(first_loaded, st.call_begin) : st.frame_start + int64_t(b) * SP - K + 1;
-                const int64_t hi_abs = st.frame_start + int64_t(e) * SP - K;   // last admissible window start
-                const int64_t rel_lo = max(lo_abs - st.call_begin, int64_t(0));
-                const int64_t w_lo = (rel_lo + L - 1) / L;
-                int64_t w_hi = (hi_abs >= st.call_begin) ? (hi_abs - st.call_begin) / L : -1;
-                w_hi = min(w_hi, n_windows - 1);
-                if (w_hi >= w_lo) {
-                    d.l1_out = geo.l1_windows + size_t(stream) * geo.l1_windows_stride;
-                    d.l1_w_lo = int(w_lo);
-                    d.l1_w_hi = int(w_hi);
-                    if (own_lo < 0) own_lo = w_lo;
-                    own_hi = w_hi;
-                }
-            }
-            out[c] = d;
-            b = e;
-        }
-        if (own_hi >= own_lo && own_lo >= 0) {
-            st.own_lo[st.own_n] = int(own_lo);
-            st.own_hi[st.own_n] = int(own_hi);
-            st.own_n++;
-        }
-        st.symbols_done = s_end;
-    }
-
-    // ---- ReadSymbols (ofdm_demodulator.cpp:550-577): returns true when the pass has to stop for the frame kernel
-    __device__ bool read_symbols_thread0(int pass, bool& dispatched) {
+    // ---- ReadSymbols (ofdm_demodulator.cpp:550-577): returns true when a frame was dispatched
+    __device__ bool read_symbols_thread0(int pass) {
         const int S = geo.n_symbols;
         const int64_t frame_cap = int64_t(S) * geo.symbol_period + geo.null_period;
         const int64_t frame_end = st.frame_start + frame_cap;
         const int64_t take = min(st.call_end - st.consumed, frame_end - st.consumed);
         st.consumed += take;
-        const bool may_dispatch = pass < geo.frame_passes;
-        if (st.consumed != frame_end) {
-            // the block ends inside the frame: the symbols that are complete can be demodulated now
-            if (geo.eager && may_dispatch) {
-                const int avail = int(min(int64_t(S), (st.consumed - st.frame_start) / geo.symbol_period));
-                if (avail > st.symbols_done) {
-                    dispatch_thread0(pass, avail);
-                    dispatched = true;
-                }
-            }
-            return false;
-        }
+        if (st.consumed != frame_end) return false;
         // the trailing NULL symbol becomes the head of the next correlation buffer (:557-562)
         st.corr_base = frame_end - geo.null_period;
         st.corr_length = uint32_t(geo.null_period);
         st.corr_explicit_len = 0;
-        // the frame is complete (SignalStart, :572): whatever the frame kernel has not seen yet goes out now
-        const bool need_kernel = st.symbols_done < S;
-        if (need_kernel) {
-            dispatch_thread0(pass, S);
-            dispatched = true;
+        // hand the frame to the frame kernel launched after this pass (SignalStart, :572), n_chunks work items of about equal length
+        const int slot = st.frames_in_call;
+        FrameDesc d;
+        d.src = src;
+        d.mask = geo.mask;
+        d.limit = geo.limit;
+        d.start = st.frame_start;
+        d.freq = st.freq_coarse + st.freq_fine;
+        d.valid = 1;
+        d.bits = geo.bits + (size_t(stream) * geo.slots + slot) * geo.frame_bits;
+        d.phase_err = geo.phase_err + size_t(stream) * geo.n_symbols;
+        d.fft_tap = geo.fft_tap ? geo.fft_tap + size_t(stream) * geo.n_symbols * NFFT : nullptr;
+        d.vec_tap = geo.vec_tap ? geo.vec_tap + size_t(stream) * (geo.n_symbols - 1) * geo.n_carriers : nullptr;
+        FrameDesc* out = geo.descs + (size_t(pass) * geo.n_streams + stream) * geo.n_chunks;
+        int b = 0;
+        for (int c = 0; c < geo.n_chunks; c++) {
+            d.s_begin = b;
+            d.s_end = b + S / geo.n_chunks + (c < S % geo.n_chunks ? 1 : 0);
+            b = d.s_end;
+            out[c] = d;
         }
-        const int f = st.frames_in_call;
-        geo.frame_slots[size_t(stream) * geo.slots + f] = st.frame_slot;
+        st.pending_info.coarse_offset = st.freq_coarse;
+        st.pending_info.fine_offset_used = st.freq_fine;
         st.pending_info.signal_average = st.l1_average;
         st.pending_info.total_desync = st.total_frames_desync;
-        st.pending_info.slot = st.frame_slot;
-        st.pending_slot = st.frame_slot;
+        st.pending_slot = slot;
         st.pipeline_pending = 1;
-        st.frames_in_call = f + 1;
+        st.frames_in_call = slot + 1;
         st.state = DAB_OFDM_READING_NULL_AND_PRS;
-        return need_kernel;
+        return true;
     }
 };
+
+// CalculateL1Average (ofdm_demodulator.cpp:922-932) for every window UpdateSignalAverage (:934-950) visits in the current call:
+// window w of stream s covers samples [call_begin + w L, + K).  One warp per group of L1_WB windows, every load of the group
+// issued before the first use (the access pattern -- 800 bytes out of every 4000 -- is DRAM-latency bound).  64-thread CTAs with
+// at most 64 registers per thread and no shared memory: they fit into what three frame-kernel CTAs leave free on an SM, so the
+// kernel runs beside the frame kernel (launched on a side stream after control pass 0 has set call_begin / call_end) instead
+// of in front of it.  Lane-strided partial sums, then the butterfly: the same order as Control::l1_windows.
+constexpr int L1_WB = 4;
+constexpr int L1_CTA_THREADS = 64;
+template <int SB>
+__global__ void __launch_bounds__(L1_CTA_THREADS, 16) ofdm_l1_windows_kernel(ControlGeom geo, int n_streams, int max_windows) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int groups = (max_windows + L1_WB - 1) / L1_WB;
+    const int total = n_streams * groups;
+    for (int task = blockIdx.x * warps_per_block + (threadIdx.x >> 5); task < total; task += gridDim.x * warps_per_block) {
+        const int stream = geo.stream0 + task / groups, w0 = (task % groups) * L1_WB;
+        const StreamState* st = geo.states + stream;
+        const int K = st->cfg.signal_l1_nb_samples;
+        const int L = K * st->cfg.signal_l1_nb_decimate;
+        const int64_t call_begin = st->call_begin;
+        const int64_t N = st->call_end - call_begin;
+        if (K <= 0 || L <= 0 || N < K || !st->avg_pending) continue;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(geo.samples) + size_t(stream) * geo.stream_stride * SB;
+        // window b: samples [first, first + K) of the stream; `flat` when it does not wrap around the ring
+        bool live[L1_WB], flat[L1_WB];
+        uint64_t first[L1_WB];
+        float acc[L1_WB];
+#pragma unroll
+        for (int b = 0; b < L1_WB; b++) {
+            live[b] = (w0 + b < max_windows) && (int64_t(w0 + b) * L < N - K);  // loop condition i < M of the reference
+            first[b] = uint64_t(call_begin + int64_t(w0 + b) * L) & geo.mask;
+            flat[b] = (geo.mask == ~uint64_t(0)) || (first[b] + uint64_t(K) <= geo.mask + 1);
+            acc[b] = 0.0f;
+        }
+        for (int i0 = 0; i0 < K; i0 += 128) {
+            float2 v[L1_WB][4];
+#pragma unroll
+            for (int b = 0; b < L1_WB; b++) {
+                const unsigned char* p = src + first[b] * SB;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int i = i0 + lane + 32 * q;
+                    v[b][q] = make_float2(0.0f, 0.0f);
+                    if (live[b] && i < K) {
+                        if (flat[b]) v[b][q] = load_sample_ptr<SB>(p + i * SB, geo.fmt);
+                        else v[b][q] = load_sample<SB>(src, (first[b] + uint64_t(i)) & geo.mask, geo.fmt);
+                    }
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < L1_WB; b++)
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (i0 + lane + 32 * q < K) acc[b] += fabsf(v[b][q].x) + fabsf(v[b][q].y);
+        }
+#pragma unroll
+        for (int b = 0; b < L1_WB; b++) {
+            float a = acc[b];
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, d);
+            if (lane == 0 && live[b]) geo.l1_windows[size_t(stream) * geo.l1_windows_stride + w0 + b] = a / float(K);
+        }
+    }
+}
 
 // pass: index of this control pass within the call (0 = first; it also opens the call: OFDM_Demod::Process's entry,
 // ofdm_demodulator.cpp:235-243).  Passes below geo.frame_passes are followed by a frame-kernel launch over the items they wrote.
@@ -696,7 +652,7 @@ ofdm_control_kernel(ControlGeom geo, int pass) {
     using C = Control<NFFT, SB>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ StreamState st;
-    __shared__ int stop_flag, dispatched_flag;
+    __shared__ int stop_flag;
     const int stream = geo.stream0 + blockIdx.x, tid = threadIdx.x;
 
     float2* tw1 = reinterpret_cast<float2*>(smem_raw);
@@ -710,15 +666,12 @@ ofdm_control_kernel(ControlGeom geo, int pass) {
     if (tid == 0) {
         st = geo.states[stream];
         stop_flag = 0;
-        dispatched_flag = 0;
         if (pass == 0) {
             const uint64_t n = geo.n_per_stream ? geo.n_per_stream[stream] : geo.n_uniform;
             st.call_begin = st.call_end;
             st.call_end = st.call_begin + int64_t(n);
             st.avg_pending = (n > 0) ? 1 : 0;
             st.frames_in_call = 0;
-            st.syncs_in_call = 0;
-            st.own_n = 0;
         }
     }
     // the work items this pass may fill start out invalid
@@ -769,19 +722,16 @@ ofdm_control_kernel(ControlGeom geo, int pass) {
             break;
         case DAB_OFDM_READING_SYMBOLS:
             if (tid == 0) {
-                bool dispatched = false;
-                if (ctl.read_symbols_thread0(pass, dispatched)) stop_flag = 1;  // wait for the frame kernel before touching the next PRS
-                if (dispatched) dispatched_flag = 1;
+                if (ctl.read_symbols_thread0(pass)) stop_flag = 1;  // wait for the frame kernel before touching the next PRS
             }
             __syncthreads();
-            // a frame whose symbols were all demodulated as they arrived needs no kernel: its fine-frequency update runs right here
-            if (st.pipeline_pending && !stop_flag) ctl.finish_pipeline();
             break;
         }
     }
     __syncthreads();
-    // the call is over for this stream and every item it dispatched has run: fold UpdateSignalAverage
-    if (st.avg_pending && st.consumed >= st.call_end && !dispatched_flag && !st.pipeline_pending) ctl.fold_average();
+    // the call is over for this stream: fold UpdateSignalAverage -- once the window kernel's results are there (from pass 1 on;
+    // a call always has a pass 1), or by summing the windows here if the call has no further pass
+    if (st.avg_pending && st.consumed >= st.call_end && !st.pipeline_pending && (geo.l1_ready || pass >= geo.frame_passes)) ctl.fold_average();
     if (tid == 0) {
         geo.states[stream] = st;
         geo.frames_in_call[stream] = st.frames_in_call;

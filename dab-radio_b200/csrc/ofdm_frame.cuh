@@ -58,8 +58,7 @@ __device__ __forceinline__ float2 load_sample(const void* src, uint64_t index, c
 // One work item of the frame kernels: symbols [s_begin, s_end) of one transmission frame of one stream.  The item writes the
 // cyclic-prefix phase error of each of its symbols and the soft-bit rows s - 1 (DQPSK of symbols s - 1 and s) for s >= 1; for
 // s_begin > 0 it transforms symbol s_begin - 1 once more as the differential reference.  A frame is covered by any tiling of
-// [0, S) into items -- chunks of a frame that completed in this Process() call, or the symbols that arrived so far of a frame
-// still being received (ofdm_control.cuh decides).
+// [0, S) into items (ofdm_control.cuh splits a completed frame into n_chunks of them for load balance).
 struct FrameDesc {
     const void* src;       // sample base of the stream (SampleFmt layout)
     uint64_t mask;         // index mask: ring size - 1, or ~0 for a linear buffer
@@ -73,14 +72,6 @@ struct FrameDesc {
     float* phase_err;      // out: S cyclic-prefix phase errors (radians), one per symbol
     float2* fft_tap;       // optional GUI tap: S * NFFT spectra (natural bin order), else nullptr
     float2* vec_tap;       // optional GUI tap: (S-1) * ncarr DQPSK vectors (carrier order), else nullptr
-    // UpdateSignalAverage (ofdm_demodulator.cpp:934-950) windows this item computes while their samples sit in shared memory:
-    // window w covers samples [l1_origin + w * l1_step, + l1_k); the item owns w in [l1_w_lo, l1_w_hi] whose last sample lies in
-    // one of its symbols after l1_after (absolute sample index; the windows ending earlier belong to the previous item)
-    float* l1_out;         // [window] averages of the current call, nullptr: none
-    int64_t l1_origin;
-    int64_t l1_after;
-    int32_t l1_k, l1_step;
-    int32_t l1_w_lo, l1_w_hi;
 };
 
 struct FrameGeom {
@@ -124,7 +115,7 @@ struct FrameSmem {
 
 // Generic-geometry frame kernel: any OFDM_Params the reference API accepts (cp <= nfft / 4, carriers a multiple of 8).  The four
 // DAB transmission modes run ofdm_frame_v3_kernel instead; DAB_B200_GENERIC_FRAME_KERNEL=1 routes them here too (cross-check in
-// tests/test_ofdm_gpu.py).  It does not compute UpdateSignalAverage windows (the control kernel evaluates them itself then).
+// tests/test_ofdm_gpu.py).
 template <int NFFT, int SB>
 __global__ void __launch_bounds__(FRAME_CTA_THREADS, 4)
 ofdm_frame_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_items) {

@@ -18,10 +18,9 @@
 //     memory right after the first FFT exchange, and all threads pick their 20 samples up with LDS after an mbarrier wait.  No
 //     global-load instructions, address arithmetic or prefetch registers in the loop.  A symbol that straddles the ring end (or
 //     an unaligned buffer end) takes a cooperative plain-load path.
-//   * While a symbol sits in shared memory the kernel also sums the UpdateSignalAverage windows (ofdm_demodulator.cpp:922-950)
-//     that end inside it -- the window averages of a locked stream cost no HBM traffic of their own (round 1 re-read 20 % of the
-//     samples for them in a separate kernel).  For windows that begin in the previous symbol the bulk copy carries the last
-//     L1_PREFIX samples before the symbol along (an L2 hit: the same CTA fetched them a few microseconds earlier).
+//   * 158 registers and 75 KB of shared memory per 128-thread CTA: three CTAs per SM, and the 4096 registers they leave are what
+//     ofdm_l1_windows_kernel (ofdm_control.cuh) runs in, concurrently, on a side stream.  Summing the UpdateSignalAverage windows
+//     here instead was built and measured: it costs more than it saves (profiles/r02_step_probes.md).
 //   * Quantisation with one MUFU.RCP (rcp.approx) instead of the IEEE reciprocal sequence + range-check branch; the GUI taps are
 //     a template parameter, so the hot variant carries none of their predicated-off instructions.
 //   * Raw integer IQ (u8 / s8 / u16 / s16) is dequantised on the way out of shared memory: the bulk copy moves
@@ -68,17 +67,11 @@ __device__ __forceinline__ float rcp_approx(float a) {
 }
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(uint16_t(v)) : "memory"); }
 
-// samples of the previous symbol that travel with a symbol's bulk copy so that every UpdateSignalAverage window ending in the
-// symbol is complete in shared memory: windows of up to L1_PREFIX + 1 samples (the default is 100; 104 keeps 16-byte alignment
-// for every sample size); longer windows are evaluated by the control kernel instead
-constexpr int L1_PREFIX = 104;
-
 template <int NFFT, int SB>
 struct FrameV3Smem {
     using G = FftGeom<NFFT>;
     using D = DabGeom<NFFT>;
     static constexpr int GROUPS = FRAME_CTA_THREADS / G::T;
-    static_assert((L1_PREFIX * SB) % 16 == 0, "the prefix must not change the 16-byte phase of the symbol");
     static constexpr size_t r16(size_t x) { return (x + 15) & ~size_t(15); }
     static constexpr size_t TW2_BYTES = r16(size_t(G::TW2_SIZE) * sizeof(float2));
     static constexpr size_t OFF_TW1 = 0;
@@ -86,7 +79,7 @@ struct FrameV3Smem {
     static constexpr size_t OFF_E2 = OFF_E1 + size_t(G::E1_SIZE) * sizeof(float2);
     static constexpr size_t OFF_STAGE = OFF_E2 + size_t(G::E2_SIZE) * sizeof(float2);
     static constexpr size_t OFF_IN = OFF_STAGE + r16((size_t(D::NCARR) + 8) * 2);
-    static constexpr size_t IN_BYTES = r16(size_t(L1_PREFIX + D::SP) * SB + 15);   // prefix + symbol + worst-case misalignment of its first byte
+    static constexpr size_t IN_BYTES = r16(size_t(D::SP) * SB + 15);   // symbol + worst-case misalignment of its first byte
     static constexpr size_t OFF_DTAB = OFF_IN + IN_BYTES;
     static constexpr size_t OFF_RED = OFF_DTAB + 16 * sizeof(float2);
     static constexpr size_t OFF_MBAR = OFF_RED + 4 * sizeof(float2);
@@ -127,7 +120,6 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_i
     constexpr int WARPS_PER_GROUP = (T + 31) / 32;
     constexpr int RED_WIDTH = (T < 32) ? T : 32;
     constexpr int CP = D::CP, SP = D::SP, NCARR = D::NCARR, TAIL0 = D::TAIL0;
-    constexpr int PFX = L1_PREFIX;
     // helper roles are spread over the warps of a group so that no single warp carries all the serial extras
     constexpr int DTAB_T0 = (T >= 64) ? 32 : 0;   // 16 lanes starting here refresh the D_j table
     constexpr int PE_T = T - 1;                   // this thread turns the cyclic-prefix correlation into a phase error
@@ -161,22 +153,19 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_i
     }
 
     const float f = desc.freq;
-    const bool l1_on = active && desc.l1_out != nullptr;   // group-uniform
 
-    // ---- fetch of one symbol into the group's input buffer.  Sample i of the symbol lands at inbuf + PFX * SB + a + i * SB, where
-    // a = (address of the symbol's first byte) & 15 (ring sizes are multiples of 16 bytes, so wrapping does not change a); with
-    // `pfx` the PFX samples before the symbol come along and land right in front of it.
+    // ---- fetch of one symbol into the group's input buffer.  Sample i of the symbol lands at inbuf + a + i * SB, where
+    // a = (address of the symbol's first byte) & 15 (ring sizes are multiples of 16 bytes, so wrapping does not change a).
     const uint32_t a0 = uint32_t((reinterpret_cast<uintptr_t>(desc.src) + uint64_t(desc.start) * SB) & 15u);
     auto align_of = [&](int s) -> uint32_t { return (a0 + uint32_t(s) * uint32_t((SP * SB) & 15)) & 15u; };
     bool pend_fast = false;   // the symbol about to be consumed was fetched by TMA (group-uniform)
     uint32_t phase = 0;       // mbarrier phase parity of the next TMA completion
-    auto fetch = [&](int s, bool with_pfx) {
-        const int pfx = with_pfx ? PFX : 0;
-        const uint64_t p0 = uint64_t(desc.start + int64_t(s) * SP - pfx) & desc.mask;
+    auto fetch = [&](int s) {
+        const uint64_t p0 = uint64_t(desc.start + int64_t(s) * SP) & desc.mask;
         const uint64_t byte0 = p0 * SB;
         const uint32_t a = align_of(s);
-        const uint32_t bytes = (a + uint32_t((pfx + SP) * SB) + 15u) & ~15u;
-        unsigned char* dst = inbuf + (PFX - pfx) * SB;
+        const uint32_t bytes = (a + uint32_t(SP * SB) + 15u) & ~15u;
+        unsigned char* dst = inbuf;
         const bool fast = (byte0 >= a) && (byte0 - a + bytes <= desc.limit * SB);
         if (fast) {
             if (t == 0) {
@@ -185,7 +174,7 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_i
                 bulk_copy_g2s(smem_u32(dst), reinterpret_cast<const unsigned char*>(desc.src) + (byte0 - a), bytes, mbar);
             }
         } else {  // ring wrap / end of an unaligned buffer: masked index per sample, visible after the next CTA barrier
-            for (int i = t; i < pfx + SP; i += T) {
+            for (int i = t; i < SP; i += T) {
                 const uint64_t p = (p0 + uint64_t(i)) & desc.mask;
                 if (SB == 2) *reinterpret_cast<unsigned short*>(dst + a + i * SB) = __ldg(reinterpret_cast<const unsigned short*>(desc.src) + p);
                 else if (SB == 4) *reinterpret_cast<unsigned int*>(dst + a + i * SB) = __ldg(reinterpret_cast<const unsigned int*>(desc.src) + p);
@@ -212,7 +201,7 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_i
 
     // ---- per work item setup; the first symbol is requested before the tables are built so that its latency hides behind them
     if (t == 0) mbar_init(mbar, 1);
-    if (active) fetch(s_load0, false);
+    if (active) fetch(s_load0);
     for (int i = threadIdx.x; i < G::TW2_SIZE; i += FRAME_CTA_THREADS) tw2[i] = __ldg(geo.twiddles + G::TW1_SIZE + i);
     {
         float ph = f * float(t);
@@ -247,17 +236,6 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_i
     for (int r = 0; r < 16; r++) prev[r] = make_float2(0.0f, 0.0f);
     int staged = -1;
 
-    // UpdateSignalAverage windows of this item: l1_w is the next window to sum, l1_a its first sample; the sub-warps of the group
-    // take the windows round robin
-    constexpr int L1_SUBS = T / RED_WIDTH;
-    const int l1_sub = t / RED_WIDTH, l1_lane = t % RED_WIDTH;
-    const unsigned l1_mask = (RED_WIDTH == 32) ? 0xFFFFFFFFu : (((1u << RED_WIDTH) - 1u) << ((threadIdx.x & 31) / RED_WIDTH * RED_WIDTH));
-    constexpr int L1_PER_LANE = (L1_PREFIX + 1 + RED_WIDTH - 1) / RED_WIDTH;   // samples per lane for the longest window an item may own
-    const int l1_k = desc.l1_k, l1_step = max(desc.l1_step, 1);
-    int l1_w = l1_on ? desc.l1_w_lo : 0x7FFFFFFF;
-    // first sample of window l1_w relative to the start of the symbol about to be processed (>= -(K - 1) once it can end there)
-    int l1_rel = l1_on ? int(desc.l1_origin + int64_t(desc.l1_w_lo) * desc.l1_step - (desc.start + int64_t(s_load0) * SP)) : 0;
-
     if (active && t >= DTAB_T0 && t < DTAB_T0 + 16) write_dtab(s_load0, t - DTAB_T0);
     __syncthreads();  // tables, mbarrier and (slow path) the first symbol are visible
     if (GROUPS > 1) n_loop = n_loop_s;
@@ -284,15 +262,12 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_i
         const bool own = sym_active && (s >= desc.s_begin);
         float2 v[16];
         float2 corr = make_float2(0.0f, 0.0f);
-        float l1_acc_a = 0.0f, l1_acc_b = 0.0f;
-        int l1_n = 0;
         if (sym_active) {
             if (pend_fast) {
                 mbar_wait(mbar, phase);
                 phase ^= 1u;
             }
-            const unsigned char* sym0 = inbuf + PFX * SB + align_of(s);
-            const unsigned char* mine = sym0 + t * SB;
+            const unsigned char* mine = inbuf + align_of(s) + t * SB;
 #pragma unroll
             for (int j = 0; j < 16; j++) v[j] = read_sample(mine + (CP + T * j) * SB);
             // cyclic-prefix correlation on the raw samples: x[N + n] conj(x[n]), n = T j + t - TAIL0 in [0, CP)
@@ -304,28 +279,6 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_i
                     const float2 pr = cmul_conj(v[j], h);
                     corr.x += pr.x;
                     corr.y += pr.y;
-                }
-            }
-            // CalculateL1Average (ofdm_demodulator.cpp:922-932) of the windows that end in this symbol: sub-warp q takes windows q and
-            // L1_SUBS + q of the symbol, every lane sums a run of consecutive samples here and the butterflies follow after barrier A,
-            // next to the second FFT pass.  Straight-line predicated code on purpose: as a loop in a block of its own the dependent
-            // load -> add -> shuffle chain could not overlap the transform and cost 14 % of the kernel (profiles/r02_step_probes.md).
-            l1_n = (l1_w <= desc.l1_w_hi && l1_rel + l1_k <= SP) ? min((SP - l1_k - l1_rel) / l1_step + 1, desc.l1_w_hi - l1_w + 1) : 0;
-            {
-                const unsigned char* wa = sym0 + (l1_rel + l1_sub * l1_step + l1_lane * L1_PER_LANE) * SB;
-                const unsigned char* wb = wa + L1_SUBS * l1_step * SB;
-                const int n_mine = l1_k - l1_lane * L1_PER_LANE;   // samples of a window that fall to this lane (<= 0: none)
-                const bool has_a = l1_sub < l1_n, has_b = L1_SUBS + l1_sub < l1_n;
-#pragma unroll
-                for (int i = 0; i < L1_PER_LANE; i++) {
-                    if (has_a && i < n_mine) {
-                        const float2 x = read_sample(wa + i * SB);
-                        l1_acc_a += fabsf(x.x) + fabsf(x.y);
-                    }
-                    if (has_b && i < n_mine) {
-                        const float2 x = read_sample(wb + i * SB);
-                        l1_acc_b += fabsf(x.x) + fabsf(x.y);
-                    }
                 }
             }
             const float4* d4 = reinterpret_cast<const float4*>(dtab);
@@ -367,7 +320,7 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_i
 
         const bool has_next = active && (s + 1 < desc.s_end);
         if (has_next) {
-            fetch(s + 1, l1_on);
+            fetch(s + 1);
             if (t >= DTAB_T0 && t < DTAB_T0 + 16) write_dtab(s + 1, t - DTAB_T0);
         }
         if (own && t == PE_T && desc.phase_err != nullptr) {
@@ -385,17 +338,6 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_i
             staged = -1;
         }
 
-        {   // the two window sums of this sub-warp: butterfly, average, store (independent of the transform around them)
-#pragma unroll
-            for (int d = RED_WIDTH / 2; d >= 1; d >>= 1) {
-                l1_acc_a += __shfl_xor_sync(l1_mask, l1_acc_a, d, RED_WIDTH);
-                l1_acc_b += __shfl_xor_sync(l1_mask, l1_acc_b, d, RED_WIDTH);
-            }
-            if (l1_lane == 0 && l1_sub < l1_n) desc.l1_out[l1_w + l1_sub] = l1_acc_a / float(l1_k);
-            if (l1_lane == 0 && L1_SUBS + l1_sub < l1_n) desc.l1_out[l1_w + L1_SUBS + l1_sub] = l1_acc_b / float(l1_k);
-            l1_w += l1_n;
-            l1_rel += l1_n * l1_step - SP;
-        }
         fft_pass2_pipelined<NFFT>(v, t, e1, e2, tw2);
         __syncthreads();  // ---- barrier B
         fft_pass3<NFFT>(v, t, e2);

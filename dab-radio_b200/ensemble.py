@@ -64,12 +64,6 @@ class EnsembleDecoder:
     def decode_frames_device(self, d_bits, stream_stride, d_frames_in_call=None, slot=0):
         capi.check(self.L.dab_ensemble_decode_frames_device(self.h, d_bits, stream_stride, d_frames_in_call, slot))
 
-    def decode_ofdm_frames(self, demod, f=0):
-        """the f-th frame every stream of an OfdmDemodBatch completed in its last call, straight from the demodulator's soft-bit ring"""
-        d_bits, n_bits, ring_slots, d_fic = demod.device_bits()
-        d_slots, max_frames = demod.device_frame_slots()
-        capi.check(self.L.dab_ensemble_decode_frames_indexed(self.h, d_bits, ring_slots * n_bits, n_bits, d_fic, d_slots, max_frames, f))
-
     def device_results(self):
         r = capi.EnsembleResults()
         capi.check(self.L.dab_ensemble_device_results(self.h, C.byref(r)))

@@ -127,13 +127,6 @@ class OfdmDemodBatch:
         capi.check(self.L.dab_ofdm_device_bits(self.h, C.byref(d_bits), C.byref(n_bits), C.byref(slots), C.byref(d_frames)))
         return d_bits.value, int(n_bits.value), int(slots.value), d_frames.value
 
-    def device_frame_slots(self):
-        """(device pointer to int32 frame_slots[n_streams][max_frames], max_frames): ring slot of the f-th frame a stream completed
-        in the last call"""
-        d_slots, max_frames = C.c_void_p(), C.c_int()
-        capi.check(self.L.dab_ofdm_device_frame_slots(self.h, C.byref(d_slots), C.byref(max_frames)))
-        return d_slots.value, int(max_frames.value)
-
     def demod_frames_device(self, d_frames, frame_stride, n_frames, freq_offsets, d_bits, d_phase_err):
         f = np.ascontiguousarray(freq_offsets, np.float32)
         capi.check(self.L.dab_ofdm_demod_frames_device(self.h, d_frames, frame_stride, n_frames, capi.ptr(f), d_bits, d_phase_err))

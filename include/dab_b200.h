@@ -119,8 +119,6 @@ typedef struct {
     float fine_offset_used;   /* used by this frame's PLL */
     float fine_offset_after;  /* after this frame's cyclic-prefix update */
     float signal_average;     /* GetSignalAverage() after the Process() call that completed the frame */
-    int32_t slot;             /* soft-bit buffer of the frame on the device (dab_ofdm_device_bits) */
-    int32_t reserved;
 } dab_ofdm_frame_info;
 
 /* How a stream's samples are stored (examples/app_helpers/app_iq_readers.h:17-35,76-88,109-110,130-135: raw_u8, raw_s8,
@@ -200,13 +198,9 @@ DAB_API int dab_ofdm_attach_device_streams(dab_ofdm* h, const dab_c32* d_iq, siz
 DAB_API int dab_ofdm_join(dab_ofdm* h);
 DAB_API int dab_ofdm_advance(dab_ofdm* h, const size_t* n);
 DAB_API int dab_ofdm_advance_uniform(dab_ofdm* h, size_t n);
-/* Device pointer / geometry of the soft-bit output: every stream owns slots_per_stream soft-bit buffers of n_bits bytes,
- * bits[stream][slot][n_bits], used in rotation (a frame is written while its symbols arrive, over several calls if the blocks are
- * short).  The frames a stream COMPLETED in the most recent process/advance call are frames_in_call[stream] many; the f-th of them
- * sits in slot frame_slots[stream * max_frames_per_call + f] (dab_ofdm_device_frame_slots; also dab_ofdm_frame_info::slot).  Streams
- * that complete one frame per call -- the batched steady state -- all use the same slot in the same call. */
+/* device pointer / geometry of the soft-bit output of the most recent process/advance call:
+ * bits[stream][slot][n_bits], frames_in_call[stream] = how many slots are valid */
 DAB_API int dab_ofdm_device_bits(dab_ofdm* h, const int8_t** d_bits, size_t* n_bits, int* slots_per_stream, const int32_t** d_frames_in_call);
-DAB_API int dab_ofdm_device_frame_slots(dab_ofdm* h, const int32_t** d_frame_slots, int* max_frames_per_call);
 
 DAB_API int dab_ofdm_reset(dab_ofdm* h, int stream);           /* OFDM_Demod::Reset() */
 DAB_API int dab_ofdm_get_state(dab_ofdm* h, int stream, dab_ofdm_state* out);
@@ -356,11 +350,6 @@ DAB_API int dab_ensemble_subchannel_schedule(const dab_subchannel* sub, dab_vit_
  * stream s is decoded iff d_frames_in_call == NULL or d_frames_in_call[s] > slot.  Asynchronous on the handle's stream. */
 DAB_API int dab_ensemble_decode_frames_device(dab_ensemble* h, const int8_t* d_bits, size_t stream_stride,
                                               const int32_t* d_frames_in_call, int slot);
-/* The f-th frame each stream completed in the demodulator's last call, straight from its soft-bit ring (dab_ofdm_device_bits +
- * dab_ofdm_device_frame_slots): stream s is decoded iff d_frames_in_call[s] > f, and its frame starts at
- * d_bits + s * stream_stride + d_frame_slots[s * frame_slots_stride + f] * slot_stride. */
-DAB_API int dab_ensemble_decode_frames_indexed(dab_ensemble* h, const int8_t* d_bits, size_t stream_stride, size_t slot_stride,
-                                               const int32_t* d_frames_in_call, const int32_t* d_frame_slots, int frame_slots_stride, int f);
 /* The same from host memory: bits[n_streams][nb_frame_bits]; present[n_streams] (optional) = 0 skips a stream. */
 DAB_API int dab_ensemble_decode_frames(dab_ensemble* h, const int8_t* bits, const uint8_t* present);
 

@@ -142,7 +142,7 @@ def test_long_subchannel_spills(ens, oracle):
 
 
 def test_demod_to_bytes_on_device(ens, oracle, pkg):
-    """OFDM soft bits stay on the device: dab_ofdm_device_bits / dab_ofdm_device_frame_slots -> dab_ensemble_decode_frames_indexed.  The oracle decodes the
+    """OFDM soft bits stay on the device: dab_ofdm_device_bits -> dab_ensemble_decode_frames_device.  The oracle decodes the
     same soft bits (copied back through the frame callback) on the CPU."""
     import dabgen
     ofdm = importlib.import_module("dab-radio_b200.ofdm")
@@ -158,11 +158,10 @@ def test_demod_to_bytes_on_device(ens, oracle, pkg):
     for off in range(0, xs[0].size, 196608):
         d.process_batch([x[off:off + 196608] for x in xs])
         d.sync()
-        d_bits, n_bits, ring_slots, d_fic = d.device_bits()
-        _, max_frames = d.device_frame_slots()
-        assert n_bits == 230400 and ring_slots == max_frames + 1
-        for slot in range(max_frames):
-            dec.decode_ofdm_frames(d, slot)     # dab_ensemble_decode_frames_indexed on the demodulator's soft-bit ring
+        d_bits, n_bits, slots, d_fic = d.device_bits()
+        assert n_bits == 230400
+        for slot in range(slots):
+            dec.decode_frames_device(d_bits + slot * n_bits, slots * n_bits, d_fic, slot)
             dec.sync()
             for s in range(n_streams):
                 frames = d.frames[s]
