@@ -169,6 +169,11 @@ class OfdmDemodBatch:
         capi.check(self.L.dab_ofdm_get_frame_data_bits(self.h, stream, capi.ptr(out), out.size))
         return out
 
+    def correlation_time_buffer(self, stream):
+        out = np.zeros(self.params.nb_null_period + self.params.nb_symbol_period, np.complex64)
+        capi.check(self.L.dab_ofdm_get_correlation_time_buffer(self.h, stream, capi.ptr(out), out.size))
+        return out
+
     def frame_fft(self, stream):
         out = np.zeros(self.params.nb_frame_symbols * self.params.nb_fft, np.complex64)
         capi.check(self.L.dab_ofdm_get_frame_fft(self.h, stream, capi.ptr(out), out.size))

@@ -409,6 +409,10 @@ const orc_c32* orc_ofdm_frame_fft(const orc_ofdm* d) { return d->pipe_fft; }
 const orc_c32* orc_ofdm_frame_data_vec(const orc_ofdm* d) { return d->pipe_vec; }
 const float* orc_ofdm_impulse_response(const orc_ofdm* d) { return d->impulse_response; }
 const float* orc_ofdm_coarse_freq_response(const orc_ofdm* d) { return d->freq_response; }
+const orc_c32* orc_ofdm_correlation_time_buffer(const orc_ofdm* d, size_t* length) {
+    if (length) *length = d->corr_length;
+    return d->corr;
+}
 
 int orc_ofdm_get_frame(const orc_ofdm* d, size_t index, orc_frame_info* info, int8_t* bits_out) {
     if (index >= d->n_frames) return -1;

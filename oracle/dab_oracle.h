@@ -94,6 +94,8 @@ const orc_c32* orc_ofdm_frame_fft(const orc_ofdm* d);       /* (S+1)*nb_fft */
 const orc_c32* orc_ofdm_frame_data_vec(const orc_ofdm* d);  /* (S-1)*nb_data_carriers */
 const float* orc_ofdm_impulse_response(const orc_ofdm* d);  /* nb_fft */
 const float* orc_ofdm_coarse_freq_response(const orc_ofdm* d);
+/* GetCorrelationTimeBuffer() (ofdm_demodulator.h:139): nb_null_period + nb_symbol_period samples, the first *length filled */
+const orc_c32* orc_ofdm_correlation_time_buffer(const orc_ofdm* d, size_t* length);
 /* stage-level entry: demodulate one already-aligned frame (S symbols of nb_symbol_period) with a given net offset */
 void orc_ofdm_demod_frame(const orc_params* p, const int* mapper, const orc_c32* frame, float freq_offset, int8_t* bits_out,
                           float* phase_error_sum);

@@ -215,9 +215,15 @@ def demod_frame(mode, frame, freq_offset):
 
 
 class OracleOfdmDemod:
-    def __init__(self, mode):
+    def __init__(self, mode, custom=None):
+        """mode: DAB transmission mode 1-4, or None with custom = (Params, prs_fft_ref complex64[nb_fft], mapper int32[nb_data_carriers])
+        for any geometry OFDM_Demod's constructor accepts (ofdm_demodulator.cpp:80-146)"""
         self.L = lib()
-        self.h = self.L.orc_ofdm_create(mode)
+        if custom is not None:
+            self._custom = (custom[0], np.ascontiguousarray(custom[1], np.complex64), np.ascontiguousarray(custom[2], np.int32))
+            self.h = self.L.orc_ofdm_create_custom(C.byref(self._custom[0]), _p(self._custom[1]), _p(self._custom[2]))
+        else:
+            self.h = self.L.orc_ofdm_create(mode)
         if not self.h:
             raise ValueError(f"invalid transmission mode {mode}")
         self.frame_bits = int(self.L.orc_ofdm_frame_bits(self.h))
@@ -271,6 +277,17 @@ class OracleOfdmDemod:
 
     def coarse_freq_response(self):
         return self._tap("orc_ofdm_coarse_freq_response", params(self.mode)["nb_fft"], np.float32)
+
+    def correlation_time_buffer(self):
+        """(buffer of nb_null_period + nb_symbol_period samples, filled length)"""
+        p = params(self.mode)
+        n = p["nb_null_period"] + p["nb_symbol_period"]
+        length = C.c_size_t(0)
+        self.L.orc_ofdm_correlation_time_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
+        self.L.orc_ofdm_correlation_time_buffer.restype = C.c_void_p
+        ptr = self.L.orc_ofdm_correlation_time_buffer(self.h, C.byref(length))
+        buf = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(2 * n,)).copy().view(np.complex64)
+        return buf, int(length.value)
 
     def close(self):
         if self.h:

@@ -89,7 +89,7 @@ def _bind(L):
     L.ref_ofdm_get_frame.argtypes = [vp, u64, C.POINTER(FrameInfo), vp]
     L.ref_ofdm_get_state.argtypes = [vp, C.POINTER(OfdmState)]
     for name in ("ref_ofdm_get_frame_fft", "ref_ofdm_get_frame_data_vec", "ref_ofdm_get_impulse_response",
-                 "ref_ofdm_get_coarse_freq_response"):
+                 "ref_ofdm_get_coarse_freq_response", "ref_ofdm_get_correlation_time_buffer"):
         getattr(L, name).argtypes = [vp, vp]
     L.ref_ofdm_bench.argtypes = [i32, i32, i32, vp, u64, u64, i32, C.POINTER(u64)]
     L.ref_ofdm_bench.restype = C.c_double
@@ -191,6 +191,7 @@ class RefOfdmDemod:
 
     def __init__(self, mode, nb_threads=1, collect=True):
         self.L = lib()
+        self.mode = mode
         self.h = self.L.ref_ofdm_create(mode, nb_threads, 1 if collect else 0)
         if not self.h:
             raise RuntimeError("ref_ofdm_create failed")
@@ -220,6 +221,30 @@ class RefOfdmDemod:
         s = OfdmState()
         self.L.ref_ofdm_get_state(self.h, C.byref(s))
         return {k: getattr(s, k) for k, _ in OfdmState._fields_ if k != "pad"}
+
+    # GUI getters (ofdm_demodulator.h:133-139) of the latest frame / synchronisation
+    def _tap(self, fn, n, dtype):
+        out = np.zeros(n, dtype)
+        getattr(self.L, fn)(self.h, _p(out))
+        return out
+
+    def frame_fft(self):
+        p = params(self.mode)
+        return self._tap("ref_ofdm_get_frame_fft", (p["nb_frame_symbols"] + 1) * p["nb_fft"], np.complex64)
+
+    def frame_data_vec(self):
+        p = params(self.mode)
+        return self._tap("ref_ofdm_get_frame_data_vec", (p["nb_frame_symbols"] - 1) * p["nb_data_carriers"], np.complex64)
+
+    def impulse_response(self):
+        return self._tap("ref_ofdm_get_impulse_response", params(self.mode)["nb_fft"], np.float32)
+
+    def coarse_freq_response(self):
+        return self._tap("ref_ofdm_get_coarse_freq_response", params(self.mode)["nb_fft"], np.float32)
+
+    def correlation_time_buffer(self):
+        p = params(self.mode)
+        return self._tap("ref_ofdm_get_correlation_time_buffer", p["nb_null_period"] + p["nb_symbol_period"], np.complex64)
 
     def close(self):
         if self.h:

@@ -305,6 +305,11 @@ void ref_ofdm_get_coarse_freq_response(void* h, float* out) {
     auto v = static_cast<OfdmCtx*>(h)->demod->GetCoarseFrequencyResponse();
     std::memcpy(out, v.data(), v.size() * sizeof(float));
 }
+// GetCorrelationTimeBuffer() (ofdm_demodulator.h:139): the whole NULL + PRS buffer, nb_null_period + nb_symbol_period samples
+void ref_ofdm_get_correlation_time_buffer(void* h, float* out) {
+    auto v = static_cast<OfdmCtx*>(h)->demod->GetCorrelationTimeBuffer();
+    std::memcpy(out, v.data(), v.size() * sizeof(std::complex<float>));
+}
 
 // CPU baseline: n_instances independent demodulators, each fed the same IQ `repeats` times in `block` sample calls
 // from its own thread with the reference's stock Process() (file mode).  Returns wall seconds; *frames_out gets the

@@ -104,3 +104,34 @@ def test_ofdm_stream_parity(oracle, ref, mode, block, cfo, start, snr):
     assert r.state()["total_frames_desync"] == o.state()["total_frames_desync"]
     r.close()
     o.close()
+
+
+def _db_close(a, b, floor_db=50.0, tol_db=0.05):
+    """dB curves agree where they are within floor_db of the peak (deep nulls are rounding noise in both)"""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    keep = np.isfinite(a) & np.isfinite(b) & (np.maximum(a, b) > max(np.max(a[np.isfinite(a)]), np.max(b[np.isfinite(b)])) - floor_db)
+    return keep.sum() > 0 and float(np.max(np.abs(a[keep] - b[keep]))) <= tol_db
+
+
+@pytest.mark.parametrize("mode,block,cfo,start", [(1, 65536, 333.0, 5000), (2, 4096, -2500.0, 0), (4, 65536, 20000.0, 44444)])
+def test_ofdm_gui_taps_parity(oracle, ref, mode, block, cfo, start):
+    """the GUI-visible buffers (ofdm_demodulator.h:133-139: GetFrameFFT, GetFrameDataVec, GetImpulseResponse,
+    GetCoarseFrequencyResponse, GetCorrelationTimeBuffer) of the reference vs the oracle after the same stream"""
+    x = dabgen.make_stream(mode, 4, seed=mode + 70, cfo_hz=cfo, start=start, snr_db=25.0)
+    r, o = ref.RefOfdmDemod(mode, 1), oracle.OracleOfdmDemod(mode)
+    r.process_blocks(x, block)
+    o.process_blocks(x, block)
+    assert r.frames_done() == o.frames_done() >= 2
+    p = oracle.params(mode)
+    S, nfft = p["nb_frame_symbols"], p["nb_fft"]
+    fr, fo = r.frame_fft()[:S * nfft], o.frame_fft()[:S * nfft]
+    assert np.max(np.abs(fr - fo)) <= 2e-4 * np.max(np.abs(fr))
+    vr, vo = r.frame_data_vec(), o.frame_data_vec()
+    assert np.max(np.abs(vr - vo)) <= 4e-4 * np.max(np.abs(vr))
+    assert _db_close(r.impulse_response(), o.impulse_response())
+    assert _db_close(r.coarse_freq_response(), o.coarse_freq_response())
+    cr = r.correlation_time_buffer()
+    co, length = o.correlation_time_buffer()
+    assert np.array_equal(cr[:length], co[:length])
+    r.close()
+    o.close()
