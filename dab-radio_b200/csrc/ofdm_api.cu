@@ -31,6 +31,20 @@ __global__ void ofdm_reset_stream_kernel(StreamState* states, int stream) {
     st.fine_time_offset = 0;
 }
 
+// dab_ofdm_rebase_device_streams: every absolute sample index of a stream moves down by delta (the caller's resident buffer is a
+// ring it refills behind the demodulator)
+__global__ void ofdm_rebase_kernel(StreamState* states, int n_streams, int64_t delta) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    StreamState& st = states[s];
+    st.corr_base -= delta;
+    st.frame_start -= delta;
+    st.consumed -= delta;
+    st.call_begin -= delta;
+    st.call_end -= delta;
+    st.pending_info.frame_start -= delta;
+}
+
 struct NvtxRange {
     explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
     ~NvtxRange() { nvtxRangePop(); }
@@ -63,6 +77,9 @@ struct Ofdm {
     // that the latency-bound control passes of one group overlap the frame kernel of another (DAB_B200_PIPELINE_WAYS, default 4)
     static constexpr int MAX_WAYS = 8;
     int ways = 4;
+    int call_ways = 1;                  // ways of the most recent call (n_ways_for)
+    uint64_t way_min_samples = uint64_t(1) << 24;   // DAB_B200_WAY_MIN_SAMPLES: samples per way and call below which ways are merged
+    uint64_t l1_side_min_block = 32768; // blocks shorter than this have too few windows for a kernel launch of their own
     cudaStream_t way_stream[MAX_WAYS] = {};
     cudaEvent_t way_done[MAX_WAYS] = {};
     cudaEvent_t counts_ready[MAX_WAYS] = {};
@@ -361,7 +378,16 @@ struct WayRange {
     int lo, hi;
     cudaStream_t st;
 };
-static int n_ways(const Ofdm* o) { return (o->n_streams >= 64 * o->ways) ? o->ways : 1; }
+// Pipeline ways of a call: splitting pays when every way still fills the GPU for a while; a call with little work per stream
+// (4096-sample blocks, the short frames of Modes II / III) is launch bound, and every extra way multiplies its launches.
+static int n_ways_for(const Ofdm* o, uint64_t n_max) {
+    if (o->n_streams < 64 * o->ways) return 1;
+    const uint64_t work = uint64_t(o->n_streams) * n_max;   // samples in this call
+    if (work >= o->way_min_samples * uint64_t(o->ways)) return o->ways;
+    if (work >= o->way_min_samples * 2 && o->ways >= 2) return 2;
+    return 1;
+}
+static int n_ways(const Ofdm* o) { return o->call_ways; }   // of the most recent call
 static WayRange way_range(const Ofdm* o, int w, int ways) {
     WayRange r;
     r.lo = int(int64_t(o->n_streams) * w / ways);
@@ -389,7 +415,7 @@ static int issue_way_kernels(Ofdm* o, int w, const WayRange& r, bool uniform, ui
             rc = launch_control(o, st, g, count, p);
         }
         if (rc != DAB_OK) return rc;
-        if (p == 0 && passes > 0 && o->l1_side_kernel) {
+        if (p == 0 && passes > 0 && o->l1_side_kernel && n_max >= o->l1_side_min_block) {
             // every slot of the window buffer that this call can reach under ANY config (the kernel skips windows past the call's
             // end; fold_average sums the windows beyond the buffer itself)
             const int max_windows = (n_max >= 1) ? o->l1_windows_stride : 0;
@@ -485,7 +511,12 @@ static int run_call(Ofdm* o, bool uniform, uint64_t n_uniform, const void* const
     }
     const int passes = passes_for(o, n_max);
     if (passes > o->slots) return set_error(DAB_ERR_CAPACITY, "call of %llu samples exceeds max_block_samples", (unsigned long long)n_max);
-    const int ways = n_ways(o);
+    const int ways = n_ways_for(o, n_max);
+    if (ways != o->call_ways) {   // the stream -> way mapping changes: order everything queued under the old mapping first
+        int rc = join_ways(o);
+        if (rc != DAB_OK) return rc;
+        o->call_ways = ways;
+    }
     const size_t sb = sample_bytes(o), ns = size_t(o->n_streams), slots = size_t(o->slots);
     if (o->cb || snapshot) {
         DAB_CUDA_CHECK(o->h_frames.reserve(ns));
@@ -856,6 +887,7 @@ dab_ofdm* dab_ofdm_create(const dab_ofdm_params* params, const dab_c32* prs_fft_
     if (const char* e = getenv("DAB_B200_PIPELINE_WAYS")) { const int w = atoi(e); if (w >= 1 && w <= Ofdm::MAX_WAYS) o->ways = w; }
     if (const char* e = getenv("DAB_B200_SYMS_PER_CHUNK")) { const int c = atoi(e); if (c >= 1 && c <= 1024) o->syms_per_chunk = c; }
     if (const char* e = getenv("DAB_B200_L1_SIDE")) o->l1_side_kernel = (e[0] != '0');
+    if (const char* e = getenv("DAB_B200_WAY_MIN_SAMPLES")) { const long long v = atoll(e); if (v >= 0) o->way_min_samples = uint64_t(v); }
     if (const char* e = getenv("DAB_B200_L1_GRID")) { const int g = atoi(e); if (g >= 1) o->l1_grid = g; }
     if (const char* e = getenv("DAB_B200_L1_PRIO")) o->l1_prio = atoi(e);
     rc = create_impl(o, prs_fft_ref, carrier_mapper);
@@ -1015,6 +1047,26 @@ int dab_ofdm_attach_device_streams(dab_ofdm* h, const dab_c32* d_iq, size_t stri
     o->ext_stride = stride_samples;
     o->ext_total = total_samples;
     return init_states(o);
+}
+
+int dab_ofdm_rebase_device_streams(dab_ofdm* h, size_t delta_samples) {
+    OFDM_HANDLE(h);
+    if (!o->ext_base) return set_error(DAB_ERR_INVALID, "no device-resident streams attached");
+    for (int s = 0; s < o->n_streams; s++)
+        if (o->fed[size_t(s)] < delta_samples) return set_error(DAB_ERR_INVALID, "stream %d has not advanced %zu samples yet", s, delta_samples);
+    { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
+    // the frame being received and the NULL + PRS window must lie at or after the new origin: the demodulator never looks further
+    // back than one frame + one NULL symbol + one symbol behind its cursor
+    const size_t keep = o->p.nb_frame_symbols * o->p.nb_symbol_period + 2 * o->p.nb_null_period + o->p.nb_symbol_period;
+    for (int s = 0; s < o->n_streams; s++)
+        if (o->fed[size_t(s)] - delta_samples < keep)
+            return set_error(DAB_ERR_INVALID, "stream %d: fewer than %zu samples would remain behind the cursor after rebasing", s, keep);
+    ofdm_rebase_kernel<<<(o->n_streams + 127) / 128, 128, 0, o->stream>>>(o->states.ptr, o->n_streams, int64_t(delta_samples));
+    o->launches++;
+    DAB_CUDA_CHECK(cudaGetLastError());
+    for (int s = 0; s < o->n_streams; s++) o->fed[size_t(s)] -= delta_samples;
+    invalidate_snapshot(o);
+    return DAB_OK;
 }
 
 static int advance_impl(Ofdm* o, const size_t* n, size_t n_uniform) {

@@ -334,10 +334,12 @@ struct Control {
     // the kernel wait on instruction fetches for a third of its cycles (profiles/r01d), and one out-of-line copy sent the
     // points through local memory, which thrashes the 22 KB of L1 left beside four CTAs' shared memory (profiles/r01f:
     // 176 us per pass against 80 us).
-    __device__ void run_sync() {
+    __device__ void run_sync(int state) {
         int stage = 3;
-        if (st.state == DAB_OFDM_RUNNING_COARSE_FREQ_SYNC) {
-            if (st.cfg.sync_is_coarse_freq_correction) {
+        if (state == DAB_OFDM_RUNNING_COARSE_FREQ_SYNC) {
+            const bool coarse = st.cfg.sync_is_coarse_freq_correction != 0;
+            __syncthreads();   // everyone has read the configuration before thread 0 touches the state
+            if (coarse) {
                 stage = 0;
             } else {
                 if (tid == 0) { st.freq_coarse = 0.0f; st.state = DAB_OFDM_RUNNING_FINE_TIME_SYNC; }
@@ -694,9 +696,16 @@ ofdm_control_kernel(ControlGeom geo, int pass) {
     if (st.pipeline_pending) ctl.finish_pipeline();
     __syncthreads();
 
-    // OFDM_Demod::Process main loop (ofdm_demodulator.cpp:245-274)
-    while (st.consumed < st.call_end && !stop_flag) {
-        switch (st.state) {
+    // OFDM_Demod::Process main loop (ofdm_demodulator.cpp:245-274).  The stream state lives in shared memory and thread 0 mutates
+    // it: every thread takes its copy of what steers the iteration, then a barrier, and only then may thread 0 move on -- without
+    // it a warp that is late to the loop head can see the NEXT state and walk into a different case (divergent barriers; found by
+    // compute-sanitizer synccheck on Mode II, where three of the four warps only wait at the barriers of the transforms).
+    for (;;) {
+        const bool go = st.consumed < st.call_end && !stop_flag;
+        const int state = st.state;
+        __syncthreads();
+        if (!go) break;
+        switch (state) {
         case DAB_OFDM_FINDING_NULL_POWER_DIP:
             ctl.find_null_power_dip();
             break;
@@ -718,7 +727,7 @@ ofdm_control_kernel(ControlGeom geo, int pass) {
                 if (tid == 0) tw_loaded = 1;
                 __syncthreads();
             }
-            ctl.run_sync();
+            ctl.run_sync(state);
             break;
         case DAB_OFDM_READING_SYMBOLS:
             if (tid == 0) {

@@ -118,6 +118,9 @@ class OfdmDemodBatch:
     def advance_uniform(self, n):
         capi.check(self.L.dab_ofdm_advance_uniform(self.h, n))
 
+    def rebase_device_streams(self, delta_samples):
+        capi.check(self.L.dab_ofdm_rebase_device_streams(self.h, delta_samples))
+
     def advance(self, ns):
         n = (C.c_size_t * self.n_streams)(*ns)
         capi.check(self.L.dab_ofdm_advance(self.h, n))

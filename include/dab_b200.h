@@ -196,6 +196,11 @@ DAB_API int dab_ofdm_attach_device_streams(dab_ofdm* h, const dab_c32* d_iq, siz
  * queued so far without blocking the host; dab_ofdm_device_bits, dab_ofdm_sync, the getters and the frame callback join
  * implicitly.  Work the caller queues on the handle's stream BEFORE a call is always ordered before that call. */
 DAB_API int dab_ofdm_join(dab_ofdm* h);
+/* The attached rows used as ring buffers: the caller has refilled (or laid out periodically) the region behind the demodulator
+ * and moves every stream's origin forward by delta_samples -- sample index i of a row now means what index i + delta meant, so the
+ * next dab_ofdm_advance continues at index (samples advanced so far - delta).  At least one frame + two NULL symbols + one symbol
+ * must remain behind the cursor.  dab_ofdm_frame_info::frame_start counts from the new origin afterwards. */
+DAB_API int dab_ofdm_rebase_device_streams(dab_ofdm* h, size_t delta_samples);
 DAB_API int dab_ofdm_advance(dab_ofdm* h, const size_t* n);
 DAB_API int dab_ofdm_advance_uniform(dab_ofdm* h, size_t n);
 /* device pointer / geometry of the soft-bit output of the most recent process/advance call:

@@ -100,6 +100,10 @@ def _bind(L):
     L.ref_ofdm_pool_frames.restype = u64
     L.ref_ofdm_pool_run.argtypes = [vp, vp, u64, u64, i32]
     L.ref_ofdm_pool_run.restype = C.c_double
+    L.ref_ofdm_pool_run_multi.argtypes = [vp, C.POINTER(vp), u64, u64, i32]
+    L.ref_ofdm_pool_run_multi.restype = C.c_double
+    L.ref_fft_bench.argtypes = [i32, i32]
+    L.ref_fft_bench.restype = C.c_double
     L.ref_vit_create.restype = vp
     L.ref_vit_destroy.argtypes = [vp]
     L.ref_vit_set_traceback_length.argtypes = [vp, u64]
@@ -312,6 +316,17 @@ class RefOfdmPool:
     def run(self, iq, block, repeats):
         iq = np.ascontiguousarray(iq, np.complex64)
         return float(self.L.ref_ofdm_pool_run(self.h, _p(iq), iq.size, block, repeats))
+
+    def run_multi(self, iqs, block, repeats):
+        """instance i consumes iqs[i] (equal lengths) `repeats` times"""
+        arrs = [np.ascontiguousarray(x, np.complex64) for x in iqs]
+        assert len(arrs) == self.n_instances and all(a.size == arrs[0].size for a in arrs)
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        return float(self.L.ref_ofdm_pool_run_multi(self.h, ptrs, arrs[0].size, block, repeats))
+
+    def fft_seconds(self, nfft, reps):
+        """seconds for reps forward FFTs of nfft points through the FFT this build of the reference is linked against"""
+        return float(self.L.ref_fft_bench(nfft, reps))
 
     def frames(self):
         return int(self.L.ref_ofdm_pool_frames(self.h))

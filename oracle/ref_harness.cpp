@@ -37,6 +37,7 @@
 
 // The harness TU alone needs to reach the private stage functions.  The reference's own TUs are built untouched.
 #define private public
+#include <fftw3.h>
 #include "ofdm/ofdm_demodulator.h"
 #undef private
 #include "ofdm/ofdm_demodulator_threads.h"
@@ -396,6 +397,52 @@ double ref_ofdm_pool_run(void* pool, const float* iq_interleaved, uint64_t n, ui
     }
     for (auto& w : workers) w.join();
     const auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// the same with one IQ buffer per instance (bench.py --impl reference: every instance its own stream, CFO and start offset, as
+// the GPU arm's streams)
+double ref_ofdm_pool_run_multi(void* pool, const float* const* iq_interleaved, uint64_t n, uint64_t block, int repeats) {
+    auto* p = static_cast<OfdmPool*>(pool);
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> workers;
+    for (size_t i = 0; i < p->hs.size(); i++) {
+        workers.emplace_back([&, i]() {
+            auto* c = static_cast<OfdmCtx*>(p->hs[i]);
+            auto* x = reinterpret_cast<const std::complex<float>*>(iq_interleaved[i]);
+            for (int r = 0; r < repeats; r++)
+                for (uint64_t off = 0; off < n; off += block) c->demod->Process({x + off, size_t(std::min<uint64_t>(block, n - off))});
+            c->demod->m_coordinator->WaitEnd();
+            c->demod->m_coordinator->SignalEnd();
+            for (int spin = 0; spin < 5000; spin++) {
+                {
+                    std::lock_guard<std::mutex> lock(c->mtx);
+                    if (c->frames_done >= size_t(c->demod->GetTotalFramesRead())) break;
+                }
+                std::this_thread::sleep_for(std::chrono::microseconds(100));
+            }
+        });
+    }
+    for (auto& w : workers) w.join();
+    const auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// seconds for `reps` forward transforms of `nfft` points through the FFT the reference was linked against here (the stand-in of
+// oracle/fftw3_shim; FFTW3 itself is absent from the image): bounds what the real FFTW could change in the CPU baseline
+double ref_fft_bench(int nfft, int reps) {
+    const size_t n_pts = static_cast<size_t>(nfft);
+    std::vector<std::complex<float>> in(n_pts), out(n_pts);
+    for (int i = 0; i < nfft; i++) in[size_t(i)] = {float((i * 37) % 101) / 101.0f - 0.5f, float((i * 53) % 97) / 97.0f - 0.5f};
+    fftwf_plan plan = fftwf_plan_dft_1d(nfft, nullptr, nullptr, FFTW_FORWARD, FFTW_ESTIMATE);
+    volatile float sink = 0.0f;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < reps; r++) {
+        fftwf_execute_dft(plan, reinterpret_cast<fftwf_complex*>(in.data()), reinterpret_cast<fftwf_complex*>(out.data()));
+        sink = sink + out[size_t(r % nfft)].real();
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    fftwf_destroy_plan(plan);
     return std::chrono::duration<double>(t1 - t0).count();
 }
 

@@ -81,6 +81,39 @@ def test_resident_streams_with_pipeline_ways(ofdm, oracle, uniform):
     d.close()
 
 
+@pytest.mark.parametrize("mode,block", [(2, 4096), (2, 49152), (3, 4096), (1, 65536)])
+def test_back_to_back_calls_every_stream_matches_oracle(ofdm, oracle, mode, block):
+    """1024 resident streams, calls queued back to back without any host synchronisation (what bench.py's modes leg does).
+    Regression for a shared-memory race in the control kernel's state loop that only showed under that load: a warp late to the
+    loop head could read the state thread 0 had already advanced and take a different case (a handful of the 1024 streams then
+    lost lock at random; compute-sanitizer synccheck: divergent barrier).  Every stream's frame / desync counts and state must
+    equal the oracle's."""
+    torch = _torch()
+    import bench
+    fl = bench.MODE_FRAME_LEN[mode]
+    n = 1024
+    iq, _ = bench.build_streams_on_device(torch, n, 9, seed=777 + mode, mode=mode, frame_len=fl)
+    torch.cuda.synchronize()
+    calls = 8 * fl // block
+    d = ofdm.OfdmDemodBatch(mode, n_streams=n, max_block_samples=block)
+    d.disable_callback()
+    d.attach_device_streams(iq.data_ptr(), iq.shape[1], iq.shape[1])
+    for _ in range(calls):
+        d.advance_uniform(block)
+    d.sync()
+    host = iq[::4].cpu().numpy()
+    bad = []
+    for i, s in enumerate(range(0, n, 4)):
+        o = oracle.OracleOfdmDemod(mode)
+        o.process_blocks(host[i][:calls * block], block)
+        so, sd = o.state(), d.state(s)
+        if (so["state"], so["total_frames_read"], so["total_frames_desync"]) != (sd["state"], sd["total_frames_read"], sd["total_frames_desync"]):
+            bad.append((s, sd, so))
+        o.close()
+    assert not bad, bad[:4]
+    d.close()
+
+
 # ---------------------------------------------------------------------------------------------------------------------------
 # the generic-geometry frame kernel
 # ---------------------------------------------------------------------------------------------------------------------------

@@ -14,7 +14,7 @@ import bench  # noqa: E402
 
 ofdm = importlib.import_module("dab-radio_b200.ofdm")
 n, FL, K = 1024, bench.FRAME_LEN, 8
-iq = bench.build_streams_on_device(torch, n, 2, seed=1)
+iq, _ = bench.build_streams_on_device(torch, n, 2, seed=1)
 for u8 in (True, False):
     if u8:
         q = torch.clamp(torch.view_as_real(iq[:, :FL]) * 127.5 + 127.5, 0.0, 255.0).to(torch.uint8)

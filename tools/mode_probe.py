@@ -16,7 +16,7 @@ n_streams = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 for mode in (1, 2, 3, 4):
     fl = bench.MODE_FRAME_LEN[mode]
     n_frames = 12
-    iq = bench.build_streams_on_device(torch, n_streams, n_frames + 1, seed=99 + mode, mode=mode, frame_len=fl)
+    iq, _ = bench.build_streams_on_device(torch, n_streams, n_frames + 1, seed=99 + mode, mode=mode, frame_len=fl)
     for block in (4096, fl // 4, fl):
         for ways in ("4", "1"):
             os.environ["DAB_B200_PIPELINE_WAYS"] = ways

@@ -14,7 +14,7 @@ import bench  # noqa: E402
 ofdm = importlib.import_module("dab-radio_b200.ofdm")
 n_streams = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 mode, fl = 1, bench.FRAME_LEN
-iq = bench.build_streams_on_device(torch, n_streams, 14, seed=100, mode=mode, frame_len=fl)
+iq, _ = bench.build_streams_on_device(torch, n_streams, 14, seed=100, mode=mode, frame_len=fl)
 CASES = [{}, {"DAB_B200_L1_SIDE": "0"}]
 for extra in sys.argv[2:]:
     CASES.append(dict(kv.split("=") for kv in extra.split(",")))
