@@ -145,7 +145,7 @@ EXPORTED_SYMBOLS = (
     "dab_get_dab_parameters", "dab_ensemble_create", "dab_ensemble_destroy", "dab_ensemble_set_cuda_stream",
     "dab_ensemble_set_subchannels", "dab_ensemble_subchannel_schedule", "dab_ensemble_decode_frames_device",
     "dab_ensemble_decode_frames", "dab_ensemble_device_results", "dab_ensemble_read_fic", "dab_ensemble_read_msc",
-    "dab_ensemble_sync", "dab_ensemble_kernel_launches", "dab_ensemble_last_work",
+    "dab_ensemble_sync", "dab_ensemble_kernel_launches", "dab_ensemble_last_work", "dab_ensemble_schedule_count",
 )
 
 _lib = None
@@ -255,6 +255,7 @@ def _bind_ensemble(L):
     L.dab_ensemble_read_fic.argtypes = [vp, i32, vp, vp, vp]
     L.dab_ensemble_read_msc.argtypes = [vp, i32, i32, i32, vp, sz, C.POINTER(C.c_int32), C.POINTER(u64)]
     L.dab_ensemble_sync.argtypes = [vp]
+    L.dab_ensemble_schedule_count.argtypes = [vp]
     L.dab_ensemble_kernel_launches.argtypes = [vp]
     L.dab_ensemble_kernel_launches.restype = u64
     L.dab_ensemble_last_work.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]

@@ -48,14 +48,28 @@ size_t DAB_Viterbi_Decoder::update(tcb::span<const viterbi_bit_t> punctured_symb
         consumed += take;
         code_index = (code_index + 1) % puncture_code.size();
     }
-    if (m_segments.size() >= DAB_VIT_MAX_SEGMENTS)
-        throw std::runtime_error("DAB_Viterbi_Decoder: more than 8 update() calls between reset() and chainback()");
     assert(m_current_decoded_bit + requested_output_symbols / m_code_rate <= m_traceback_length + (m_constraint_length - 1));
     Segment seg{};
     for (size_t i = 0; i < puncture_code.size(); i++) seg.counts[i] = puncture_code[i];
     seg.code_len = uint32_t(puncture_code.size());
     seg.n_out = uint32_t(requested_output_symbols);
-    m_segments.push_back(seg);
+    // The reference accepts any number of update() calls.  A call that continues the previous call's code where that one stopped
+    // (same code, previous call ended on a code boundary) extends the previous segment; anything else starts a new one.
+    bool merged = false;
+    if (!m_segments.empty()) {
+        Segment& last = m_segments.back();
+        const bool same_code = last.code_len == seg.code_len && std::memcmp(last.counts, seg.counts, sizeof(seg.counts)) == 0;
+        if (same_code && (last.n_out / m_code_rate) % last.code_len == 0) {
+            last.n_out += seg.n_out;
+            merged = true;
+        }
+    }
+    if (!merged) {
+        if (m_segments.size() >= DAB_VIT_MAX_SEGMENTS)
+            throw std::runtime_error("DAB_Viterbi_Decoder: more than " + std::to_string(DAB_VIT_MAX_SEGMENTS) +
+                                     " distinct puncturing segments between reset() and chainback()");
+        m_segments.push_back(seg);
+    }
     m_soft.insert(m_soft.end(), punctured_symbols.begin(), punctured_symbols.begin() + consumed);
     m_current_decoded_bit += requested_output_symbols / m_code_rate;
     return consumed;
@@ -65,6 +79,13 @@ uint64_t DAB_Viterbi_Decoder::chainback(tcb::span<uint8_t> bytes_out, const size
     const size_t total_bits = bytes_out.size() * 8u;
     assert(m_traceback_length >= total_bits);                                     // viterbi_decoder_core.h:216-218
     assert(m_current_decoded_bit >= total_bits + (m_constraint_length - 1));
+    if (m_segments.empty() || bytes_out.empty()) {
+        // nothing decoded since reset(): the reference chains back over zeroed decisions (all predecessors 0) and reports the
+        // start metric of state 0 -- zero bytes, error 0 when the trellis started there, the initial penalty otherwise
+        // (dab_viterbi_decoder.cpp:31-41: non-start states begin at 5080)
+        std::memset(bytes_out.data(), 0, bytes_out.size());
+        return (m_start_state == 0) ? 0u : 5080u;
+    }
     dab_vit_schedule s{};
     s.n_seg = uint32_t(m_segments.size());
     for (size_t i = 0; i < m_segments.size(); i++) {

@@ -39,8 +39,11 @@ void FIC_Decoder::DecodeFIBGroup(tcb::span<const viterbi_bit_t> encoded_bits, co
     // the reference only knows the Mode I puncturing and decodes nothing for other group sizes (fic_decoder.cpp:68-75)
     const size_t nb_decoded_bits_mode_I = (128 * 21 + 128 * 3 + 24) / 4 - 6;
     if (m_group_bits / 3 != nb_decoded_bits_mode_I) return;
-    if (dab_ensemble_decode_frames(m_ensemble, encoded_bits.data(), nullptr) != DAB_OK) return;
-    if (dab_ensemble_read_fic(m_ensemble, 0, m_bytes.data(), m_crc_ok.data(), &m_path_error) != DAB_OK) return;
+    // a failing call is a CUDA / library error, not "no valid FIB": report it like the OFDM_Demod and DAB_Viterbi_Decoder mirrors do
+    if (dab_ensemble_decode_frames(m_ensemble, encoded_bits.data(), nullptr) != DAB_OK)
+        throw std::runtime_error(std::string("FIC_Decoder::DecodeFIBGroup: ") + dab_last_error());
+    if (dab_ensemble_read_fic(m_ensemble, 0, m_bytes.data(), m_crc_ok.data(), &m_path_error) != DAB_OK)
+        throw std::runtime_error(std::string("FIC_Decoder::DecodeFIBGroup: ") + dab_last_error());
     const size_t nb_fib_bytes = m_group_bytes / m_fibs;
     const size_t nb_crc16_bytes = 2;
     assert(nb_fib_bytes >= nb_crc16_bytes);

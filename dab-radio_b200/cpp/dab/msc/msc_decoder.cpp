@@ -54,9 +54,12 @@ tcb::span<uint8_t> MSC_Decoder::DecodeCIF(tcb::span<const viterbi_bit_t> buf) {
         if (dab_ensemble_set_subchannels(m_handle, 0, &s, 1) != DAB_OK) throw std::runtime_error(std::string("MSC_Decoder: ") + dab_last_error());
         m_cif_bits = N;
     }
-    if (dab_ensemble_decode_frames(m_handle, buf.data(), nullptr) != DAB_OK) return {};
+    // a failing call is a CUDA / library error, not "the de-interleaver is still filling": report it
+    if (dab_ensemble_decode_frames(m_handle, buf.data(), nullptr) != DAB_OK)
+        throw std::runtime_error(std::string("MSC_Decoder::DecodeCIF: ") + dab_last_error());
     int32_t n_bytes = 0;
-    if (dab_ensemble_read_msc(m_handle, 0, 0, 0, m_decoded_bytes_buf.data(), m_decoded_bytes_buf.size(), &n_bytes, &m_last_error) != DAB_OK) return {};
+    if (dab_ensemble_read_msc(m_handle, 0, 0, 0, m_decoded_bytes_buf.data(), m_decoded_bytes_buf.size(), &n_bytes, &m_last_error) != DAB_OK)
+        throw std::runtime_error(std::string("MSC_Decoder::DecodeCIF: ") + dab_last_error());
     if (n_bytes <= 0) return {};   // the de-interleaver is still collecting CIFs (msc_decoder.cpp:60-63)
     return {m_decoded_bytes_buf.data(), size_t(n_bytes)};
 }

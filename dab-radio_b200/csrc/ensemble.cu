@@ -721,6 +721,25 @@ int dab_ensemble_set_subchannels(dab_ensemble* h, int stream, const dab_subchann
         }
         e->subs[size_t(s)].assign(subs, subs + n_subs);
     }
+    // garbage-collect the puncturing schedules no sub-channel refers to any more (schedule 0 is the FIC's): a receiver that is
+    // re-tuned for days must not grow the host and device tables without bound
+    {
+        std::vector<int> remap(e->schedules.size(), -1);
+        remap[0] = 0;
+        int next = 1;
+        for (const SubDesc& sd : e->h_subs)
+            if (sd.schedule > 0 && remap[size_t(sd.schedule)] < 0) remap[size_t(sd.schedule)] = next++;
+        if (size_t(next) < e->schedules.size()) {
+            std::vector<dab_vit_schedule> keys(static_cast<size_t>(next));
+            std::vector<DevSchedule> scheds(static_cast<size_t>(next));
+            for (size_t i = 0; i < remap.size(); i++)
+                if (remap[i] >= 0) { keys[size_t(remap[i])] = e->schedule_keys[i]; scheds[size_t(remap[i])] = e->schedules[i]; }
+            e->schedule_keys.swap(keys);
+            e->schedules.swap(scheds);
+            for (SubDesc& sd : e->h_subs)
+                if (sd.schedule > 0) sd.schedule = remap[size_t(sd.schedule)];
+        }
+    }
     DAB_CUDA_CHECK(cudaMemcpy(e->d_stored.ptr, stored.data(), stored.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     DAB_CUDA_CHECK(cudaMemsetAsync(e->d_msc_nbytes.ptr + size_t(s0) * g.nb_cifs * K, 0, size_t(s1 - s0) * g.nb_cifs * K * sizeof(int32_t), e->stream));
     e->tables_dirty = true;
@@ -834,6 +853,11 @@ int dab_ensemble_sync(dab_ensemble* h) {
     DAB_CUDA_CHECK(cudaSetDevice(e->device));
     DAB_CUDA_CHECK(cudaStreamSynchronize(e->stream));
     return DAB_OK;
+}
+
+int dab_ensemble_schedule_count(const dab_ensemble* h) {
+    auto* e = reinterpret_cast<const Ensemble*>(h);
+    return e ? int(e->schedules.size()) : 0;
 }
 
 uint64_t dab_ensemble_kernel_launches(const dab_ensemble* h) {

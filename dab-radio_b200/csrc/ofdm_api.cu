@@ -441,7 +441,7 @@ static int issue_way_kernels(Ofdm* o, int w, const WayRange& r, bool uniform, ui
         }
         if (p < passes) {
             ScopedKernelTimer timer(o, st, p, true);
-            rc = launch_frame(o, st, o->descs.ptr + (size_t(p) * size_t(o->n_streams) + size_t(r.lo)) * size_t(o->n_chunks), count * o->n_chunks);
+            rc = launch_frame(o, st, g.descs + (size_t(p) * size_t(o->n_streams) + size_t(r.lo)) * size_t(o->n_chunks), count * o->n_chunks);
             if (rc != DAB_OK) return rc;
         }
         if (p == 0 && g.l1_ready) DAB_CUDA_CHECK(cudaStreamWaitEvent(st, o->l1_done[w], 0));
@@ -771,6 +771,7 @@ static int create_impl(Ofdm* o, const dab_c32* prs, const int* mapper) {
     DAB_CUDA_CHECK(o->states.reserve(ns));
     DAB_CUDA_CHECK(o->descs.reserve(ns * size_t(o->slots) * size_t(o->n_chunks)));
     DAB_CUDA_CHECK(o->infos.reserve(ns * size_t(o->slots)));
+    DAB_CUDA_CHECK(cudaMemset(o->infos.ptr, 0, ns * size_t(o->slots) * sizeof(dab_ofdm_frame_info)));
     DAB_CUDA_CHECK(o->frames_in_call.reserve(ns));
     DAB_CUDA_CHECK(o->bits.reserve(ns * size_t(o->slots) * o->frame_bits));
     DAB_CUDA_CHECK(cudaMemset(o->bits.ptr, 0, ns * size_t(o->slots) * o->frame_bits));

@@ -21,7 +21,7 @@
 
 namespace dabb200 {
 
-constexpr int FRAME_MAX_CHUNKS = 4;  // work items a frame is split into (load balance: a frame is 76 - 153 symbols long)
+constexpr int FRAME_MAX_CHUNKS = 6;  // work items a frame is split into (load balance: a frame is 76 - 153 symbols long)
 
 struct StreamState {
     // --- mirrors of the OFDM_Demod members (ofdm_demodulator.h:58-75)
@@ -96,10 +96,11 @@ constexpr int CTRL_L1_BATCH = 1024;  // windows whose L1 averages are computed i
 template <int NFFT>
 struct ControlSmem {
     using G = FftGeom<NFFT>;
-    // at least four warps whatever the FFT size: the transforms use the first N/16 threads, the L1 window scans (FindNullPowerDip
-    // walks whole blocks while a stream is unlocked) use all of them -- with one warp per stream a 1024-stream Mode II / III step
-    // spent 0.5 ms in the scans of the unlocked streams (profiles/r02a_mode_probe_baseline.txt)
-    static constexpr int THREADS = (G::T < 128) ? 128 : G::T;
+    // four warps whatever the FFT size: the transforms use the first N/16 threads, the L1 window scans (FindNullPowerDip walks whole
+    // blocks while a stream is unlocked) use all of them.  With N/16 threads (one warp in Modes II / III) a 1024-stream step spent
+    // 0.5 ms in the scans of the unlocked streams; 64 threads (twice the CTAs per SM for the synchronisation transforms) measured
+    // 20 - 30 % slower than 128 on every Mode II / III configuration (profiles/r02_modes.md)
+    static constexpr int THREADS = 128;
     // `nat` (natural-order spectrum between two transforms) aliases exchange 1 and the L1 window batch aliases the (contiguous) exchanges: both
     // are only alive while no transform is in flight (every hand-over is separated by a CTA barrier)
     static_assert(G::E1_SIZE >= NFFT, "nat must fit into exchange 1");
@@ -115,6 +116,33 @@ struct ArgMax {
 __device__ __forceinline__ ArgMax argmax_combine(ArgMax a, ArgMax b) {
     const bool take_b = (b.value > a.value) || (b.value == a.value && b.index < a.index);
     return take_b ? b : a;
+}
+
+// CalculateL1Average of a window of K <= 32 samples by ONE thread, bit-identical to the warp form used for longer windows (one
+// sample per lane, then the xor butterfly: what lane 0 ends up with is the tree t[i] += t[i + d], d = 16, 8, 4, 2, 1 over the
+// zero-padded samples).  With one window per lane a warp sums 32 short windows per round instead of one: the 25-sample windows
+// that make Modes II / III lock (OFDM_Demod_Config::signal_l1) otherwise use 25 lanes for one 8-byte load each.
+template <int SB>
+__device__ __forceinline__ float l1_short_window(const void* src, uint64_t first, uint64_t mask, int K, const SampleFmt& fmt) {
+    float s16[16];
+    // eight pairs (i, i + 16) at a time: sixteen independent loads in flight before the first addition
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        float2 xa[8], xb[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int i = 8 * h + j;
+            xa[j] = (i < K) ? load_sample<SB>(src, (first + uint64_t(i)) & mask, fmt) : make_float2(0.0f, 0.0f);
+            xb[j] = (i + 16 < K) ? load_sample<SB>(src, (first + uint64_t(i + 16)) & mask, fmt) : make_float2(0.0f, 0.0f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) s16[8 * h + j] = (fabsf(xa[j].x) + fabsf(xa[j].y)) + (fabsf(xb[j].x) + fabsf(xb[j].y));
+    }
+#pragma unroll
+    for (int d = 8; d >= 1; d >>= 1)
+#pragma unroll
+        for (int i = 0; i < d; i++) s16[i] += s16[i + d];
+    return s16[0] / float(K);
 }
 
 template <int NFFT, int SB>
@@ -144,6 +172,10 @@ struct Control {
     // (FindNullPowerDip scans whole blocks) the long pole of a 1024-stream step.  Per window the additions keep their order
     // (lane-strided partial sums, then the butterfly): the frame kernel sums its windows the same way.  No barrier inside.
     __device__ void l1_windows(float* out, int64_t first, int step, int K, int count) {
+        if (K <= 32) {   // one window per thread
+            for (int w = tid; w < count; w += THREADS) out[w] = l1_short_window<SB>(src, uint64_t(first + int64_t(w) * step), geo.mask, K, geo.fmt);
+            return;
+        }
         constexpr int U = 8;
         const int lane = tid & 31, warp = tid >> 5, n_warps = THREADS / 32;
         for (int w = warp * U; w < count; w += n_warps * U) {
@@ -592,6 +624,19 @@ template <int SB>
 __global__ void __launch_bounds__(L1_CTA_THREADS, 16) ofdm_l1_windows_kernel(ControlGeom geo, int n_streams, int max_windows) {
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
+    // short windows (K <= 32, checked per stream): one window per thread, streams in turn
+    for (int s = blockIdx.x; s < n_streams; s += gridDim.x) {
+        const int stream = geo.stream0 + s;
+        const StreamState* st = geo.states + stream;
+        const int K = st->cfg.signal_l1_nb_samples;
+        const int L = K * st->cfg.signal_l1_nb_decimate;
+        const int64_t N = st->call_end - st->call_begin;
+        if (K <= 0 || K > 32 || L <= 0 || N < K || !st->avg_pending) continue;
+        const int64_t n_windows = min(int64_t(max_windows), (N - K + L - 1) / L);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(geo.samples) + size_t(stream) * geo.stream_stride * SB;
+        for (int64_t w = threadIdx.x; w < n_windows; w += blockDim.x)
+            geo.l1_windows[size_t(stream) * geo.l1_windows_stride + w] = l1_short_window<SB>(src, uint64_t(st->call_begin + w * L), geo.mask, K, geo.fmt);
+    }
     const int groups = (max_windows + L1_WB - 1) / L1_WB;
     const int total = n_streams * groups;
     for (int task = blockIdx.x * warps_per_block + (threadIdx.x >> 5); task < total; task += gridDim.x * warps_per_block) {
@@ -601,7 +646,7 @@ __global__ void __launch_bounds__(L1_CTA_THREADS, 16) ofdm_l1_windows_kernel(Con
         const int L = K * st->cfg.signal_l1_nb_decimate;
         const int64_t call_begin = st->call_begin;
         const int64_t N = st->call_end - call_begin;
-        if (K <= 0 || L <= 0 || N < K || !st->avg_pending) continue;
+        if (K <= 32 || L <= 0 || N < K || !st->avg_pending) continue;
         const unsigned char* src = reinterpret_cast<const unsigned char*>(geo.samples) + size_t(stream) * geo.stream_stride * SB;
         // window b: samples [first, first + K) of the stream; `flat` when it does not wrap around the ring
         bool live[L1_WB], flat[L1_WB];
@@ -656,6 +701,8 @@ ofdm_control_kernel(ControlGeom geo, int pass) {
     __shared__ StreamState st;
     __shared__ int stop_flag;
     const int stream = geo.stream0 + blockIdx.x, tid = threadIdx.x;
+    // the work items this pass may fill start out invalid
+    if (pass < geo.frame_passes && tid < geo.n_chunks) geo.descs[(size_t(pass) * geo.n_streams + stream) * geo.n_chunks + tid].valid = 0;
 
     float2* tw1 = reinterpret_cast<float2*>(smem_raw);
     float2* tw2 = tw1 + G::TW1_SIZE;
@@ -676,8 +723,6 @@ ofdm_control_kernel(ControlGeom geo, int pass) {
             st.frames_in_call = 0;
         }
     }
-    // the work items this pass may fill start out invalid
-    if (pass < geo.frame_passes && tid < geo.n_chunks) geo.descs[(size_t(pass) * geo.n_streams + stream) * geo.n_chunks + tid].valid = 0;
     __syncthreads();
     // nothing to do: no frame waiting for its fine update, no unread samples, the signal average of the call is folded
     if (!st.pipeline_pending && st.consumed >= st.call_end && !st.avg_pending) {

@@ -45,8 +45,8 @@ template <int SB>
 __device__ __forceinline__ float2 load_sample_ptr(const void* p, const SampleFmt& f) {
     if (SB == 2) return decode_sample<2>(uint32_t(__ldg(reinterpret_cast<const unsigned short*>(p))), f);
     if (SB == 4) return decode_sample<4>(__ldg(reinterpret_cast<const unsigned int*>(p)), f);
-    float2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    float2 v;   // read-only for the kernel's lifetime: not volatile, the compiler may batch independent loads
+    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
     return v;
 }
 

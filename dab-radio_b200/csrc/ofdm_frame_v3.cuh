@@ -21,6 +21,8 @@
 //   * 158 registers and 75 KB of shared memory per 128-thread CTA: three CTAs per SM, and the 4096 registers they leave are what
 //     ofdm_l1_windows_kernel (ofdm_control.cuh) runs in, concurrently, on a side stream.  Summing the UpdateSignalAverage windows
 //     here instead was built and measured: it costs more than it saves (profiles/r02_step_probes.md).
+//     The 512- and 256-point modes (4 / 8 transforms per CTA, symbols of 5 KB / 2.5 KB) keep the bulk copies too: 8-byte cp.async per
+//     thread with a third barrier per symbol was measured 30 % slower (profiles/r02_modes.md).
 //   * Quantisation with one MUFU.RCP (rcp.approx) instead of the IEEE reciprocal sequence + range-check branch; the GUI taps are
 //     a template parameter, so the hot variant carries none of their predicated-off instructions.
 //   * Raw integer IQ (u8 / s8 / u16 / s16) is dequantised on the way out of shared memory: the bulk copy moves

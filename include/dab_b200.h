@@ -384,6 +384,9 @@ DAB_API int dab_ensemble_read_msc(dab_ensemble* h, int stream, int cif, int sub_
                                   int32_t* n_bytes, uint64_t* path_error);
 DAB_API int dab_ensemble_sync(dab_ensemble* h);
 DAB_API uint64_t dab_ensemble_kernel_launches(const dab_ensemble* h);
+/* puncturing schedules currently held (the FIC's + one per distinct sub-channel profile / length in use: unused ones are
+ * garbage-collected by dab_ensemble_set_subchannels) */
+DAB_API int dab_ensemble_schedule_count(const dab_ensemble* h);
 /* trellises decoded / trellis steps run by the most recent decode call (host-side count from the sub-channel tables; upper
  * bound when d_frames_in_call masks streams) */
 DAB_API int dab_ensemble_last_work(const dab_ensemble* h, uint64_t* trellises, uint64_t* trellis_steps);

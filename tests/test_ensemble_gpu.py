@@ -183,3 +183,30 @@ def test_demod_to_bytes_on_device(ens, oracle, pkg):
     assert min(seen) >= n_frames - 2 and decoded_any > 0
     d.close()
     dec.close()
+
+
+def test_schedules_are_garbage_collected_across_reconfigurations(ens, oracle):
+    """repeated sub-channel reconfiguration must not grow the schedule tables without bound.  Every EEP-A profile /
+    length combination passes through one stream (539 distinct schedules); the table never holds more than the FIC's schedule and
+    the ones in use, and afterwards the decoder still matches the oracle on a fresh layout."""
+    dec = ens.EnsembleDecoder(1, n_streams=1, max_subchannels=8)
+    n = 0
+    for length in range(6, 866, 2):                      # EEP A needs a multiple of {12, 8, 6, 4}; the schedule differs per length
+        for level, type_b in ((0, 0), (1, 0), (2, 0), (3, 0)):
+            unit = (12, 8, 6, 4)[level]
+            if length % unit:
+                continue
+            dec.set_subchannels(0, [ens.subchannel(0, length, 0, 0, level, type_b)])
+            n += 1
+            assert dec.L.dab_ensemble_schedule_count(dec.h) == 2        # FIC + the one sub-channel
+    assert n > 500
+    layout = LAYOUTS[1]
+    subs_o = [oracle.subchannel(*a) for a in layout]
+    dec.set_subchannels(0, [ens.subchannel(*a) for a in layout])
+    tx = ensgen.EnsembleTx(1, subs_o, seed=91, sigma=50.0)
+    frames = np.stack([tx.next_frame() for _ in range(5)])
+    want = ensgen.oracle_decode_stream(1, subs_o, frames)
+    for f in range(5):
+        dec.decode_frames(frames[f])
+        _check_stream(dec, 0, want[f], len(layout), f"frame {f}")
+    dec.close()
