@@ -66,9 +66,6 @@ struct Ofdm {
     size_t frame_bits = 0;
     int syms_per_chunk = 26;            // DAB_B200_SYMS_PER_CHUNK: target symbols per frame-kernel work item
     int n_chunks = 3;                   // work items per frame
-    bool l1_side_kernel = true;         // DAB_B200_L1_SIDE=0: the control kernel sums every UpdateSignalAverage window itself
-    int l1_grid = 148 * 8;              // DAB_B200_L1_GRID: CTAs of the window kernel (grid-stride loop)
-    int l1_prio = 2;                    // DAB_B200_L1_PRIO: 0 lowest, 1 highest, 2 default stream priority (profiles/r02_step_probes.md)
     bool force_generic_kernel = false;  // DAB_B200_GENERIC_FRAME_KERNEL=1: run the generic-geometry frame kernel (tests)
     bool dab_geometry = false;          // the v3 kernel applies
     cudaStream_t own_stream = nullptr;
@@ -79,15 +76,11 @@ struct Ofdm {
     int ways = 4;
     int call_ways = 1;                  // ways of the most recent call (n_ways_for)
     uint64_t way_min_samples = uint64_t(1) << 24;   // DAB_B200_WAY_MIN_SAMPLES: samples per way and call below which ways are merged
-    uint64_t l1_side_min_block = 32768; // blocks shorter than this have too few windows for a kernel launch of their own
     cudaStream_t way_stream[MAX_WAYS] = {};
     cudaEvent_t way_done[MAX_WAYS] = {};
     cudaEvent_t counts_ready[MAX_WAYS] = {};
     cudaEvent_t bits_ready[MAX_WAYS] = {};
     cudaEvent_t up_done[MAX_WAYS] = {};
-    // UpdateSignalAverage's window kernel runs beside the frame kernel on a side stream per way (ofdm_control.cuh)
-    cudaStream_t l1_stream[MAX_WAYS] = {};
-    cudaEvent_t call_open[MAX_WAYS] = {}, l1_done[MAX_WAYS] = {};
     // host-buffer path: all uploads on one stream and all soft-bit downloads on another, each in way order, so that the PCIe
     // link serves the ways first-in first-out (copies queued on the way streams themselves share the link and all finish last)
     cudaStream_t up_stream = nullptr, down_stream = nullptr;
@@ -97,8 +90,7 @@ struct Ofdm {
     // device memory
     DeviceBuffer<unsigned char> ring_iq;
     DeviceBuffer<float2> null_ring, corr_explicit, prs_fft_ref_conj, prs_time_ref_conj, fft_tap, vec_tap, twiddles;
-    DeviceBuffer<float> impulse, freq_resp, phase_err, stage_phase_err, l1_windows;
-    int l1_windows_stride = 0;
+    DeviceBuffer<float> impulse, freq_resp, phase_err, stage_phase_err;
     DeviceBuffer<StreamState> states;
     DeviceBuffer<FrameDesc> descs, stage_descs;
     DeviceBuffer<dab_ofdm_frame_info> infos;
@@ -299,7 +291,6 @@ static ControlGeom control_geom(const Ofdm* o) {
     g.stream0 = 0;
     g.n_chunks = o->n_chunks;
     g.frame_passes = 0;
-    g.l1_ready = 0;
     g.frame_bits = o->frame_bits;
     if (o->ext_base) {
         g.mask = ~uint64_t(0);
@@ -326,8 +317,6 @@ static ControlGeom control_geom(const Ofdm* o) {
     g.bits = o->bits.ptr;
     g.phase_err = o->phase_err.ptr;
     g.twiddles = o->twiddles.ptr;
-    g.l1_windows = o->l1_windows.ptr;
-    g.l1_windows_stride = o->l1_windows_stride;
     g.fft_tap = o->debug_taps ? o->fft_tap.ptr : nullptr;
     g.vec_tap = o->debug_taps ? o->vec_tap.ptr : nullptr;
     g.n_per_stream = nullptr;
@@ -397,10 +386,9 @@ static WayRange way_range(const Ofdm* o, int w, int ways) {
 }
 
 // (control -> frame)* -> control  for the streams of one way, in order on the way's CUDA stream.  Control pass 0 opens the call
-// (OFDM_Demod::Process's entry); the frame kernel after pass p runs the work items pass p wrote.  UpdateSignalAverage's window
-// averages are summed by ofdm_l1_windows_kernel on the way's side stream between pass 0 and pass 1, i.e. while the frame kernel
-// runs; the stream's last pass folds them into the running average.
-static int issue_way_kernels(Ofdm* o, int w, const WayRange& r, bool uniform, uint64_t n_uniform, uint64_t n_max, int passes) {
+// (OFDM_Demod::Process's entry); the frame kernel after pass p runs the work items pass p wrote; the pass in which a stream
+// finishes its block folds the block's UpdateSignalAverage windows into the running average.
+static int issue_way_kernels(Ofdm* o, const WayRange& r, bool uniform, uint64_t n_uniform, int passes) {
     const int count = r.hi - r.lo;
     cudaStream_t st = r.st;
     ControlGeom g = control_geom(o);
@@ -415,36 +403,11 @@ static int issue_way_kernels(Ofdm* o, int w, const WayRange& r, bool uniform, ui
             rc = launch_control(o, st, g, count, p);
         }
         if (rc != DAB_OK) return rc;
-        if (p == 0 && passes > 0 && o->l1_side_kernel && n_max >= o->l1_side_min_block) {
-            // every slot of the window buffer that this call can reach under ANY config (the kernel skips windows past the call's
-            // end; fold_average sums the windows beyond the buffer itself)
-            const int max_windows = (n_max >= 1) ? o->l1_windows_stride : 0;
-            const int64_t tasks = int64_t(count) * ((max_windows + L1_WB - 1) / L1_WB);
-            const int grid = int(std::min<int64_t>((tasks + 1) / 2, o->l1_grid));
-            if (grid > 0) {
-                cudaStream_t side = o->l1_stream[w];
-                DAB_CUDA_CHECK(cudaEventRecord(o->call_open[w], st));
-                DAB_CUDA_CHECK(cudaStreamWaitEvent(side, o->call_open[w], 0));
-                {
-                    ScopedKernelTimer timer(o, side, DAB_OFDM_TIMING_PASSES - 1, false);
-                    switch (o->sb) {
-                    case 8: ofdm_l1_windows_kernel<8><<<grid, L1_CTA_THREADS, 0, side>>>(g, count, max_windows); break;
-                    case 2: ofdm_l1_windows_kernel<2><<<grid, L1_CTA_THREADS, 0, side>>>(g, count, max_windows); break;
-                    default: ofdm_l1_windows_kernel<4><<<grid, L1_CTA_THREADS, 0, side>>>(g, count, max_windows); break;
-                    }
-                    o->launches++;
-                    DAB_CUDA_CHECK(cudaGetLastError());
-                }
-                DAB_CUDA_CHECK(cudaEventRecord(o->l1_done[w], side));
-                g.l1_ready = 1;   // for the passes from here on, which wait for l1_done below
-            }
-        }
         if (p < passes) {
             ScopedKernelTimer timer(o, st, p, true);
             rc = launch_frame(o, st, g.descs + (size_t(p) * size_t(o->n_streams) + size_t(r.lo)) * size_t(o->n_chunks), count * o->n_chunks);
             if (rc != DAB_OK) return rc;
         }
-        if (p == 0 && g.l1_ready) DAB_CUDA_CHECK(cudaStreamWaitEvent(st, o->l1_done[w], 0));
     }
     return DAB_OK;
 }
@@ -539,7 +502,7 @@ static int run_call(Ofdm* o, bool uniform, uint64_t n_uniform, const void* const
                 DAB_CUDA_CHECK(cudaStreamWaitEvent(r.st, o->up_done[w], 0));
             }
         }
-        int rc = issue_way_kernels(o, w, r, uniform, n_uniform, n_max, passes);
+        int rc = issue_way_kernels(o, r, uniform, n_uniform, passes);
         if (rc != DAB_OK) return rc;
         const size_t cnt = size_t(r.hi - r.lo);
         if (o->cb) {
@@ -743,17 +706,12 @@ static int create_impl(Ofdm* o, const dab_c32* prs, const int* mapper) {
 
     DAB_CUDA_CHECK(cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking));
     o->stream = o->own_stream;
-    int prio_low = 0, prio_high = 0;
-    DAB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
     for (int w = 0; w < Ofdm::MAX_WAYS; w++) {
         DAB_CUDA_CHECK(cudaStreamCreateWithFlags(&o->way_stream[w], cudaStreamNonBlocking));
         DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->way_done[w], cudaEventDisableTiming));
         DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->counts_ready[w], cudaEventDisableTiming));
         DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->bits_ready[w], cudaEventDisableTiming));
         DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->up_done[w], cudaEventDisableTiming));
-        DAB_CUDA_CHECK(cudaStreamCreateWithPriority(&o->l1_stream[w], cudaStreamNonBlocking, o->l1_prio == 1 ? prio_high : (o->l1_prio == 0 ? prio_low : 0)));
-        DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->call_open[w], cudaEventDisableTiming));
-        DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->l1_done[w], cudaEventDisableTiming));
     }
     DAB_CUDA_CHECK(cudaStreamCreateWithFlags(&o->up_stream, cudaStreamNonBlocking));
     DAB_CUDA_CHECK(cudaStreamCreateWithFlags(&o->down_stream, cudaStreamNonBlocking));
@@ -780,8 +738,6 @@ static int create_impl(Ofdm* o, const dab_c32* prs, const int* mapper) {
     DAB_CUDA_CHECK(o->bin_to_pos.reserve(nfft));
     DAB_CUDA_CHECK(o->bin_to_carrier.reserve(nfft));
     DAB_CUDA_CHECK(o->d_n.reserve(ns));
-    o->l1_windows_stride = int(o->max_block / 500 + 2);
-    DAB_CUDA_CHECK(o->l1_windows.reserve(ns * size_t(o->l1_windows_stride)));
     {
         const int n_tw = int(nfft) + 16 * int(nfft / 256);  // TW1_SIZE + TW2_SIZE
         DAB_CUDA_CHECK(o->twiddles.reserve(size_t(n_tw)));
@@ -887,10 +843,7 @@ dab_ofdm* dab_ofdm_create(const dab_ofdm_params* params, const dab_c32* prs_fft_
     if (const char* e = getenv("DAB_B200_GENERIC_FRAME_KERNEL")) o->force_generic_kernel = (e[0] == '1');
     if (const char* e = getenv("DAB_B200_PIPELINE_WAYS")) { const int w = atoi(e); if (w >= 1 && w <= Ofdm::MAX_WAYS) o->ways = w; }
     if (const char* e = getenv("DAB_B200_SYMS_PER_CHUNK")) { const int c = atoi(e); if (c >= 1 && c <= 1024) o->syms_per_chunk = c; }
-    if (const char* e = getenv("DAB_B200_L1_SIDE")) o->l1_side_kernel = (e[0] != '0');
     if (const char* e = getenv("DAB_B200_WAY_MIN_SAMPLES")) { const long long v = atoll(e); if (v >= 0) o->way_min_samples = uint64_t(v); }
-    if (const char* e = getenv("DAB_B200_L1_GRID")) { const int g = atoi(e); if (g >= 1) o->l1_grid = g; }
-    if (const char* e = getenv("DAB_B200_L1_PRIO")) o->l1_prio = atoi(e);
     rc = create_impl(o, prs_fft_ref, carrier_mapper);
     if (rc != DAB_OK) { delete o; return fail(rc); }
     if (status) *status = DAB_OK;
@@ -911,9 +864,6 @@ void dab_ofdm_destroy(dab_ofdm* h) {
         if (o->counts_ready[w]) cudaEventDestroy(o->counts_ready[w]);
         if (o->bits_ready[w]) cudaEventDestroy(o->bits_ready[w]);
         if (o->up_done[w]) cudaEventDestroy(o->up_done[w]);
-        if (o->l1_stream[w]) { cudaStreamSynchronize(o->l1_stream[w]); cudaStreamDestroy(o->l1_stream[w]); }
-        if (o->call_open[w]) cudaEventDestroy(o->call_open[w]);
-        if (o->l1_done[w]) cudaEventDestroy(o->l1_done[w]);
     }
     if (o->up_stream) { cudaStreamSynchronize(o->up_stream); cudaStreamDestroy(o->up_stream); }
     if (o->down_stream) { cudaStreamSynchronize(o->down_stream); cudaStreamDestroy(o->down_stream); }
@@ -967,16 +917,6 @@ int dab_ofdm_set_config(dab_ofdm* h, int stream, const dab_ofdm_config* cfg) {
     DAB_CUDA_CHECK(cudaMemcpy2DAsync(reinterpret_cast<char*>(o->states.ptr + lo) + offsetof(StreamState, cfg), sizeof(StreamState), &o->cfgs[size_t(lo)],
                                      sizeof(dab_ofdm_config), sizeof(dab_ofdm_config), size_t(hi - lo), cudaMemcpyHostToDevice, o->stream));
     DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
-    // the window buffer the frame kernel writes UpdateSignalAverage's window averages to must hold a whole call under this
-    // configuration too, otherwise the control kernel sums every window itself
-    if (cfg->signal_l1_nb_samples > 0 && cfg->signal_l1_nb_decimate > 0) {
-        const size_t step = size_t(cfg->signal_l1_nb_samples) * size_t(cfg->signal_l1_nb_decimate);
-        const size_t need = std::min<size_t>(o->max_block / step + 2, size_t(1) << 20);
-        if (need > size_t(o->l1_windows_stride)) {
-            DAB_CUDA_CHECK(o->l1_windows.reserve(size_t(o->n_streams) * need));
-            o->l1_windows_stride = int(need);
-        }
-    }
     return DAB_OK;
 }
 

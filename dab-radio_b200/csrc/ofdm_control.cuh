@@ -10,10 +10,11 @@
 // frame kernel's per-symbol phase errors into the fine frequency offset, then continues with the remaining samples.
 //
 // UpdateSignalAverage (ofdm_demodulator.cpp:934-950) runs first in the reference's Process(); here its value is only needed when a
-// stream searches for the NULL symbol or when the call is over, so it is folded lazily: the window averages of every stream are
-// computed by ofdm_l1_windows_kernel on a side stream WHILE the frame kernel runs (it is DRAM-latency bound and fits into the
-// registers the frame kernel leaves free on every SM), and the last control pass of the call folds them into the running average
-// in window order.  A stream that needs the average earlier (FindNullPowerDip) sums its windows itself.
+// stream searches for the NULL symbol or when the call is over, so it is folded lazily: the pass in which a stream finishes its
+// block sums the block's window averages and folds them into the running average in window order (a searching stream does it the
+// moment FindNullPowerDip needs the thresholds).  Two other homes for the window sums were built and measured -- inside the frame
+// kernel while the samples sit in shared memory, and a kernel of their own on a side stream beside the frame kernel -- and dropped:
+// profiles/r02_step_probes.md.
 #pragma once
 #include "ofdm_device.cuh"
 #include "ofdm_frame.cuh"
@@ -63,7 +64,6 @@ struct ControlGeom {
     int stream0;             // first stream this launch covers (launches are split into pipeline ways, see run_call)
     int n_chunks;            // work items per frame (<= FRAME_MAX_CHUNKS)
     int frame_passes;        // control passes of this call that are followed by a frame-kernel launch
-    int l1_ready;            // 1: l1_windows holds the window averages of this call (ofdm_l1_windows_kernel has completed)
     size_t frame_bits;
     uint64_t mask;           // stream index mask (ring size - 1 or ~0)
     uint64_t limit;          // samples addressable per stream (ring size, or the attached buffer's length)
@@ -83,8 +83,6 @@ struct ControlGeom {
     int8_t* bits;            // [n_streams][slots][frame_bits]
     float* phase_err;        // [n_streams][n_symbols]
     const float2* twiddles;  // precomputed FFT twiddles (fft_twiddle_init_kernel)
-    float* l1_windows;       // [n_streams][l1_windows_stride] window averages of the current call (ofdm_l1_windows_kernel)
-    int l1_windows_stride;
     float2* fft_tap;         // optional [n_streams][n_symbols * NFFT]
     float2* vec_tap;         // optional [n_streams][(n_symbols-1) * n_carriers]
     const uint64_t* n_per_stream;  // samples of this call per stream, nullptr: n_uniform
@@ -207,10 +205,8 @@ struct Control {
         }
     }
 
-    // ---- UpdateSignalAverage (ofdm_demodulator.cpp:934-950) of the current call, folded into l1_average in window order.  The
-    // window averages come from ofdm_l1_windows_kernel when it has completed (geo.l1_ready: the passes after the first frame
-    // launch) and are summed here otherwise.  Runs once per call: in the stream's last pass, or the moment FindNullPowerDip needs
-    // the average.
+    // ---- UpdateSignalAverage (ofdm_demodulator.cpp:934-950) of the current call, folded into l1_average in window order.  Runs
+    // once per call: in the pass in which the stream finishes its block, or the moment FindNullPowerDip needs the average.
     __device__ void fold_average() {
         const int64_t N = st.call_end - st.call_begin;
         const int K = st.cfg.signal_l1_nb_samples;
@@ -218,14 +214,9 @@ struct Control {
             const int64_t M = N - K;
             const int L = K * st.cfg.signal_l1_nb_decimate;
             const int64_t n_windows = (L > 0) ? (M + L - 1) / L : 0;
-            const float* win = geo.l1_windows + size_t(stream) * geo.l1_windows_stride;
             for (int64_t w0 = 0; w0 < n_windows; w0 += CTRL_L1_BATCH) {
                 const int count = int(min(int64_t(CTRL_L1_BATCH), n_windows - w0));
-                if (geo.l1_ready && w0 + count <= geo.l1_windows_stride) {
-                    for (int w = tid; w < count; w += THREADS) l1buf[w] = win[w0 + w];
-                } else {
-                    l1_windows(l1buf, st.call_begin + w0 * L, L, K, count);
-                }
+                l1_windows(l1buf, st.call_begin + w0 * L, L, K, count);
                 __syncthreads();
                 if (tid == 0) {
                     const float beta = st.cfg.signal_l1_update_beta;
@@ -612,84 +603,6 @@ struct Control {
     }
 };
 
-// CalculateL1Average (ofdm_demodulator.cpp:922-932) for every window UpdateSignalAverage (:934-950) visits in the current call:
-// window w of stream s covers samples [call_begin + w L, + K).  One warp per group of L1_WB windows, every load of the group
-// issued before the first use (the access pattern -- 800 bytes out of every 4000 -- is DRAM-latency bound).  64-thread CTAs with
-// at most 64 registers per thread and no shared memory: they fit into what three frame-kernel CTAs leave free on an SM, so the
-// kernel runs beside the frame kernel (launched on a side stream after control pass 0 has set call_begin / call_end) instead
-// of in front of it.  Lane-strided partial sums, then the butterfly: the same order as Control::l1_windows.
-constexpr int L1_WB = 4;
-constexpr int L1_CTA_THREADS = 64;
-template <int SB>
-__global__ void __launch_bounds__(L1_CTA_THREADS, 16) ofdm_l1_windows_kernel(ControlGeom geo, int n_streams, int max_windows) {
-    const int lane = threadIdx.x & 31;
-    const int warps_per_block = blockDim.x >> 5;
-    // short windows (K <= 32, checked per stream): one window per thread, streams in turn
-    for (int s = blockIdx.x; s < n_streams; s += gridDim.x) {
-        const int stream = geo.stream0 + s;
-        const StreamState* st = geo.states + stream;
-        const int K = st->cfg.signal_l1_nb_samples;
-        const int L = K * st->cfg.signal_l1_nb_decimate;
-        const int64_t N = st->call_end - st->call_begin;
-        if (K <= 0 || K > 32 || L <= 0 || N < K || !st->avg_pending) continue;
-        const int64_t n_windows = min(int64_t(max_windows), (N - K + L - 1) / L);
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(geo.samples) + size_t(stream) * geo.stream_stride * SB;
-        for (int64_t w = threadIdx.x; w < n_windows; w += blockDim.x)
-            geo.l1_windows[size_t(stream) * geo.l1_windows_stride + w] = l1_short_window<SB>(src, uint64_t(st->call_begin + w * L), geo.mask, K, geo.fmt);
-    }
-    const int groups = (max_windows + L1_WB - 1) / L1_WB;
-    const int total = n_streams * groups;
-    for (int task = blockIdx.x * warps_per_block + (threadIdx.x >> 5); task < total; task += gridDim.x * warps_per_block) {
-        const int stream = geo.stream0 + task / groups, w0 = (task % groups) * L1_WB;
-        const StreamState* st = geo.states + stream;
-        const int K = st->cfg.signal_l1_nb_samples;
-        const int L = K * st->cfg.signal_l1_nb_decimate;
-        const int64_t call_begin = st->call_begin;
-        const int64_t N = st->call_end - call_begin;
-        if (K <= 32 || L <= 0 || N < K || !st->avg_pending) continue;
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(geo.samples) + size_t(stream) * geo.stream_stride * SB;
-        // window b: samples [first, first + K) of the stream; `flat` when it does not wrap around the ring
-        bool live[L1_WB], flat[L1_WB];
-        uint64_t first[L1_WB];
-        float acc[L1_WB];
-#pragma unroll
-        for (int b = 0; b < L1_WB; b++) {
-            live[b] = (w0 + b < max_windows) && (int64_t(w0 + b) * L < N - K);  // loop condition i < M of the reference
-            first[b] = uint64_t(call_begin + int64_t(w0 + b) * L) & geo.mask;
-            flat[b] = (geo.mask == ~uint64_t(0)) || (first[b] + uint64_t(K) <= geo.mask + 1);
-            acc[b] = 0.0f;
-        }
-        for (int i0 = 0; i0 < K; i0 += 128) {
-            float2 v[L1_WB][4];
-#pragma unroll
-            for (int b = 0; b < L1_WB; b++) {
-                const unsigned char* p = src + first[b] * SB;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int i = i0 + lane + 32 * q;
-                    v[b][q] = make_float2(0.0f, 0.0f);
-                    if (live[b] && i < K) {
-                        if (flat[b]) v[b][q] = load_sample_ptr<SB>(p + i * SB, geo.fmt);
-                        else v[b][q] = load_sample<SB>(src, (first[b] + uint64_t(i)) & geo.mask, geo.fmt);
-                    }
-                }
-            }
-#pragma unroll
-            for (int b = 0; b < L1_WB; b++)
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (i0 + lane + 32 * q < K) acc[b] += fabsf(v[b][q].x) + fabsf(v[b][q].y);
-        }
-#pragma unroll
-        for (int b = 0; b < L1_WB; b++) {
-            float a = acc[b];
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, d);
-            if (lane == 0 && live[b]) geo.l1_windows[size_t(stream) * geo.l1_windows_stride + w0 + b] = a / float(K);
-        }
-    }
-}
-
 // pass: index of this control pass within the call (0 = first; it also opens the call: OFDM_Demod::Process's entry,
 // ofdm_demodulator.cpp:235-243).  Passes below geo.frame_passes are followed by a frame-kernel launch over the items they wrote.
 template <int NFFT, int SB>
@@ -783,9 +696,8 @@ ofdm_control_kernel(ControlGeom geo, int pass) {
         }
     }
     __syncthreads();
-    // the call is over for this stream: fold UpdateSignalAverage -- once the window kernel's results are there (from pass 1 on;
-    // a call always has a pass 1), or by summing the windows here if the call has no further pass
-    if (st.avg_pending && st.consumed >= st.call_end && !st.pipeline_pending && (geo.l1_ready || pass >= geo.frame_passes)) ctl.fold_average();
+    // the call is over for this stream: fold UpdateSignalAverage
+    if (st.avg_pending && st.consumed >= st.call_end && !st.pipeline_pending) ctl.fold_average();
     if (tid == 0) {
         geo.states[stream] = st;
         geo.frames_in_call[stream] = st.frames_in_call;

@@ -183,20 +183,31 @@ __device__ __forceinline__ void fft_pass2(float2 (&v)[16], int t, const float2* 
     }
 }
 
-// fft_pass2 with the twiddle loads issued one batch of four ahead of the exchange-2 stores (see ofdm_frame_v3.cuh, pass 1)
+// Exchange 1 without padding (ofdm_frame_v3.cuh): element (k1, col) lives at k1 * T + (col ^ e1_swizzle(k1)).  The pass-1 store of a
+// row is a permutation of consecutive columns; the pass-2 load of 16 lanes covers 16 / R3 consecutive rows at the columns
+// n2 R3 + n3: the row-dependent xor above the n3 bits sends them to 16 different 8-byte banks.
 template <int NFFT>
-__device__ __forceinline__ void fft_pass2_pipelined(float2 (&v)[16], int t, const float2* e1, float2* e2, const float2* tw2) {
+__device__ __forceinline__ int e1_swizzle(int k1) {
+    using G = FftGeom<NFFT>;
+    return (k1 & (16 / G::R3 - 1)) * G::R3;
+}
+
+// fft_pass2 over the swizzled exchange 1, with the twiddle loads (global memory, L1-resident: 16 R3 values per CTA) issued one batch
+// of four ahead of the exchange-2 stores (see ofdm_frame_v3.cuh, pass 1)
+template <int NFFT>
+__device__ __forceinline__ void fft_pass2_pipelined(float2 (&v)[16], int t, const float2* e1, float2* e2, const float2* __restrict__ tw2) {
     using G = FftGeom<NFFT>;
     const int k1p = t / G::R3, n3p = t % G::R3;
+    const int sw = e1_swizzle<NFFT>(k1p);
 #pragma unroll
-    for (int n2 = 0; n2 < 16; n2++) v[n2] = e1[k1p * G::E1_STRIDE + n2 * G::R3 + n3p];
+    for (int n2 = 0; n2 < 16; n2++) v[n2] = e1[k1p * G::T + ((n2 * G::R3 + n3p) ^ sw)];
     if (G::R3 == 1) {
         dft16(v);
         return;
     }
     float2 wn[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) wn[q] = tw2[q * G::R3 + n3p];
+    for (int q = 0; q < 4; q++) wn[q] = __ldg(tw2 + q * G::R3 + n3p);
     dft16(v);
 #pragma unroll
     for (int b = 0; b < 4; b++) {
@@ -205,7 +216,7 @@ __device__ __forceinline__ void fft_pass2_pipelined(float2 (&v)[16], int t, cons
         for (int q = 0; q < 4; q++) wc[q] = wn[q];
         if (b < 3) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) wn[q] = tw2[(4 * (b + 1) + q) * G::R3 + n3p];
+            for (int q = 0; q < 4; q++) wn[q] = __ldg(tw2 + (4 * (b + 1) + q) * G::R3 + n3p);
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) {

@@ -69,16 +69,23 @@ __device__ __forceinline__ float rcp_approx(float a) {
 }
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(uint16_t(v)) : "memory"); }
 
+// DAB_V3_TW1_REGS (default 1): the inter-pass twiddles W_N^{t k1} B_t = (B_t W^{t b}) (W^{t 4a}), k1 = 4a + b, live in seven
+// registers per thread (four Q_b, three R_a) instead of a 16 x T shared-memory table: 16 fewer LDS.64 per thread and symbol (the
+// kernel's busiest unit is l1tex) for 12 more complex multiplies, and 16 KB less shared memory per transform.
+#ifndef DAB_V3_TW1_REGS
+#define DAB_V3_TW1_REGS 1
+#endif
+
 template <int NFFT, int SB>
 struct FrameV3Smem {
     using G = FftGeom<NFFT>;
     using D = DabGeom<NFFT>;
     static constexpr int GROUPS = FRAME_CTA_THREADS / G::T;
     static constexpr size_t r16(size_t x) { return (x + 15) & ~size_t(15); }
-    static constexpr size_t TW2_BYTES = r16(size_t(G::TW2_SIZE) * sizeof(float2));
+    static constexpr size_t TW2_BYTES = 0;   // the last-pass twiddles are read from global memory (16 R3 values, L1-resident)
     static constexpr size_t OFF_TW1 = 0;
-    static constexpr size_t OFF_E1 = OFF_TW1 + size_t(G::TW1_SIZE) * sizeof(float2);
-    static constexpr size_t OFF_E2 = OFF_E1 + size_t(G::E1_SIZE) * sizeof(float2);
+    static constexpr size_t OFF_E1 = OFF_TW1 + (DAB_V3_TW1_REGS ? 0 : size_t(G::TW1_SIZE) * sizeof(float2));
+    static constexpr size_t OFF_E2 = OFF_E1 + size_t(NFFT) * sizeof(float2);   // exchange 1 swizzled instead of padded (e1_swizzle)
     static constexpr size_t OFF_STAGE = OFF_E2 + size_t(G::E2_SIZE) * sizeof(float2);
     static constexpr size_t OFF_IN = OFF_STAGE + r16((size_t(D::NCARR) + 8) * 2);
     static constexpr size_t IN_BYTES = r16(size_t(D::SP) * SB + 15);   // symbol + worst-case misalignment of its first byte
@@ -111,7 +118,7 @@ struct SlotInfo {
 };
 
 template <int NFFT, int SB, bool TAPS>
-__global__ void __launch_bounds__(FRAME_CTA_THREADS, 3)
+__global__ void __launch_bounds__(FRAME_CTA_THREADS, 4)
 ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_items) {
     using G = FftGeom<NFFT>;
     using D = DabGeom<NFFT>;
@@ -128,7 +135,7 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_i
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int n_loop_s;
-    float2* tw2 = reinterpret_cast<float2*>(smem_raw);
+    const float2* __restrict__ tw2 = geo.twiddles + G::TW1_SIZE;
     const int group = threadIdx.x / T, t = threadIdx.x % T;
     unsigned char* gbase = smem_raw + SM::TW2_BYTES + size_t(group) * SM::GROUP_BYTES;
     float2* tw1 = reinterpret_cast<float2*>(gbase + SM::OFF_TW1);
@@ -201,18 +208,26 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_i
         dtab[j] = make_float2(cs, sn);
     };
 
+    float2 tw_q[4], tw_r[3];   // DAB_V3_TW1_REGS: the inter-pass twiddles of this thread
+    (void)tw_q; (void)tw_r; (void)tw1;
     // ---- per work item setup; the first symbol is requested before the tables are built so that its latency hides behind them
     if (t == 0) mbar_init(mbar, 1);
     if (active) fetch(s_load0);
-    for (int i = threadIdx.x; i < G::TW2_SIZE; i += FRAME_CTA_THREADS) tw2[i] = __ldg(geo.twiddles + G::TW1_SIZE + i);
     {
         float ph = f * float(t);
         ph -= rintf(ph);
         float sn, cs;
         sincospif(2.0f * ph, &sn, &cs);
         const float2 b = make_float2(cs, sn);
+#if DAB_V3_TW1_REGS
+#pragma unroll
+        for (int q = 0; q < 4; q++) tw_q[q] = cmul(__ldg(geo.twiddles + q * T + t), b);          // B_t W_N^{t q}
+#pragma unroll
+        for (int a = 1; a < 4; a++) tw_r[a - 1] = __ldg(geo.twiddles + (4 * a) * T + t);          // W_N^{t 4a}
+#else
 #pragma unroll
         for (int k1 = 0; k1 < 16; k1++) tw1[k1 * T + t] = cmul(__ldg(geo.twiddles + k1 * T + t), b);
+#endif
     }
     float2 cp_rot = make_float2(1.0f, 0.0f);  // exp(j 2 pi f N): what the PLL adds to x[N + n] conj(x[n])
     if (t == PE_T) {
@@ -297,9 +312,21 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_i
         corr = group_reduce_sum<RED_WIDTH>(corr);
         if (WARPS_PER_GROUP > 1 && (t & 31) == 0) red[t >> 5] = corr;
 
-        // pass 1: DFT16 over n1, twiddle W_N^{t k1} B_t, scatter A[k1][t].  The twiddle loads are issued a batch of four ahead of
-        // the stores that consume the previous batch: the compiler cannot move a shared-memory load above a shared-memory store
-        // by itself, and a load placed right before its use costs the full LDS latency sixteen times over.
+        // pass 1: DFT16 over n1, twiddle W_N^{t k1} B_t, scatter A[k1][t]
+#if DAB_V3_TW1_REGS
+        dft16(v);
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float2 x = (a == 0) ? v[q] : cmul(v[4 * a + q], tw_r[a - 1]);
+                e1[(4 * a + q) * T + (t ^ e1_swizzle<NFFT>(4 * a + q))] = cmul(x, tw_q[q]);
+            }
+        }
+#else
+        // The twiddle loads are issued a batch of four ahead of the stores that consume the previous batch: the compiler cannot move
+        // a shared-memory load above a shared-memory store by itself, and a load placed right before its use costs the full LDS
+        // latency sixteen times over.
         {
             float2 wn[4];
 #pragma unroll
@@ -315,9 +342,10 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_i
                     for (int q = 0; q < 4; q++) wn[q] = tw1[(4 * (b + 1) + q) * T + t];
                 }
 #pragma unroll
-                for (int q = 0; q < 4; q++) e1[(4 * b + q) * G::E1_STRIDE + t] = cmul(v[4 * b + q], wc[q]);
+                for (int q = 0; q < 4; q++) e1[(4 * b + q) * T + (t ^ e1_swizzle<NFFT>(4 * b + q))] = cmul(v[4 * b + q], wc[q]);
             }
         }
+#endif
         __syncthreads();  // ---- barrier A: every thread has consumed the input buffer and the D table
 
         const bool has_next = active && (s + 1 < desc.s_end);
