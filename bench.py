@@ -513,10 +513,48 @@ def run_ours(args):
         del host
         return out
 
+    def pcie_ceiling(bytes_per_sample):
+        """What the host link gives a bare pinned copy of the same size IN THIS RUN (every rank copying at once, as in the e2e leg):
+        one step's H2D block and one step's D2H soft bits on two CUDA streams, K times.  The e2e leg cannot be faster than this."""
+        h_in = torch.empty(n_streams * FRAME_LEN * bytes_per_sample, dtype=torch.uint8).pin_memory()
+        d_in = torch.empty_like(h_in, device="cuda")
+        d_out = torch.empty(n_streams * FRAME_BITS, dtype=torch.int8, device="cuda")
+        h_out = torch.empty(n_streams * FRAME_BITS, dtype=torch.int8).pin_memory()
+        s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+        def once():
+            with torch.cuda.stream(s_up):
+                d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s_down):
+                h_out.copy_(d_out, non_blocking=True)
+        for _ in range(2):
+            once()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            once()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        dt_max = aggregate(dt * 1e3, 0, world, dist)[0] * 1e-3
+        return {"ms_per_step": round(dt_max / K * 1e3, 3), "h2d_gbs_per_gpu": round(h_in.numel() * K / dt_max / 1e9, 1),
+                "d2h_gbs_per_gpu": round(h_out.numel() * K / dt_max / 1e9, 1),
+                "note": "bare pinned cudaMemcpyAsync of one step's input and output, both directions at once, all ranks at once, max over ranks"}
+
     e2e = None
     if not args.no_e2e:
         e2e = e2e_leg(False)
+        try:
+            ceil = pcie_ceiling(8)
+            ceil["e2e_fraction_of_ceiling"] = round(ceil["ms_per_step"] / e2e["ms_per_step"], 3)
+            e2e["pcie_ceiling"] = ceil
+        except Exception as ex:  # noqa: BLE001
+            e2e["pcie_ceiling"] = {"unavailable": repr(ex)}
         e2e["raw_u8_ingest"] = e2e_leg(True)   # SURVEY 8(f) rank 1: raw 8-bit IQ uploaded and dequantised on the device
+        try:
+            ceil = pcie_ceiling(2)
+            ceil["e2e_fraction_of_ceiling"] = round(ceil["ms_per_step"] / e2e["raw_u8_ingest"]["ms_per_step"], 3)
+            e2e["raw_u8_ingest"]["pcie_ceiling"] = ceil
+        except Exception as ex:  # noqa: BLE001
+            e2e["raw_u8_ingest"]["pcie_ceiling"] = {"unavailable": repr(ex)}
         try:   # SURVEY 8(f) ranks 1-3 chained: IQ in, FIBs + sub-channel bytes out (a secondary line must not take the headline down)
             e2e["raw_u8_to_decoded_bytes"] = full_chain_leg()
         except Exception as ex:  # noqa: BLE001
