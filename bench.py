@@ -141,7 +141,7 @@ def shard_streams(n_global, rank, world):
     return range(rank, n_global, world)
 
 
-def build_streams_on_device(torch, n_streams, n_frames, seed, mode=None, frame_len=None, period=None):
+def build_streams_on_device(torch, n_streams, n_frames, seed, mode=None, frame_len=None, period=None, stream_ids=None):
     """Synthetic Mode I streams in HBM: [n_streams, n_frames * FRAME_LEN] complex64.  With `period` the frame sequence of every
     stream repeats after `period` frames, so the buffer can be used as a ring (dab_ofdm_rebase_device_streams): the signal at
     sample i + period * FRAME_LEN continues the one at sample i (same frames, continuous CFO phase; the noise differs).
@@ -164,11 +164,19 @@ def build_streams_on_device(torch, n_streams, n_frames, seed, mode=None, frame_l
     total = n_frames * frame_len
     out = torch.empty((n_streams, total), dtype=torch.complex64, device="cuda")
     g = torch.Generator(device="cuda")
-    g.manual_seed(seed)
-    starts = rng.integers(0, frame_len, n_streams)
+    g.manual_seed(seed if stream_ids is None else seed + 7919 * int(stream_ids[0]))
     max_bin = 4800 * frame_len // FRAME_LEN                   # x Fs/frame_len: +-50 kHz in every mode (10.4 Hz steps in Mode I)
-    cfo_bins = rng.integers(-max_bin, max_bin + 1, n_streams)
-    choice = rng.integers(0, POOL_FRAMES, (n_streams, n_frames + 1))
+    if stream_ids is None:
+        starts = rng.integers(0, frame_len, n_streams)
+        cfo_bins = rng.integers(-max_bin, max_bin + 1, n_streams)
+        choice = rng.integers(0, POOL_FRAMES, (n_streams, n_frames + 1))
+    else:
+        # what a stream looks like depends on its GLOBAL id only (shard_streams: stream i lives on rank i mod N): the same job on
+        # 1, 2, 4 or 8 GPUs demodulates the same streams
+        per = [np.random.default_rng([seed, int(g)]) for g in stream_ids]
+        starts = np.array([r.integers(0, frame_len) for r in per])
+        cfo_bins = np.array([r.integers(-max_bin, max_bin + 1) for r in per])
+        choice = np.stack([r.integers(0, POOL_FRAMES, n_frames + 1) for r in per])
     if period:
         choice = choice[:, np.arange(n_frames + 1) % period]
     chunk = 16
@@ -280,7 +288,8 @@ def run_ours(args):
     # (a stream that is still searching runs FindNullPowerDip over whole blocks), then come the W warm-up and the K timed steps.
     # The streams live in a ring of RING_PERIOD + 3 frames per stream whose content repeats every RING_PERIOD frames, so a run
     # can be as long as wanted (the sustained leg) in 17.7 GB of HBM.
-    iq, gen = build_streams_on_device(torch, n_streams, RING_PERIOD + 3, seed=1234 + rank, period=RING_PERIOD)
+    my_streams = shard_streams(world * n_streams, rank, world)      # global stream ids of this rank: i -> rank i mod N
+    iq, gen = build_streams_on_device(torch, n_streams, RING_PERIOD + 3, seed=1234, period=RING_PERIOD, stream_ids=my_streams)
     torch.cuda.synchronize()
 
     def barrier():
@@ -568,8 +577,14 @@ def run_ours(args):
     # ------------------------------------------------------------------ Viterbi (secondary line; rank 0, N = 1 only)
     viterbi = None
     modes = None
+    impaired = None
     if rank == 0 and world == 1 and not args.no_viterbi:
         del iq
+        torch.cuda.empty_cache()
+        try:
+            impaired = impairments_leg(torch, ofdm, n_streams, 10, local_rank)
+        except Exception as ex:  # noqa: BLE001
+            impaired = {"unavailable": repr(ex)}
         torch.cuda.empty_cache()
         viterbi = viterbi_leg(torch, pkg, n_streams, 5, not args.no_cpu)
         try:
@@ -600,7 +615,7 @@ def run_ours(args):
             "realtime_streams": round(value * 1e6 / FS, 1), "realtime_streams_per_gpu": round(value * 1e6 / FS / world, 1),
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "viterbi": viterbi, "modes": modes,
             "frames_per_stream_in_timed_region": frames_per_stream, "locked_streams": locked, "locked_fraction": round(locked / max(1, len(states)), 4),
-            "parity": parity, "sustained": sustained, "single_stream": single,
+            "parity": parity, "sustained": sustained, "single_stream": single, "impairments": impaired,
         }
         emit(line)
     if world > 1:
@@ -631,6 +646,53 @@ def single_stream_leg(ofdm, iq, device):
     out = {"value": round(samples / dt / 1e6, 2), "unit": "MSamples/s", "realtime_factor": round(samples / dt / FS, 1), "block_samples": block,
            "ms_per_call": round(dt / (reps * n_blocks) * 1e3, 3), "frames_delivered": int(counter.frames) - f0, "seconds": round(dt, 2),
            "api": "dab_ofdm_process, one stream per handle (the OFDM_Demod mirror class's path), pageable host blocks, callback per frame"}
+    d.close()
+    return out
+
+
+def impairments_leg(torch, ofdm, n_streams, steps, device):
+    """BASELINE.json configs[2] as a throughput line: the headline workload under a three-tap multipath channel (delays up to half the
+    cyclic prefix, -3 / -9 dB), +-50 kHz CFO and 12 dB SNR.  Two streams are replayed through the oracle (parity under impairments
+    is what tests/test_ofdm_gpu.py::test_impairments_match_oracle covers case by case, incl. sample-rate drift)."""
+    iq, _ = build_streams_on_device(torch, n_streams, RING_PERIOD + 3, seed=77, period=RING_PERIOD)
+    # multipath: y[n] = x[n] + g1 x[n - d1] + g2 x[n - d2] (circular over the periodic ring content, so the ring stays periodic)
+    per = RING_PERIOD * FRAME_LEN
+    base = iq[:, :per]
+    y = base.clone()
+    for delay, gain_db, phase in ((100, -3.0, 2.0), (230, -9.0, -1.0)):
+        g = 10.0 ** (gain_db / 20.0) * np.exp(1j * phase)
+        y += torch.roll(base, delay, dims=1) * complex(g)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    sigma = float(torch.sqrt(torch.mean(torch.abs(y[:8]) ** 2)).item()) * 10 ** (-12.0 / 20) / np.sqrt(2.0)
+    y += torch.view_as_complex(torch.randn((n_streams, per, 2), device="cuda", generator=gen) * sigma)
+    iq[:, :per] = y
+    iq[:, per:] = y[:, :iq.shape[1] - per]
+    del y, base
+    d = ofdm.OfdmDemodBatch(MODE, n_streams=n_streams, device=device, max_block_samples=FRAME_LEN)
+    d.disable_callback()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        d.set_cuda_stream(st.cuda_stream)
+        ring = ResidentRing(d, iq, FRAME_LEN, RING_PERIOD)
+        for _ in range(LOCK_FRAMES + 3):
+            ring.step()
+        d.join()
+        st.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            ring.step()
+        d.join()
+        e1.record()
+        st.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    locked = sum(1 for s in range(n_streams) if d.state(s)["state"] != 0)
+    desync = sum(d.state(s)["total_frames_desync"] for s in range(0, n_streams, max(1, n_streams // 64)))
+    checked = check_streams_against_oracle(d, ring, MODE, [1, n_streams // 2 + 1], FRAME_LEN)
+    out = {"value": round(n_streams * FRAME_LEN / ms / 1e3, 1), "unit": "MSamples/s", "ms_per_step": round(ms, 4), "streams": n_streams,
+           "channel": "3 taps (0 / 100 / 230 samples, 0 / -3 / -9 dB), +-50 kHz CFO, 12 dB SNR", "locked_fraction": round(locked / n_streams, 4),
+           "desyncs_in_64_sampled_streams": int(desync), "streams_checked_against_oracle": checked}
     d.close()
     return out
 
