@@ -208,15 +208,16 @@ class ResidentRing:
     wanted: once the cursor is period + 2 frames into the buffer the origin moves forward by `period` frames
     (dab_ofdm_rebase_device_streams) and the demodulator continues in the same buffer, on the same signal."""
 
-    def __init__(self, d, iq, frame_len, period):
-        self.d, self.iq, self.fl, self.period = d, iq, frame_len, period
+    def __init__(self, d, iq, frame_len, period, raw_u8=False):
+        self.d, self.iq, self.fl, self.period, self.raw_u8 = d, iq, frame_len, period, raw_u8
+        self.total = iq.shape[1] // 2 if raw_u8 else iq.shape[1]      # samples per row
         self.pos = 0            # samples advanced since the origin
         self.fed = []           # (first sample, count) of every call so far, in buffer coordinates: the oracle replays them
-        d.attach_device_streams(iq.data_ptr(), iq.shape[1], iq.shape[1])
+        d.attach_device_streams(iq.data_ptr(), self.total, self.total)
 
     def step(self, n=None):
         n = self.fl if n is None else n
-        if self.pos + n > self.iq.shape[1]:   # the buffer holds period + 2 frames + one block: at least two frames stay behind the cursor
+        if self.pos + n > self.total:   # the buffer holds period + 2 frames + one block: at least two frames stay behind the cursor
             self.d.rebase_device_streams(self.period * self.fl)
             self.pos -= self.period * self.fl
         self.d.advance_uniform(n)
@@ -226,6 +227,8 @@ class ResidentRing:
     def replay(self, stream):
         """the samples stream `stream` has been fed so far, as one host array"""
         row = self.iq[stream].cpu().numpy()
+        if self.raw_u8:   # what the reference's raw_u8 reader hands to OFDM_Demod (app_iq_readers.h:36-43, 76-88)
+            row = ((row.astype(np.float32) - np.float32(127.5)) * np.float32(1.0 / 127.5)).view(np.complex64)
         return np.concatenate([row[a:a + n] for a, n in self.fed])
 
 
@@ -422,6 +425,37 @@ def run_ours(args):
     d.close()
     del d
 
+    # ------------------------------------------------------------------ the same resident workload as raw 8-bit IQ (what an RTL-SDR style
+    # front end delivers and the reference's apps read by default: examples/app_helpers/app_iq_readers.h raw_u8), dequantised in the kernels
+    resident_u8 = None
+    try:
+        iq8 = torch.clamp(torch.view_as_real(iq) * (127.5 * 16.0) + 127.5, 0.0, 255.0).to(torch.uint8).reshape(n_streams, -1).contiguous()
+        d = ofdm.OfdmDemodBatch(MODE, n_streams=n_streams, device=local_rank, max_block_samples=FRAME_LEN, raw_u8=True)
+        d.disable_callback()
+        d.set_cuda_stream(work_stream.cuda_stream)
+        ring8 = ResidentRing(d, iq8, FRAME_LEN, RING_PERIOD, raw_u8=True)
+        for _ in range(LOCK_FRAMES + W):
+            ring8.step()
+        d.join()
+        barrier()
+        ev6, ev7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev6.record()
+        for _ in range(K):
+            ring8.step()
+        d.join()
+        ev7.record()
+        barrier()
+        ms8, v8 = aggregate(ev6.elapsed_time(ev7), samples_per_rank, world, dist)
+        resident_u8 = {"value": round(v8, 1), "unit": "MSamples/s", "ms_per_step": round(ms8 / K, 4), "realtime_streams": round(v8 * 1e6 / FS, 1),
+                       "algorithmic_bytes_per_sample": round((2 * FRAME_LEN + FRAME_BITS) / FRAME_LEN, 3),
+                       "api": "dab_ofdm_attach_device_streams_raw (uint8 IQ resident in HBM, gain x16 so that the 8 bits are used) + dab_ofdm_advance_uniform",
+                       "checked_streams": check_streams_against_oracle(d, ring8, MODE, [3, n_streams // 2 + 5], FRAME_LEN)}
+        d.close()
+        del d, iq8, ring8
+        torch.cuda.empty_cache()
+    except Exception as ex:  # noqa: BLE001
+        resident_u8 = {"unavailable": repr(ex)}
+
     # ------------------------------------------------------------------ e2e: host buffers through dab_ofdm_process_batch
     def e2e_leg(u8):
         """K calls of the reference-facing batch entry point with pinned HOST blocks (one frame period per stream; fed repeatedly
@@ -615,7 +649,7 @@ def run_ours(args):
             "realtime_streams": round(value * 1e6 / FS, 1), "realtime_streams_per_gpu": round(value * 1e6 / FS / world, 1),
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "viterbi": viterbi, "modes": modes,
             "frames_per_stream_in_timed_region": frames_per_stream, "locked_streams": locked, "locked_fraction": round(locked / max(1, len(states)), 4),
-            "parity": parity, "sustained": sustained, "single_stream": single, "impairments": impaired,
+            "parity": parity, "sustained": sustained, "single_stream": single, "impairments": impaired, "resident_raw_u8": resident_u8,
         }
         emit(line)
     if world > 1:

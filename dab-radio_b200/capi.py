@@ -134,7 +134,7 @@ EXPORTED_SYMBOLS = (
     "dab_get_mapper_reference", "dab_get_puncture_code",
     "dab_ofdm_create", "dab_ofdm_destroy", "dab_ofdm_set_cuda_stream", "dab_ofdm_set_frame_callback", "dab_ofdm_set_config",
     "dab_ofdm_get_config", "dab_ofdm_default_config", "dab_ofdm_process", "dab_ofdm_process_batch", "dab_ofdm_process_batch_u8",
-    "dab_ofdm_process_batch_raw", "dab_iq_format_bytes", "dab_ofdm_rebase_device_streams",
+    "dab_ofdm_process_batch_raw", "dab_iq_format_bytes", "dab_ofdm_rebase_device_streams", "dab_ofdm_attach_device_streams_raw",
     "dab_ofdm_attach_device_streams", "dab_ofdm_advance", "dab_ofdm_advance_uniform", "dab_ofdm_device_bits", "dab_ofdm_reset",
     "dab_ofdm_get_state", "dab_ofdm_sync", "dab_ofdm_join", "dab_ofdm_count_frames_cb", "dab_ofdm_frame_bits", "dab_ofdm_get_params", "dab_ofdm_get_impulse_response",
     "dab_ofdm_get_coarse_frequency_response", "dab_ofdm_get_correlation_time_buffer", "dab_ofdm_get_frame_data_bits", "dab_ofdm_get_frame_fft", "dab_ofdm_get_frame_data_vec",
@@ -186,6 +186,7 @@ def load():
     L.dab_iq_format_bytes.argtypes = [i32]
     L.dab_iq_format_bytes.restype = sz
     L.dab_ofdm_attach_device_streams.argtypes = [vp, vp, sz, sz]
+    L.dab_ofdm_attach_device_streams_raw.argtypes = [vp, vp, sz, sz]
     L.dab_ofdm_advance.argtypes = [vp, C.POINTER(sz)]
     L.dab_ofdm_advance_uniform.argtypes = [vp, sz]
     L.dab_ofdm_rebase_device_streams.argtypes = [vp, sz]

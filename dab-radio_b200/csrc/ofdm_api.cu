@@ -979,15 +979,24 @@ int dab_ofdm_process(dab_ofdm* h, int stream, const dab_c32* iq, size_t n) {
     return ingest_and_run(o, ptrs.data(), ns.data(), DAB_IQ_F32);
 }
 
-int dab_ofdm_attach_device_streams(dab_ofdm* h, const dab_c32* d_iq, size_t stride_samples, size_t total_samples) {
+static int attach_impl(dab_ofdm* h, const void* d_iq, size_t stride_samples, size_t total_samples, bool raw) {
     OFDM_HANDLE(h);
     { int jrc = join_ways(o); if (jrc != DAB_OK) return jrc; }
     if (!d_iq || stride_samples < total_samples) return set_error(DAB_ERR_INVALID, "bad device stream geometry");
+    if (!raw && o->format != DAB_IQ_F32) return set_error(DAB_ERR_INVALID, "handle was created with sample_format = %d: use dab_ofdm_attach_device_streams_raw", o->format);
     DAB_CUDA_CHECK(cudaStreamSynchronize(o->stream));
     o->ext_base = d_iq;
     o->ext_stride = stride_samples;
     o->ext_total = total_samples;
     return init_states(o);
+}
+
+int dab_ofdm_attach_device_streams(dab_ofdm* h, const dab_c32* d_iq, size_t stride_samples, size_t total_samples) {
+    return attach_impl(h, d_iq, stride_samples, total_samples, false);
+}
+
+int dab_ofdm_attach_device_streams_raw(dab_ofdm* h, const void* d_iq, size_t stride_samples, size_t total_samples) {
+    return attach_impl(h, d_iq, stride_samples, total_samples, true);
 }
 
 int dab_ofdm_rebase_device_streams(dab_ofdm* h, size_t delta_samples) {

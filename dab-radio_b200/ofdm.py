@@ -113,7 +113,8 @@ class OfdmDemodBatch:
         return self.counter
 
     def attach_device_streams(self, d_ptr, stride_samples, total_samples):
-        capi.check(self.L.dab_ofdm_attach_device_streams(self.h, d_ptr, stride_samples, total_samples))
+        fn = self.L.dab_ofdm_attach_device_streams if self.sample_format == capi.IQ_F32 else self.L.dab_ofdm_attach_device_streams_raw
+        capi.check(fn(self.h, d_ptr, stride_samples, total_samples))
 
     def advance_uniform(self, n):
         capi.check(self.L.dab_ofdm_advance_uniform(self.h, n))

@@ -191,6 +191,9 @@ DAB_API int dab_ofdm_process_batch_raw(dab_ofdm* h, const void* const* iq, const
  * HBM.  The demodulator then reads the rows in place -- no ring copy.  dab_ofdm_advance(h, n) is one Process() call of n[s]
  * further samples per stream.  Soft bits stay on the device (dab_ofdm_device_bits) unless a callback is attached. */
 DAB_API int dab_ofdm_attach_device_streams(dab_ofdm* h, const dab_c32* d_iq, size_t stride_samples, size_t total_samples);
+/* the same for rows of raw samples in the handle's sample_format (what a capture card DMAs into HBM): 2 or 4 bytes per sample
+ * instead of 8 out of HBM. */
+DAB_API int dab_ofdm_attach_device_streams_raw(dab_ofdm* h, const void* d_iq, size_t stride_samples, size_t total_samples);
 /* dab_ofdm_advance* only queue work: internally the streams are split into pipeline ways on CUDA streams of their own, so that
  * consecutive calls overlap (no GPU-wide barrier per call).  dab_ofdm_join orders the handle's CUDA stream after everything
  * queued so far without blocking the host; dab_ofdm_device_bits, dab_ofdm_sync, the getters and the frame callback join

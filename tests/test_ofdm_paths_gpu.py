@@ -278,6 +278,40 @@ def test_raw_formats_match_host_dequantised_path(ofdm, oracle, fmt, mode, block,
     o.close()
 
 
+@pytest.mark.parametrize("fmt", ["u8", "s16be"])
+def test_raw_resident_streams(ofdm, oracle, fmt):
+    """dab_ofdm_attach_device_streams_raw: rows of raw integer samples already in HBM (what a capture card DMAs there), read in
+    place by the kernels; odd row stride so that the rows are not 16-byte aligned"""
+    torch = _torch()
+    mode, block, n_streams = 1, 65536, 5
+    xs = [dabgen.make_stream(mode, 4, seed=80 + s, cfo_hz=700.0 * s, start=11111 * s + 1, snr_db=25.0, u8=False) for s in range(n_streams)]
+    hosts, raws = [], []
+    for x in xs:
+        x = x * np.float32(0.25 / np.sqrt(np.mean(np.abs(x) ** 2)))
+        raw, host = _quantise(x, fmt)
+        hosts.append(host)
+        raws.append(raw)
+    d = ofdm.OfdmDemodBatch(mode, n_streams=n_streams, max_block_samples=block, sample_format=fmt)
+    sb = d.sample_bytes
+    total = hosts[0].size
+    stride = total + 3                                  # samples
+    buf = np.zeros((n_streams, stride * sb), np.uint8)
+    for s in range(n_streams):
+        buf[s, :total * sb] = raws[s]
+    t = torch.from_numpy(buf).cuda()
+    d.attach_device_streams(t.data_ptr(), stride, total)
+    for off in range(0, total - block + 1, block):
+        d.advance_uniform(block)
+    d.sync()
+    n_used = (total // block) * block
+    for s in range(n_streams):
+        o = oracle.OracleOfdmDemod(mode)
+        o.process_blocks(hosts[s][:n_used], block)
+        _assert_stream_parity(oracle, mode, o, d, stream=s, min_frames=2)
+        o.close()
+    d.close()
+
+
 # ---------------------------------------------------------------------------------------------------------------------------
 # host-side contracts
 # ---------------------------------------------------------------------------------------------------------------------------
