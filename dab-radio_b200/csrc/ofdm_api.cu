@@ -77,6 +77,7 @@ struct Ofdm {
     int call_ways = 1;                  // ways of the most recent call (n_ways_for)
     uint64_t way_min_samples = uint64_t(1) << 24;   // DAB_B200_WAY_MIN_SAMPLES: samples per way and call below which ways are merged
     cudaStream_t way_stream[MAX_WAYS] = {};
+    int n_sm = 148;                     // cudaDevAttrMultiProcessorCount (set at create)
     cudaEvent_t way_done[MAX_WAYS] = {};
     cudaEvent_t counts_ready[MAX_WAYS] = {};
     cudaEvent_t bits_ready[MAX_WAYS] = {};
@@ -304,6 +305,7 @@ static ControlGeom control_geom(const Ofdm* o) {
         g.samples = o->ring_iq.ptr;
     }
     g.fmt = o->fmt;
+    g.n_sm = o->n_sm;
     g.ring = o->null_ring.ptr;
     g.corr_explicit = o->corr_explicit.ptr;
     g.prs_fft_ref_conj = o->prs_fft_ref_conj.ptr;
@@ -706,6 +708,11 @@ static int create_impl(Ofdm* o, const dab_c32* prs, const int* mapper) {
 
     DAB_CUDA_CHECK(cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking));
     o->stream = o->own_stream;
+    {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, o->device) == cudaSuccess && v > 0) o->n_sm = v;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxPitch, o->device) == cudaSuccess && v > 0) o->max_pitch = size_t(v);
+    }
     for (int w = 0; w < Ofdm::MAX_WAYS; w++) {
         DAB_CUDA_CHECK(cudaStreamCreateWithFlags(&o->way_stream[w], cudaStreamNonBlocking));
         DAB_CUDA_CHECK(cudaEventCreateWithFlags(&o->way_done[w], cudaEventDisableTiming));

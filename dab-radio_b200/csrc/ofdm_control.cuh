@@ -87,6 +87,7 @@ struct ControlGeom {
     float2* vec_tap;         // optional [n_streams][(n_symbols-1) * n_carriers]
     const uint64_t* n_per_stream;  // samples of this call per stream, nullptr: n_uniform
     uint64_t n_uniform;
+    int n_sm;                      // SMs of the device: CTAs b and b + n_sm share an SM in the first wave (phase staggering)
 };
 
 constexpr int CTRL_L1_BATCH = 1024;  // windows whose L1 averages are computed in parallel before the sequential scan
@@ -165,42 +166,78 @@ struct Control {
     }
 
     // ---- CalculateL1Average (ofdm_demodulator.cpp:922-932) of `count` windows of K samples, window w starting at first + w * step,
-    // into out[0 .. count).  A warp takes 8 windows at a time and walks them together, so that 8 independent loads are in flight
-    // per lane: one window after the other costs a full memory latency per window (~1 us), which made a single unlocked stream
-    // (FindNullPowerDip scans whole blocks) the long pole of a 1024-stream step.  Per window the additions keep their order
-    // (lane-strided partial sums, then the butterfly): the frame kernel sums its windows the same way.  No barrier inside.
+    // into out[0 .. count).  One window after the other costs a full memory latency per window (~1 us), which made a single unlocked
+    // stream (FindNullPowerDip scans whole blocks) the long pole of a 1024-stream step, and one lane per sample costs ~70 warp
+    // instructions per 100-sample window (the fold of a Mode I frame's 393 windows was half of the control pass that ran it:
+    // profiles/r02_control_ncu.md).  No barrier inside.
     __device__ void l1_windows(float* out, int64_t first, int step, int K, int count) {
         if (K <= 32) {   // one window per thread
             for (int w = tid; w < count; w += THREADS) out[w] = l1_short_window<SB>(src, uint64_t(first + int64_t(w) * step), geo.mask, K, geo.fmt);
             return;
         }
-        constexpr int U = 8;
+        // Eight lanes per window, 4 x U windows per warp and round.  A lane reads its windows two samples per load (8 x 16 bytes =
+        // the four sectors of a 128-byte line per request) and all loads of a round are issued before the first addition: the fold
+        // is DRAM-latency bound, what counts is bytes in flight per round trip.  The odd sample in front of / behind the aligned
+        // pairs is read by lane 0 / lane 1 of the group.  A window that wraps around the stream's ring (one per revolution) takes
+        // masked single-sample loads instead.
+        constexpr int U = 1;    // windows per lane group and round (2: no faster, profiles/r02_step_probes.md)
+        constexpr int Q = 8;    // pair loads per lane and window in one batch (Q * 8 pairs = 128 samples)
         const int lane = tid & 31, warp = tid >> 5, n_warps = THREADS / 32;
-        for (int w = warp * U; w < count; w += n_warps * U) {
-            const int64_t base = first + int64_t(w) * step;
+        const int sub = lane & 7, grp = lane >> 3;
+        const unsigned char* base_ptr = reinterpret_cast<const unsigned char*>(src);
+        const uint32_t base_odd = uint32_t(reinterpret_cast<uintptr_t>(base_ptr) / uint32_t(SB)) & 1u;
+        for (int w = warp * 4 * U; w < count; w += n_warps * 4 * U) {
             float acc[U];
+            const unsigned char* wp[U];
+            int j_first[U], j_end[U];   // aligned pairs j_first + sub, + 8, ... < j_end of window u are read by this lane
+            bool slow[U];
+            uint64_t p0[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) acc[u] = 0.0f;
-            // four strides of 32 samples per round: with the default 100-sample windows every load of the 8 windows is issued
-            // before the first addition (one memory round trip per 8 windows instead of four)
-            for (int i0 = lane; i0 < K; i0 += 128) {
-                float2 v[4][U];
+            for (int u = 0; u < U; u++) {
+                const int ww = w + 4 * u + grp;
+                acc[u] = 0.0f;
+                j_first[u] = j_end[u] = 0;
+                slow[u] = false;
+                wp[u] = base_ptr;
+                p0[u] = uint64_t(first + int64_t(ww) * step) & geo.mask;
+                if (ww >= count) continue;
+                if (p0[u] + uint64_t(K) - 1 > geo.mask) { slow[u] = true; continue; }
+                const int o = int((uint32_t(p0[u]) ^ base_odd) & 1u);   // 1: the window starts on the second sample of an aligned pair
+                wp[u] = base_ptr + (p0[u] - uint64_t(o)) * uint64_t(SB);   // pair j = samples 2j - o, 2j - o + 1 of the window
+                j_first[u] = o + sub;
+                j_end[u] = (K + o) / 2;
+                float2 edge = make_float2(0.0f, 0.0f);
+                if (sub == 0 && o) edge = load_sample_ptr<SB>(wp[u] + SB, geo.fmt);
+                if (sub == 1 && ((K + o) & 1)) edge = load_sample_ptr<SB>(wp[u] + size_t(K - 1 + o) * SB, geo.fmt);
+                acc[u] = fabsf(edge.x) + fabsf(edge.y);
+            }
+            for (int jj = 0; jj < (K + 1) / 2; jj += 8 * Q) {
+                float2 a[U][Q], b[U][Q];
 #pragma unroll
-                for (int q = 0; q < 4; q++)
+                for (int u = 0; u < U; u++)
 #pragma unroll
-                    for (int u = 0; u < U; u++)
-                        v[q][u] = (w + u < count && i0 + 32 * q < K) ? sample(base + int64_t(u) * step + i0 + 32 * q) : make_float2(0.0f, 0.0f);
+                    for (int q = 0; q < Q; q++) {
+                        a[u][q] = b[u][q] = make_float2(0.0f, 0.0f);
+                        const int j = j_first[u] + jj + 8 * q;
+                        if (j < j_end[u]) load_sample_pair<SB>(wp[u] + size_t(j) * (2 * SB), geo.fmt, a[u][q], b[u][q]);
+                    }
 #pragma unroll
-                for (int q = 0; q < 4; q++)
+                for (int u = 0; u < U; u++)
 #pragma unroll
-                    for (int u = 0; u < U; u++) acc[u] += fabsf(v[q][u].x) + fabsf(v[q][u].y);
+                    for (int q = 0; q < Q; q++) acc[u] += (fabsf(a[u][q].x) + fabsf(a[u][q].y)) + (fabsf(b[u][q].x) + fabsf(b[u][q].y));
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                float a = acc[u];
+                if (slow[u]) {
+                    for (int i = sub; i < K; i += 8) {
+                        const float2 x = sample(int64_t(p0[u]) + i);
+                        acc[u] += fabsf(x.x) + fabsf(x.y);
+                    }
+                }
 #pragma unroll
-                for (int d = 16; d >= 1; d >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, d);
-                if (lane == 0 && w + u < count) out[w + u] = a / float(K);
+                for (int d = 4; d >= 1; d >>= 1) acc[u] += __shfl_xor_sync(0xFFFFFFFFu, acc[u], d);
+                const int ww = w + 4 * u + grp;
+                if (sub == 0 && ww < count) out[ww] = acc[u] / float(K);
             }
         }
     }
@@ -651,6 +688,11 @@ ofdm_control_kernel(ControlGeom geo, int pass) {
     const void* src = reinterpret_cast<const unsigned char*>(geo.samples) + size_t(stream) * geo.stream_stride * size_t(SB);
     C ctl{geo, st, stream, tid, tw1, tw2, e1, e2, nat, l1buf, red, src};
 
+    // UpdateSignalAverage belongs to the entry of Process() (ofdm_demodulator.cpp:241) and only reads the samples of this call, so
+    // where in the call it runs is free.  It is DRAM-latency bound and the synchronisation transforms are issue bound: every other
+    // CTA of an SM folds before its transforms instead of after them, so the two kinds of phase meet on the SM instead of all CTAs
+    // waiting on memory together (pass 0 stays short: the frame kernel of this way waits for it).
+    if (pass >= 1 && st.avg_pending && ((blockIdx.x / geo.n_sm) & 1)) ctl.fold_average();
     if (st.pipeline_pending) ctl.finish_pipeline();
     __syncthreads();
 

@@ -55,6 +55,22 @@ __device__ __forceinline__ float2 load_sample(const void* src, uint64_t index, c
     return load_sample_ptr<SB>(reinterpret_cast<const unsigned char*>(src) + index * uint64_t(SB), f);
 }
 
+// Two consecutive samples with one load; p is aligned to 2 * SB bytes.
+template <int SB>
+__device__ __forceinline__ void load_sample_pair(const void* p, const SampleFmt& f, float2& a, float2& b) {
+    if (SB == 2) {
+        const uint32_t raw = __ldg(reinterpret_cast<const unsigned int*>(p));
+        a = decode_sample<2>(raw & 0xFFFFu, f);
+        b = decode_sample<2>(raw >> 16, f);
+    } else if (SB == 4) {
+        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+        a = decode_sample<4>(raw.x, f);
+        b = decode_sample<4>(raw.y, f);
+    } else {
+        asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y) : "l"(p));
+    }
+}
+
 // One work item of the frame kernels: symbols [s_begin, s_end) of one transmission frame of one stream.  The item writes the
 // cyclic-prefix phase error of each of its symbols and the soft-bit rows s - 1 (DQPSK of symbols s - 1 and s) for s >= 1; for
 // s_begin > 0 it transforms symbol s_begin - 1 once more as the differential reference.  A frame is covered by any tiling of

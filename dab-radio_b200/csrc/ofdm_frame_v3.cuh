@@ -72,6 +72,9 @@ __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v) { asm v
 // DAB_V3_TW1_REGS (default 1): the inter-pass twiddles W_N^{t k1} B_t = (B_t W^{t b}) (W^{t 4a}), k1 = 4a + b, live in seven
 // registers per thread (four Q_b, three R_a) instead of a 16 x T shared-memory table: 16 fewer LDS.64 per thread and symbol (the
 // kernel's busiest unit is l1tex) for 12 more complex multiplies, and 16 KB less shared memory per transform.
+#ifndef DAB_V3_EARLY_FETCH
+#define DAB_V3_EARLY_FETCH 1
+#endif
 #ifndef DAB_V3_TW1_REGS
 #define DAB_V3_TW1_REGS 1
 #endif
@@ -309,6 +312,14 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_i
 #pragma unroll
             for (int j = 0; j < 16; j++) v[j] = make_float2(0.0f, 0.0f);
         }
+#if DAB_V3_EARLY_FETCH
+        __syncthreads();  // ---- barrier A0: the input buffer and the D table are in registers everywhere
+        const bool has_next = active && (s + 1 < desc.s_end);
+        if (has_next) {
+            fetch(s + 1);
+            if (t >= DTAB_T0 && t < DTAB_T0 + 16) write_dtab(s + 1, t - DTAB_T0);
+        }
+#endif
         corr = group_reduce_sum<RED_WIDTH>(corr);
         if (WARPS_PER_GROUP > 1 && (t & 31) == 0) red[t >> 5] = corr;
 
@@ -348,11 +359,13 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_i
 #endif
         __syncthreads();  // ---- barrier A: every thread has consumed the input buffer and the D table
 
+#if !DAB_V3_EARLY_FETCH
         const bool has_next = active && (s + 1 < desc.s_end);
         if (has_next) {
             fetch(s + 1);
             if (t >= DTAB_T0 && t < DTAB_T0 + 16) write_dtab(s + 1, t - DTAB_T0);
         }
+#endif
         if (own && t == PE_T && desc.phase_err != nullptr) {
             float2 tot = corr;
             if (WARPS_PER_GROUP > 1) {

@@ -14,12 +14,12 @@ import bench  # noqa: E402
 ofdm = importlib.import_module("dab-radio_b200.ofdm")
 n_streams = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 mode, fl = 1, bench.FRAME_LEN
-iq, _ = bench.build_streams_on_device(torch, n_streams, 14, seed=100, mode=mode, frame_len=fl)
-CASES = [{}, {"DAB_B200_L1_SIDE": "0"}]
+iq, _ = bench.build_streams_on_device(torch, n_streams, 30, seed=100, mode=mode, frame_len=fl)
+CASES = [{}]
 for extra in sys.argv[2:]:
     CASES.append(dict(kv.split("=") for kv in extra.split(",")))
 for case in CASES:
-    for ways in ("4", "1"):
+    for ways in os.environ.get("PROBE_WAYS", "4,1").split(","):
         env = dict(case, DAB_B200_PIPELINE_WAYS=ways)
         for k, v in env.items():
             os.environ[k] = v
@@ -38,7 +38,7 @@ for case in CASES:
                 d.set_kernel_timing(True)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            K = 8
+            K = 24
             for _ in range(K):
                 d.advance_uniform(fl)
             d.join()
