@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <complex>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -13,6 +14,7 @@
 
 #include "common.cuh"
 #include "ofdm_control.cuh"
+#include "stage_layout.h"
 #include "ofdm_frame.cuh"
 #include "ofdm_frame_v3.cuh"
 
@@ -97,7 +99,9 @@ struct Ofdm {
     DeviceBuffer<dab_ofdm_frame_info> infos;
     DeviceBuffer<int32_t> frames_in_call;
     DeviceBuffer<int8_t> bits;
-    DeviceBuffer<int16_t> bin_to_pos, bin_to_carrier;
+    DeviceBuffer<int16_t> bin_to_pos, bin_to_carrier, bin_to_slot;
+    DeviceBuffer<uint16_t> chunk_src;
+    int stage_wavefronts[3] = {0, 0, 0};   // store instructions per symbol, wavefronts in position order, wavefronts as laid out
     DeviceBuffer<uint64_t> d_n;
     // external (device resident) streams
     const void* ext_base = nullptr;
@@ -226,6 +230,8 @@ static FrameGeom frame_geom(const Ofdm* o) {
     g.fmt = o->fmt;
     g.bin_to_pos = o->bin_to_pos.ptr;
     g.bin_to_carrier = o->bin_to_carrier.ptr;
+    g.bin_to_slot = o->bin_to_slot.ptr;
+    g.chunk_src = o->chunk_src.ptr;
     g.twiddles = o->twiddles.ptr;
     return g;
 }
@@ -666,6 +672,33 @@ static int init_states(Ofdm* o) {
     return DAB_OK;
 }
 
+// Staging layout of the v3 frame kernel for one carrier map (stage_layout.h): the search runs once per process and map.
+static const StageLayout& stage_layout_for(int nfft, int ncarr, const std::vector<int16_t>& b2p, bool optimise) {
+    static std::mutex mtx;
+    static std::map<std::vector<int16_t>, StageLayout> cache;
+    std::vector<int16_t> key(b2p);
+    key.push_back(int16_t(optimise ? 1 : 0));
+    std::lock_guard<std::mutex> lock(mtx);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    // the kernel's store instructions: register slot r of the lanes of one warp (or of one transform when it has fewer threads)
+    const int T = nfft / 16, R3 = nfft / 256, lanes = std::min(T, 32);
+    std::vector<std::vector<int>> groups;
+    for (int t0 = 0; t0 < T; t0 += lanes)
+        for (int r = 0; r < 16; r++) {
+            std::vector<int> g;
+            bool any = false;
+            for (int l = 0; l < lanes; l++) {
+                const int t = t0 + l;
+                const int bin = (R3 == 1) ? t + 16 * r : (t + T * (r / R3)) + 256 * (r % R3);   // fft_out_bin (ofdm_device.cuh)
+                g.push_back(bin);
+                any = any || b2p[size_t(bin)] >= 0;
+            }
+            if (any) groups.push_back(std::move(g));
+        }
+    return cache.emplace(std::move(key), stage_layout_optimise(groups, b2p, ncarr, optimise, 20000)).first->second;
+}
+
 static int create_impl(Ofdm* o, const dab_c32* prs, const int* mapper) {
     const size_t nfft = o->p.nb_fft, ncarr = o->p.nb_data_carriers, ns = size_t(o->n_streams);
     const size_t frame_cap = o->p.nb_frame_symbols * o->p.nb_symbol_period + o->p.nb_null_period;
@@ -768,6 +801,16 @@ static int create_impl(Ofdm* o, const dab_c32* prs, const int* mapper) {
     DAB_CUDA_CHECK(cudaMemcpy(o->prs_time_ref_conj.ptr, time_conj.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice));
     DAB_CUDA_CHECK(cudaMemcpy(o->bin_to_pos.ptr, b2p.data(), nfft * sizeof(int16_t), cudaMemcpyHostToDevice));
     DAB_CUDA_CHECK(cudaMemcpy(o->bin_to_carrier.ptr, b2c.data(), nfft * sizeof(int16_t), cudaMemcpyHostToDevice));
+    {
+        const StageLayout& lay = stage_layout_for(int(nfft), int(ncarr), b2p, o->dab_geometry && ncarr % 64 == 0);
+        DAB_CUDA_CHECK(o->bin_to_slot.reserve(nfft));
+        DAB_CUDA_CHECK(o->chunk_src.reserve(lay.chunk_src.size()));
+        DAB_CUDA_CHECK(cudaMemcpy(o->bin_to_slot.ptr, lay.bin_to_slot.data(), nfft * sizeof(int16_t), cudaMemcpyHostToDevice));
+        DAB_CUDA_CHECK(cudaMemcpy(o->chunk_src.ptr, lay.chunk_src.data(), lay.chunk_src.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        o->stage_wavefronts[0] = lay.store_instructions;
+        o->stage_wavefronts[1] = lay.wavefronts_before;
+        o->stage_wavefronts[2] = lay.wavefronts_after;
+    }
     o->fed.assign(ns, 0);
     o->n_call.assign(ns, 0);
     return init_states(o);

@@ -98,6 +98,8 @@ struct FrameGeom {
     SampleFmt fmt;
     const int16_t* bin_to_pos;      // [NFFT]: de-interleaved soft-bit position of FFT bin k, -1 for DC / guard bins
     const int16_t* bin_to_carrier;  // [NFFT]: carrier index (DQPSK vector order) of bin k, -1 if unused
+    const int16_t* bin_to_slot;     // [NFFT]: v3 kernel, staging slot of bin k's soft-bit pair (stage_layout.h), -1 if unused
+    const uint16_t* chunk_src;      // [n_carriers / 8]: v3 kernel, chunk slot << 2 | word rotation of output chunk i
     const float2* twiddles;         // [TW1_SIZE + TW2_SIZE] precomputed FFT twiddles
 };
 

@@ -245,7 +245,7 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_i
     for (int r = 0; r < 16; r++) {
         stage_addr[r] = stage_base + 2u * uint32_t(NCARR);
         if (SL::mode(r) != 0) {
-            const int p = geo.bin_to_pos[fft_out_bin<NFFT>(t, r)];
+            const int p = geo.bin_to_slot[fft_out_bin<NFFT>(t, r)];
             if (p >= 0) stage_addr[r] = stage_base + 2u * uint32_t(p);
         }
     }
@@ -265,7 +265,11 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_i
         int8_t* out = desc.bits + size_t(s_out) * size_t(2 * NCARR);
         const uint4* src4 = reinterpret_cast<const uint4*>(stage);
         for (int i = t; i < NCARR / 8; i += T) {
-            const uint4 w = src4[i];
+            // the chunk sits where the store instructions of the DQPSK step meet the fewest bank conflicts, its four words rotated
+            const uint32_t cs = __ldg(geo.chunk_src + i);
+            uint4 w = src4[cs >> 2];
+            if (cs & 1u) w = make_uint4(w.y, w.z, w.w, w.x);
+            if (cs & 2u) w = make_uint4(w.z, w.w, w.x, w.y);
             uint2 re, im;
             re.x = __byte_perm(w.x, w.y, 0x6420);
             re.y = __byte_perm(w.z, w.w, 0x6420);
@@ -404,8 +408,9 @@ ofdm_frame_v3_kernel(FrameGeom geo, const FrameDesc* __restrict__ descs, int n_i
                 // the reference divides by A exactly (largest component -> +-127).  127.00006 / A with a 1-ulp reciprocal keeps
                 // that component at or above 127.0 before truncation and moves the other by < 1e-4 LSB; A = 0 -> NaN -> 0
                 const float ra = rcp_approx(a) * 127.00006f;
-                const uint32_t bre = uint32_t(__float2int_rz(-d.x * ra));
-                const uint32_t bim = uint32_t(__float2int_rz(d.y * ra));
+                const float2 sc = __fmul2_rn(d, make_float2(-ra, ra));   // one packed multiply; (-x) * r == x * (-r) exactly
+                const uint32_t bre = uint32_t(__float2int_rz(sc.x));
+                const uint32_t bim = uint32_t(__float2int_rz(sc.y));
                 st_shared_u16(stage_addr[r], __byte_perm(bre, bim, 0x0040));
                 if (TAPS) {
                     if (desc.vec_tap != nullptr && stage_addr[r] != stage_dummy) {
