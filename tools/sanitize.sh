@@ -22,4 +22,4 @@ for cmd in "python tools/async_probe.py 2 4096" "python tools/async_probe.py 1 1
   echo "##### compute-sanitizer --tool racecheck $cmd" >> $log
   timeout 1200 compute-sanitizer --tool racecheck --print-limit 5 $cmd 2>&1 | grep -v "^$" | tail -12 >> $log
 done
-tail -5 $out/${tag}_sanitizer_*.log
+for f in $out/${tag}_sanitizer_*.log; do echo "== $f"; tail -n 5 $f; done
