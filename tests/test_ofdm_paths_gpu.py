@@ -361,3 +361,73 @@ def test_getters_between_calls_come_from_the_snapshot(ofdm, oracle):
     assert d.state(1)["total_frames_read"] == 0
     d.close()
     o.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# UpdateSignalAverage windows: lengths, strides and alignments of the paired-load fold (ofdm_control.cuh l1_windows)
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("K,decimate", [(33, 1), (64, 3), (99, 5), (100, 1), (101, 2), (250, 4), (257, 1)])
+@pytest.mark.parametrize("resident_offset", [None, 0, 1])
+def test_signal_average_window_geometries(ofdm, oracle, K, decimate, resident_offset):
+    """CalculateL1Average / UpdateSignalAverage (ofdm_demodulator.cpp:922-950) for window lengths either side of the default 100 (odd and
+    even: with / without a lone sample in front of or behind the 16-byte pairs), strides from contiguous to sparse, windows longer
+    than one batch of loads, through the stream ring of the host path (windows that wrap around the ring take the masked loads) and
+    over resident streams whose first sample is / is not 16-byte aligned.  The running average must stay within 1e-4 of the oracle
+    and the null search that uses it must find the same frames."""
+    torch = _torch()
+    mode, block = 4, 30000   # Mode IV: 98304-sample frames; the block is no multiple of any window stride
+    x = dabgen.make_stream(mode, 6, seed=11, cfo_hz=1234.0, start=4097, snr_db=25.0)
+    o = oracle.OracleOfdmDemod(mode)
+    o.config.signal_l1_nb_samples = K
+    o.config.signal_l1_nb_decimate = decimate
+    d = ofdm.OfdmDemodBatch(mode, n_streams=1, max_block_samples=32768)
+    cfg = d.get_config(0)
+    cfg.signal_l1_nb_samples = K
+    cfg.signal_l1_nb_decimate = decimate
+    d.set_config(cfg)
+    if resident_offset is None:
+        for off in range(0, x.size, block):
+            o.process(x[off:off + block])
+            d.process(0, x[off:off + block])
+    else:
+        pad = np.zeros(2 + resident_offset, np.complex64)   # cudaMalloc is 256-byte aligned: + 2 samples keeps 16 bytes, + 3 does not
+        t = torch.from_numpy(np.concatenate([pad, x]).view(np.float32)).cuda()
+        d.attach_device_streams(t.data_ptr() + 8 * pad.size, x.size, x.size)
+        n_blocks = x.size // block
+        for k in range(n_blocks):
+            o.process(x[k * block:(k + 1) * block])
+            d.advance_uniform(block)
+        d.sync()
+    # long windows lose lock now and then (in the oracle as here): frames, desyncs and the average must agree whatever happens
+    _assert_stream_parity(oracle, mode, o, d, min_frames=1)
+    d.close()
+    o.close()
+
+
+def test_stage_layout_of_a_custom_carrier_map(ofdm, oracle, pkg):
+    """The v3 frame kernel stages soft bits where a host-side search puts them (csrc/stage_layout.h) for whatever carrier map the
+    caller passes with a DAB geometry: a reversed and a block-interleaved map must come out in exactly the order the map asks for."""
+    mode = 2
+    p = oracle.params(mode)
+    ncarr = p["nb_data_carriers"]
+    x = dabgen.make_stream(mode, 5, seed=3, cfo_hz=-777.0, start=1500, snr_db=30.0)
+    ref = ofdm.OfdmDemodBatch(mode, n_streams=1, max_block_samples=65536)
+    for off in range(0, x.size, 65536):
+        ref.process(0, x[off:off + 65536])
+    base_map = np.asarray(ofdm.mapper_reference(mode), np.int32)
+    for name, perm in (("reversed", np.arange(ncarr - 1, -1, -1, dtype=np.int32)),
+                       ("blocks", (np.arange(ncarr, dtype=np.int32).reshape(8, -1).T.reshape(-1)).astype(np.int32))):
+        # mapper[i] = carrier whose soft bit lands at position i
+        mapper = base_map[perm]
+        d = ofdm.OfdmDemodBatch(mode, n_streams=1, max_block_samples=65536, mapper=mapper)
+        for off in range(0, x.size, 65536):
+            d.process(0, x[off:off + 65536])
+        assert len(d.frames[0]) == len(ref.frames[0]) >= 3, name
+        for (gi, gb), (ri, rb) in zip(d.frames[0], ref.frames[0]):
+            assert gi["frame_start"] == ri["frame_start"]
+            S1 = gb.size // (2 * ncarr)
+            g3 = gb.reshape(S1, 2, ncarr)
+            r3 = rb.reshape(S1, 2, ncarr)
+            assert np.array_equal(g3, r3[:, :, perm]), f"{name}: soft bits are not the reference order permuted by the map"
+        d.close()
+    ref.close()
