@@ -1067,7 +1067,7 @@ def reference_runner(cores, threads_each=1, n_instances=None):
         from oracle import pyref
         pool = pyref.RefOfdmPool(MODE, n_instances, threads_each, fast=True)
         note = ("reference sources compiled unmodified (oracle/_ref/libdabref_fast.so, -O3 -march=x86-64-v3 -ffast-math, AVX2 PLL); "
-                "FFTW3 absent -> vectorised float radix-2 stand-in FFT")
+                "FFTW3 absent -> single-precision radix-4 Stockham stand-in FFT (AVX2 + FMA intrinsics)")
         return (lambda reps: pool.run_multi(xs, FRAME_LEN, reps)), "reference", note, pool
     except (FileNotFoundError, OSError, AttributeError):
         from oracle import pyoracle as po
