@@ -117,33 +117,6 @@ __device__ __forceinline__ ArgMax argmax_combine(ArgMax a, ArgMax b) {
     return take_b ? b : a;
 }
 
-// CalculateL1Average of a window of K <= 32 samples by ONE thread, bit-identical to the warp form used for longer windows (one
-// sample per lane, then the xor butterfly: what lane 0 ends up with is the tree t[i] += t[i + d], d = 16, 8, 4, 2, 1 over the
-// zero-padded samples).  With one window per lane a warp sums 32 short windows per round instead of one: the 25-sample windows
-// that make Modes II / III lock (OFDM_Demod_Config::signal_l1) otherwise use 25 lanes for one 8-byte load each.
-template <int SB>
-__device__ __forceinline__ float l1_short_window(const void* src, uint64_t first, uint64_t mask, int K, const SampleFmt& fmt) {
-    float s16[16];
-    // eight pairs (i, i + 16) at a time: sixteen independent loads in flight before the first addition
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        float2 xa[8], xb[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int i = 8 * h + j;
-            xa[j] = (i < K) ? load_sample<SB>(src, (first + uint64_t(i)) & mask, fmt) : make_float2(0.0f, 0.0f);
-            xb[j] = (i + 16 < K) ? load_sample<SB>(src, (first + uint64_t(i + 16)) & mask, fmt) : make_float2(0.0f, 0.0f);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; j++) s16[8 * h + j] = (fabsf(xa[j].x) + fabsf(xa[j].y)) + (fabsf(xb[j].x) + fabsf(xb[j].y));
-    }
-#pragma unroll
-    for (int d = 8; d >= 1; d >>= 1)
-#pragma unroll
-        for (int i = 0; i < d; i++) s16[i] += s16[i + d];
-    return s16[0] / float(K);
-}
-
 template <int NFFT, int SB>
 struct Control {
     using G = FftGeom<NFFT>;
@@ -171,30 +144,36 @@ struct Control {
     // instructions per 100-sample window (the fold of a Mode I frame's 393 windows was half of the control pass that ran it:
     // profiles/r02_control_ncu.md).  No barrier inside.
     __device__ void l1_windows(float* out, int64_t first, int step, int K, int count) {
-        if (K <= 32) {   // one window per thread
-            for (int w = tid; w < count; w += THREADS) out[w] = l1_short_window<SB>(src, uint64_t(first + int64_t(w) * step), geo.mask, K, geo.fmt);
-            return;
-        }
-        // Eight lanes per window, 4 x U windows per warp and round.  A lane reads its windows two samples per load (8 x 16 bytes =
-        // the four sectors of a 128-byte line per request) and all loads of a round are issued before the first addition: the fold
-        // is DRAM-latency bound, what counts is bytes in flight per round trip.  The odd sample in front of / behind the aligned
-        // pairs is read by lane 0 / lane 1 of the group.  A window that wraps around the stream's ring (one per revolution) takes
-        // masked single-sample loads instead.
-        constexpr int U = 1;    // windows per lane group and round (2: no faster, profiles/r02_step_probes.md)
-        constexpr int Q = 8;    // pair loads per lane and window in one batch (Q * 8 pairs = 128 samples)
+        // the fold is DRAM-latency bound (what counts is bytes in flight per round trip) and, for short windows, bound by the
+        // sectors per load instruction: a group of LPW lanes shares a window, each lane reads two samples per 16-byte load, so a
+        // request covers whole 32-byte sectors exactly once.  100-sample windows: 8 lanes x 7 loads, 4 windows per warp and
+        // round; windows of up to 32 samples (25 x 2 is the setting under which Modes II / III lock on whole-frame blocks):
+        // 2 lanes x up to 8 loads, 2 x 16 windows per warp and round -- one 8-byte load per sample and one window per thread made
+        // that fold 1.7 ms of a 2.3 ms Mode I step (32 sectors per request, every sector requested four times).
+        if (K <= 32) l1_windows_t<2, 2>(out, first, step, K, count);
+        else l1_windows_t<8, 1>(out, first, step, K, count);
+    }
+
+    // LPW lanes per window, U windows per lane group and round.  The odd sample in front of / behind the aligned pairs is read by
+    // lane 0 / lane 1 of the group.  A window that wraps around the stream's ring (one per revolution) takes masked single-sample
+    // loads instead.
+    template <int LPW, int U>
+    __device__ __forceinline__ void l1_windows_t(float* out, int64_t first, int step, int K, int count) {
+        constexpr int Q = 8;            // pair loads per lane and window in one batch (Q * LPW pairs)
+        constexpr int WPR = 32 / LPW;   // windows per warp and round (x U)
         const int lane = tid & 31, warp = tid >> 5, n_warps = THREADS / 32;
-        const int sub = lane & 7, grp = lane >> 3;
+        const int sub = lane & (LPW - 1), grp = lane / LPW;
         const unsigned char* base_ptr = reinterpret_cast<const unsigned char*>(src);
         const uint32_t base_odd = uint32_t(reinterpret_cast<uintptr_t>(base_ptr) / uint32_t(SB)) & 1u;
-        for (int w = warp * 4 * U; w < count; w += n_warps * 4 * U) {
+        for (int w = warp * WPR * U; w < count; w += n_warps * WPR * U) {
             float acc[U];
             const unsigned char* wp[U];
-            int j_first[U], j_end[U];   // aligned pairs j_first + sub, + 8, ... < j_end of window u are read by this lane
+            int j_first[U], j_end[U];   // aligned pairs j_first, + LPW, ... < j_end of window u are read by this lane
             bool slow[U];
             uint64_t p0[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                const int ww = w + 4 * u + grp;
+                const int ww = w + WPR * u + grp;
                 acc[u] = 0.0f;
                 j_first[u] = j_end[u] = 0;
                 slow[u] = false;
@@ -211,14 +190,14 @@ struct Control {
                 if (sub == 1 && ((K + o) & 1)) edge = load_sample_ptr<SB>(wp[u] + size_t(K - 1 + o) * SB, geo.fmt);
                 acc[u] = fabsf(edge.x) + fabsf(edge.y);
             }
-            for (int jj = 0; jj < (K + 1) / 2; jj += 8 * Q) {
+            for (int jj = 0; jj < (K + 1) / 2; jj += LPW * Q) {
                 float2 a[U][Q], b[U][Q];
 #pragma unroll
                 for (int u = 0; u < U; u++)
 #pragma unroll
                     for (int q = 0; q < Q; q++) {
                         a[u][q] = b[u][q] = make_float2(0.0f, 0.0f);
-                        const int j = j_first[u] + jj + 8 * q;
+                        const int j = j_first[u] + jj + LPW * q;
                         if (j < j_end[u]) load_sample_pair<SB>(wp[u] + size_t(j) * (2 * SB), geo.fmt, a[u][q], b[u][q]);
                     }
 #pragma unroll
@@ -229,14 +208,14 @@ struct Control {
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 if (slow[u]) {
-                    for (int i = sub; i < K; i += 8) {
+                    for (int i = sub; i < K; i += LPW) {
                         const float2 x = sample(int64_t(p0[u]) + i);
                         acc[u] += fabsf(x.x) + fabsf(x.y);
                     }
                 }
 #pragma unroll
-                for (int d = 4; d >= 1; d >>= 1) acc[u] += __shfl_xor_sync(0xFFFFFFFFu, acc[u], d);
-                const int ww = w + 4 * u + grp;
+                for (int d = LPW / 2; d >= 1; d >>= 1) acc[u] += __shfl_xor_sync(0xFFFFFFFFu, acc[u], d);
+                const int ww = w + WPR * u + grp;
                 if (sub == 0 && ww < count) out[ww] = acc[u] / float(K);
             }
         }
@@ -289,20 +268,28 @@ struct Control {
             const int count = int(min(int64_t(CTRL_L1_BATCH), n_windows - w0));
             l1_windows(l1buf, c0 + w0 * K, K, K, count);
             __syncthreads();
+            // The reference walks the windows in order: the first one below the start threshold arms the detector, the first one
+            // after it above the end threshold ends the NULL symbol (:306-326).  Both are "first index where" searches: two block
+            // reductions instead of one thread walking up to 1024 windows while the other 127 wait (that walk was 39 % of the stall
+            // samples of a control pass with unlocked streams in it, and unlocked streams are its long pole).
+            const float start_thresh = st.l1_average * st.cfg.null_l1_thresh_null_start;
+            const float end_thresh = st.l1_average * st.cfg.null_l1_thresh_null_end;
+            bool started = st.null_start_found != 0;
+            int from = 0;
+            if (!started) {
+                const int a = block_first(count, [&](int i) { return l1buf[i] < start_thresh; });
+                if (a != 0x7FFFFFFF) {
+                    started = true;
+                    from = a + 1;
+                }
+            }
+            int b = 0x7FFFFFFF;
+            if (started) b = block_first(count - from, [&](int i) { return l1buf[from + i] > end_thresh; });
             if (tid == 0) {
-                const float start_thresh = st.l1_average * st.cfg.null_l1_thresh_null_start;
-                const float end_thresh = st.l1_average * st.cfg.null_l1_thresh_null_end;
-                for (int w = 0; w < count; w++) {
-                    const float l1 = l1buf[w];
-                    if (st.null_start_found) {
-                        if (l1 > end_thresh) {
-                            st.null_end_found = 1;
-                            nb_read_s = (w0 + w) * K + K;
-                            break;
-                        }
-                    } else if (l1 < start_thresh) {
-                        st.null_start_found = 1;
-                    }
+                if (started) st.null_start_found = 1;
+                if (b != 0x7FFFFFFF) {
+                    st.null_end_found = 1;
+                    nb_read_s = (w0 + from + b) * K + K;
                 }
             }
             __syncthreads();
@@ -366,6 +353,24 @@ struct Control {
             for (int r = 0; r < 16; r++) nat[fft_out_bin<NFFT>(tid, r)] = conjugate ? cconj(v[r]) : v[r];
         }
         __syncthreads();
+    }
+
+    // smallest i < n with pred(i), 0x7FFFFFFF if there is none; the same value in every thread
+    template <typename P>
+    __device__ int block_first(int n, P pred) {
+        int best = 0x7FFFFFFF;
+        for (int i = tid; i < n; i += THREADS)
+            if (pred(i)) {
+                best = i;
+                break;
+            }
+        best = __reduce_min_sync(0xFFFFFFFFu, best);
+        if ((tid & 31) == 0) red[tid >> 5] = make_float2(__int_as_float(best), 0.0f);
+        __syncthreads();
+        int r = __float_as_int(red[0].x);
+        for (int w = 1; w < THREADS / 32; w++) r = min(r, __float_as_int(red[w].x));
+        __syncthreads();
+        return r;
     }
 
     template <typename F>

@@ -15,13 +15,16 @@ ofdm = importlib.import_module("dab-radio_b200.ofdm")
 mode, block = int(sys.argv[1]), int(sys.argv[2])
 l1 = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else None
 fl = bench.MODE_FRAME_LEN[mode]
-n = 1024
+n = int(os.environ.get("PROBE_STREAMS", "1024"))
 iq, _ = bench.build_streams_on_device(torch, n, 11, seed=4321 + mode, mode=mode, frame_len=fl, period=8)
-for ways in ("auto", "1"):
-    if ways == "1":
-        os.environ["DAB_B200_PIPELINE_WAYS"] = "1"
+for ways in os.environ.get("PROBE_WAYS", "auto,1").split(","):
+    if ways != "auto":
+        os.environ["DAB_B200_PIPELINE_WAYS"] = ways.split(":")[0]
+        if ":" in ways:
+            os.environ["DAB_B200_WAY_MIN_SAMPLES"] = ways.split(":")[1]
     d = ofdm.OfdmDemodBatch(mode, n_streams=n, device=0, max_block_samples=block)
     os.environ.pop("DAB_B200_PIPELINE_WAYS", None)
+    os.environ.pop("DAB_B200_WAY_MIN_SAMPLES", None)
     d.disable_callback()
     if l1:
         cfg = d.get_config(0)
