@@ -167,6 +167,7 @@ struct Control {
         const uint32_t base_odd = uint32_t(reinterpret_cast<uintptr_t>(base_ptr) / uint32_t(SB)) & 1u;
         for (int w = warp * WPR * U; w < count; w += n_warps * WPR * U) {
             float acc[U];
+            float2 edge[U];
             const unsigned char* wp[U];
             int j_first[U], j_end[U];   // aligned pairs j_first, + LPW, ... < j_end of window u are read by this lane
             bool slow[U];
@@ -175,6 +176,7 @@ struct Control {
             for (int u = 0; u < U; u++) {
                 const int ww = w + WPR * u + grp;
                 acc[u] = 0.0f;
+                edge[u] = make_float2(0.0f, 0.0f);
                 j_first[u] = j_end[u] = 0;
                 slow[u] = false;
                 wp[u] = base_ptr;
@@ -185,10 +187,9 @@ struct Control {
                 wp[u] = base_ptr + (p0[u] - uint64_t(o)) * uint64_t(SB);   // pair j = samples 2j - o, 2j - o + 1 of the window
                 j_first[u] = o + sub;
                 j_end[u] = (K + o) / 2;
-                float2 edge = make_float2(0.0f, 0.0f);
-                if (sub == 0 && o) edge = load_sample_ptr<SB>(wp[u] + SB, geo.fmt);
-                if (sub == 1 && ((K + o) & 1)) edge = load_sample_ptr<SB>(wp[u] + size_t(K - 1 + o) * SB, geo.fmt);
-                acc[u] = fabsf(edge.x) + fabsf(edge.y);
+                // requested here, added after the pair loads are on their way (one memory round trip per round, not two)
+                if (sub == 0 && o) edge[u] = load_sample_ptr<SB>(wp[u] + SB, geo.fmt);
+                if (sub == 1 && ((K + o) & 1)) edge[u] = load_sample_ptr<SB>(wp[u] + size_t(K - 1 + o) * SB, geo.fmt);
             }
             for (int jj = 0; jj < (K + 1) / 2; jj += LPW * Q) {
                 float2 a[U][Q], b[U][Q];
@@ -207,6 +208,7 @@ struct Control {
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
+                acc[u] += fabsf(edge[u].x) + fabsf(edge[u].y);
                 if (slow[u]) {
                     for (int i = sub; i < K; i += LPW) {
                         const float2 x = sample(int64_t(p0[u]) + i);
