@@ -66,7 +66,7 @@ struct Ofdm {
     size_t max_pitch = 1u << 30;        // cudaDeviceProp::memPitch bound for pitched copies (set at create)
     int slots = 1;                      // frames a stream can complete in one call = soft-bit buffers per stream
     size_t frame_bits = 0;
-    int syms_per_chunk = 26;            // DAB_B200_SYMS_PER_CHUNK: target symbols per frame-kernel work item
+    int syms_per_chunk = 0;             // DAB_B200_SYMS_PER_CHUNK: target symbols per frame-kernel work item, 0 = by geometry (create_impl)
     int n_chunks = 3;                   // work items per frame
     bool force_generic_kernel = false;  // DAB_B200_GENERIC_FRAME_KERNEL=1: run the generic-geometry frame kernel (tests)
     bool dab_geometry = false;          // the v3 kernel applies
@@ -708,7 +708,12 @@ static int create_impl(Ofdm* o, const dab_c32* prs, const int* mapper) {
                       (o->nfft == 1024 && DabGeom<1024>::matches(int(o->p.nb_symbol_period), int(o->p.nb_cyclic_prefix), int(ncarr))) ||
                       (o->nfft == 512 && DabGeom<512>::matches(int(o->p.nb_symbol_period), int(o->p.nb_cyclic_prefix), int(ncarr))) ||
                       (o->nfft == 256 && DabGeom<256>::matches(int(o->p.nb_symbol_period), int(o->p.nb_cyclic_prefix), int(ncarr)));
-    // work items per frame: pieces of about syms_per_chunk symbols
+    // Work items per frame: pieces of about syms_per_chunk symbols.  An item costs one more transform (its differential reference)
+    // and its symbols run one after the other, so long items are cheap in work and long in latency.  Where the frame kernel's grid
+    // is several waves of long transforms (Modes I / IV, hundreds of streams) 26-symbol items are the measured optimum; with the
+    // short transforms of Modes II / III, or few streams, the launch is one or two waves and its duration is the length of an item:
+    // 13 symbols (Mode III, 1024 streams: 0.48 -> 0.40 ms per frame period; 256 streams: -10 %), 8 for a handful of streams.
+    if (o->syms_per_chunk <= 0) o->syms_per_chunk = (o->n_streams < 64) ? 8 : (o->nfft >= 1024 && o->n_streams >= 512) ? 26 : 13;
     o->n_chunks = std::max(1, std::min(FRAME_MAX_CHUNKS, int((o->p.nb_frame_symbols + size_t(o->syms_per_chunk) - 1) / size_t(o->syms_per_chunk))));
     size_t need = frame_cap + o->p.nb_null_period + o->p.nb_symbol_period + o->max_block + 1024;
     o->ring_samples = 1;

@@ -22,7 +22,7 @@
 
 namespace dabb200 {
 
-constexpr int FRAME_MAX_CHUNKS = 6;  // work items a frame is split into (load balance: a frame is 76 - 153 symbols long)
+constexpr int FRAME_MAX_CHUNKS = 16;  // work items a frame is split into (load balance: a frame is 76 - 153 symbols long)
 
 struct StreamState {
     // --- mirrors of the OFDM_Demod members (ofdm_demodulator.h:58-75)
