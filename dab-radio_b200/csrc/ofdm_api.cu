@@ -381,7 +381,7 @@ static int n_ways_for(const Ofdm* o, uint64_t n_max) {
     if (o->n_streams < 64 * o->ways) return 1;
     const uint64_t work = uint64_t(o->n_streams) * n_max;   // samples in this call
     if (work >= o->way_min_samples * uint64_t(o->ways)) return o->ways;
-    if (work >= o->way_min_samples * 2 && o->ways >= 2) return 2;
+    if (work * 4 >= o->way_min_samples * 5 && o->ways >= 2) return 2;   // 1024 Mode III frames (25 M samples): two ways measured 4 - 16 % faster than one
     return 1;
 }
 static int n_ways(const Ofdm* o) { return o->call_ways; }   // of the most recent call
