@@ -1,7 +1,7 @@
 // Frame demodulation kernel for the four DAB transmission modes ("v3"): one pass over HBM per symbol -- IQ in, int8 soft bits
 // out -- with everything OFDM_Demod::PipelineThread does in between (reference ofdm_demodulator.cpp:650-766).  Built around the
 // ncu finding that the kernel is bound by instruction issue and shared-memory wavefronts, not by HBM
-// (profiles/r01a_frame_kernel_ncu.md, profiles/r01g_frame_kernel_ncu.md):
+// (profiles/r01a_frame_kernel_ncu.md, profiles/r01g_frame_kernel_ncu.md, profiles/r02_frame_kernel_ncu.md):
 //
 //   * PLL as a separable phasor.  exp(j 2 pi f n) for sample n = s SP + CP + t + T j of the frame factors into
 //         D_j(s) = exp(j 2 pi (f s SP + f (CP + T j)))   16 values per symbol, the same for every thread
@@ -15,14 +15,19 @@
 //   * The cyclic-prefix correlation (ofdm_demodulator.cpp:768-777) runs on the raw samples; the rotation contributes the
 //     constant factor exp(j 2 pi f N), applied once to the sum before atan2.
 //   * Samples arrive by TMA: one elected thread issues a 1-D bulk copy (cp.async.bulk, UBLKCP) of the next symbol into shared
-//     memory right after the first FFT exchange, and all threads pick their 20 samples up with LDS after an mbarrier wait.  No
+//     memory at a CTA barrier right after the current symbol's samples and D table are in registers (DAB_V3_EARLY_FETCH: ~85 % of
+//     a symbol period for the copy to land), and all threads pick their 20 samples up with LDS after an mbarrier wait.  No
 //     global-load instructions, address arithmetic or prefetch registers in the loop.  A symbol that straddles the ring end (or
 //     an unaligned buffer end) takes a cooperative plain-load path.
-//   * 158 registers and 75 KB of shared memory per 128-thread CTA: three CTAs per SM, and the 4096 registers they leave are what
-//     ofdm_l1_windows_kernel (ofdm_control.cuh) runs in, concurrently, on a side stream.  Summing the UpdateSignalAverage windows
-//     here instead was built and measured: it costs more than it saves (profiles/r02_step_probes.md).
+//   * 128 registers and 56.5 KB of shared memory per 128-thread CTA: four CTAs per SM.  The inter-pass twiddles live in seven
+//     complex registers (DAB_V3_TW1_REGS), the last-pass twiddles come from global memory (L1-resident), exchange 1 is xor-swizzled
+//     instead of padded.  Summing the UpdateSignalAverage windows here (while the samples sit in shared memory) was built and
+//     measured in three forms: it costs more than it saves (profiles/r02_step_probes.md).
 //     The 512- and 256-point modes (4 / 8 transforms per CTA, symbols of 5 KB / 2.5 KB) keep the bulk copies too: 8-byte cp.async per
 //     thread with a third barrier per symbol was measured 30 % slower (profiles/r02_modes.md).
+//   * Soft bits are staged in shared memory where a host-side search puts them (stage_layout.h: chunk slot + word rotation per 8
+//     positions, 3.4 -> 2.0 wavefronts per 2-byte store of the frequency de-interleave scatter) and leave as 8-byte coalesced
+//     stores while the next symbol is in flight.
 //   * Quantisation with one MUFU.RCP (rcp.approx) instead of the IEEE reciprocal sequence + range-check branch; the GUI taps are
 //     a template parameter, so the hot variant carries none of their predicated-off instructions.
 //   * Raw integer IQ (u8 / s8 / u16 / s16) is dequantised on the way out of shared memory: the bulk copy moves

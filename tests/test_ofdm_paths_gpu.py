@@ -29,8 +29,7 @@ def _torch():
 # ---------------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("uniform", [True, False])
 def test_resident_streams_with_pipeline_ways(ofdm, oracle, uniform):
-    """288 device-resident Mode I streams (>= 256: the handle splits them into 4 pipeline ways, each on its own CUDA stream with its
-    window kernel on a side stream).  9 distinct base streams x 32 replicas; the call pattern is uniform blocks (advance_uniform,
+    """288 device-resident Mode I streams (>= 256: the handle splits them into 4 pipeline ways, each on its own CUDA stream).  9 distinct base streams x 32 replicas; the call pattern is uniform blocks (advance_uniform,
     the ways stay un-joined between calls) or ragged per-stream blocks (advance: per-stream sample counts, join per call).  Every
     base stream must match the oracle fed the same block sequence, every replica its base stream bit for bit."""
     torch = _torch()

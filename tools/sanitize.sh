@@ -1,7 +1,7 @@
 #!/bin/bash
 # compute-sanitizer passes over the library's kernels (run on the GPU box through gpurun); logs land in gpurun_out/<tag>_sanitizer_*.log
-# memcheck / initcheck / synccheck: smoke() + the 1024-stream back-to-back probe (Modes I and II: every OFDM kernel, pipeline ways,
-# side-stream window kernel) + the Viterbi / ensemble smoke paths.  racecheck (shared-memory hazards, ~100x slower): 64 streams.
+# memcheck / initcheck / synccheck: smoke() + the back-to-back probe (Modes I and II: every OFDM kernel, pipeline ways)
+# + the Viterbi / ensemble smoke paths.  racecheck (shared-memory hazards, ~100x slower): 64 streams.
 tag=${1:-r02}
 out=gpurun_out
 mkdir -p $out
