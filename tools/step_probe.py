@@ -27,6 +27,10 @@ for case in CASES:
         for k in env:
             del os.environ[k]
         d.disable_callback()
+        if os.environ.get("PROBE_DECIMATE"):
+            cfg = d.get_config(0)
+            cfg.signal_l1_nb_decimate = int(os.environ["PROBE_DECIMATE"])
+            d.set_config(cfg)
         st = torch.cuda.Stream()
         with torch.cuda.stream(st):
             d.set_cuda_stream(st.cuda_stream)
