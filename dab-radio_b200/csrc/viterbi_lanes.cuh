@@ -38,6 +38,9 @@ namespace dabb200 {
 constexpr int VITL_THREADS = 32;              // one warp per CTA: the finest grain the block scheduler can balance
 constexpr int VITL_MAX_REGS = 128;            // 4 warps per scheduler (16384 registers each): 96 would buy a fifth warp at the price of spills
 constexpr int VITL_TB_BYTES = 5;               // traceback: decoded bytes (x 8 decision rows) buffered per lane
+#ifndef VITL_TB_PREFETCH
+#define VITL_TB_PREFETCH 16                    // traceback: bytes (x 8 rows x 256 B per warp) prefetched into L2 ahead of the row loads
+#endif
 constexpr uint32_t VITL_CAREFUL = 58000;      // < 65535 - 1020 - 6 * 1020: below this no metric can be near saturation
 
 // Batches of at least this many trellises run one trellis per thread; smaller ones one per warp (viterbi_core.cuh), which
@@ -295,6 +298,18 @@ __device__ __forceinline__ uint64_t viterbi_lane_trellis(const DevSchedule* sch,
             for (int i = 0; i < 8; i++) w[i] = __ldcs(row + size_t(i) * 32u);
         }
     };
+    // The traceback starts when every warp of the GPU has just finished its trellis: for a while all that runs is 2368 warps streaming
+    // their decision rows back from HBM (the newest ~13 % are still in L2), and what a lane can keep in flight in registers
+    // (VITL_TB_BYTES - 1 bytes = 32 rows) left that phase at ~3.6 TB/s, 20 % of the kernel's time for 1 % of its instructions
+    // (profiles/r02_viterbi_lanes_ncu.md).  Rows VITL_TB_PREFETCH bytes further down the walk are pulled into L2 by prefetches, one
+    // per 32-byte sector: no registers, and the row loads behind them find their data on chip.
+    auto prefetch_rows = [&](int32_t b) {
+        if (b >= 0 && uint32_t(b) < warp_bytes && (lane & 3) == 0) {   // the sector of lanes lane .. lane + 3, whichever of them are active
+            const uint2* row = dec + (size_t(b) * 8u + 6u) * 32u + uint32_t(lane);
+#pragma unroll
+            for (int i = 0; i < 8; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + size_t(i) * 32u));
+        }
+    };
     auto walk_byte = [&](const uint2 (&w)[8], int32_t b) {
         if (b >= 0 && uint32_t(b) < n_bytes) {
 #pragma unroll
@@ -317,6 +332,7 @@ __device__ __forceinline__ uint64_t viterbi_lane_trellis(const DevSchedule* sch,
 #pragma unroll
         for (int i = 0; i < VITL_TB_BYTES; i++) {
             load_rows(w[(i + VITL_TB_BYTES - 1) % VITL_TB_BYTES], b - i - (VITL_TB_BYTES - 1));
+            prefetch_rows(b - i - (VITL_TB_BYTES - 1) - VITL_TB_PREFETCH);
             walk_byte(w[i], b - i);
         }
     }
