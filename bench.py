@@ -517,6 +517,8 @@ def run_ours(args):
         d.disable_callback()
         dec = ens.EnsembleDecoder(1, n_streams=n_streams, device=local_rank, max_subchannels=18)
         dec.set_cuda_stream(work_stream.cuda_stream)
+        decode_stream = torch.cuda.Stream()
+        dec.set_decode_stream(decode_stream.cuda_stream)   # ingest on the demodulator's stream, decode + read-back beside the next upload
         dec.set_subchannels(-1, [ens.subchannel(48 * k, 48, 0, 0, 2, 0) for k in range(18)])
         res = dec.device_results()
         sizes = {"msc_bytes": n_streams * res.nb_cifs * res.msc_cif_bytes, "fib_bytes": n_streams * res.nb_cifs * res.fib_group_bytes,
@@ -526,23 +528,31 @@ def run_ours(args):
         d_bits, n_bits, slots, d_fic = d.device_bits()
 
         def step():
+            # frame k: upload + demodulate (asynchronous); meanwhile the decode of frame k - 1 and the read-back of its bytes finish on
+            # the decode stream; then frame k is ingested (soft bits -> de-interleaver ring, on the demodulator's stream) and its decode
+            # and read-back are queued behind that.  Every frame's bytes are in pinned host memory one step later; the timed region
+            # ends with everything drained.
             d.process_batch_prepared(p, n, True)
+            decode_stream.synchronize()
             d.join()
             for slot in range(slots):
                 dec.decode_frames_device(d_bits + slot * n_bits, slots * n_bits, d_fic, slot)
             r = dec.device_results()
             for k in sizes:
                 (err,) = cudart.cudaMemcpyAsync(h_out[k].data_ptr(), getattr(r, k), sizes[k], cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost,
-                                                work_stream.cuda_stream)
+                                                decode_stream.cuda_stream)
                 assert int(err) == 0, err
-            work_stream.synchronize()
 
         for _ in range(max(W, 5)):
             step()
+        decode_stream.synchronize()
+        work_stream.synchronize()
         barrier()
         t0 = time.perf_counter()
         for _ in range(K):
             step()
+        decode_stream.synchronize()
+        work_stream.synchronize()
         dt = time.perf_counter() - t0
         dt_max = aggregate(dt * 1e3, 0, world, dist)[0] * 1e-3
         nbytes = h_out["msc_nbytes"].view(torch.int32)
@@ -550,7 +560,8 @@ def run_ours(args):
                "ensemble_frames_per_s": round(world * n_streams * K / dt_max, 1), "realtime_ensembles": round(world * n_streams * K / dt_max * 0.096, 1),
                "ms_per_step": round(dt_max / K * 1e3, 3), "h2d_bytes_per_step": int(n_streams * FRAME_LEN * 2),
                "d2h_bytes_per_step": int(sum(sizes.values())), "subchannel_cifs_decoded_last_step": int((nbytes > 0).sum().item()),
-               "api": "dab_ofdm_process_batch_u8 (pinned host uint8 IQ) -> dab_ensemble_decode_frames_device -> decoded bytes to pinned host memory"}
+               "api": "dab_ofdm_process_batch_u8 (pinned host uint8 IQ) -> dab_ensemble_decode_frames_device with dab_ensemble_set_decode_stream "
+                      "(the decode of frame k runs beside the upload of frame k + 1) -> decoded bytes to pinned host memory"}
         dec.close()
         d.close()
         del host

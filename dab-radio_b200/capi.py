@@ -142,7 +142,7 @@ EXPORTED_SYMBOLS = (
     "dab_viterbi_create", "dab_viterbi_destroy", "dab_viterbi_set_cuda_stream", "dab_viterbi_add_schedule",
     "dab_viterbi_schedule_soft_symbols", "dab_viterbi_decode_batch", "dab_viterbi_decode_batch_device",
     "dab_viterbi_decode_jobs_device", "dab_viterbi_prepare_jobs", "dab_viterbi_decode_prepared", "dab_viterbi_release_jobs", "dab_viterbi_decode_one", "dab_viterbi_sync", "dab_viterbi_kernel_launches",
-    "dab_get_dab_parameters", "dab_ensemble_create", "dab_ensemble_destroy", "dab_ensemble_set_cuda_stream",
+    "dab_get_dab_parameters", "dab_ensemble_create", "dab_ensemble_destroy", "dab_ensemble_set_cuda_stream", "dab_ensemble_set_decode_stream",
     "dab_ensemble_set_subchannels", "dab_ensemble_subchannel_schedule", "dab_ensemble_decode_frames_device",
     "dab_ensemble_decode_frames", "dab_ensemble_device_results", "dab_ensemble_read_fic", "dab_ensemble_read_msc",
     "dab_ensemble_sync", "dab_ensemble_kernel_launches", "dab_ensemble_last_work", "dab_ensemble_schedule_count",
@@ -248,6 +248,7 @@ def _bind_ensemble(L):
     L.dab_ensemble_destroy.argtypes = [vp]
     L.dab_ensemble_destroy.restype = None
     L.dab_ensemble_set_cuda_stream.argtypes = [vp, vp]
+    L.dab_ensemble_set_decode_stream.argtypes = [vp, vp]
     L.dab_ensemble_set_subchannels.argtypes = [vp, i32, vp, i32]
     L.dab_ensemble_subchannel_schedule.argtypes = [C.POINTER(Subchannel), C.POINTER(VitSchedule), C.POINTER(C.c_uint32)]
     L.dab_ensemble_decode_frames_device.argtypes = [vp, vp, sz, vp, i32]

@@ -376,6 +376,13 @@ struct Ensemble {
     dab_parameters params{};
     EnsGeom g{};
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    // dab_ensemble_set_decode_stream: everything after the ingest of a frame runs here, so that it overlaps whatever the caller queues
+    // on `stream` next (the next frame's upload and demodulation)
+    cudaStream_t decode_stream = nullptr;
+    cudaEvent_t ev_pushed = nullptr, ev_done = nullptr;
+    bool done_pending = false;
+    DeviceBuffer<int8_t> d_fic_copy;        // [n_streams][nb_fic_bits]: the FIC soft bits of the ingested frame
+    DeviceBuffer<int32_t> d_frames_copy;    // [n_streams]: the caller's frames_in_call at ingest
     int max_smem_optin = 0;
     std::mutex mtx;
     // host tables
@@ -481,46 +488,89 @@ static int upload_tables(Ensemble* e) {
     return DAB_OK;
 }
 
+static int sync_streams(Ensemble* e) {
+    DAB_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (e->decode_stream) DAB_CUDA_CHECK(cudaStreamSynchronize(e->decode_stream));
+    return DAB_OK;
+}
+
+// One frame per stream: ingest (the only part that reads the caller's buffers) -> de-interleave -> Viterbi (+ descramble, CRC) ->
+// commit.  With a decode stream the ingest stays on the handle's stream -- it also stages the FIC soft bits and the caller's
+// frames_in_call, so the caller may overwrite both as soon as the work queued on that stream so far has run -- and the rest runs on
+// the decode stream; the next ingest waits for the previous decode (it shares the ring counters and the staging buffers with it).
 static int decode_device(Ensemble* e, const int8_t* d_bits, size_t stream_stride, const int32_t* d_frames_in_call, int slot) {
     const EnsGeom base = e->g;
     if (e->tables_dirty) {
-        int rc = upload_tables(e);
+        int rc = sync_streams(e);
+        if (rc != DAB_OK) return rc;
+        rc = upload_tables(e);
         if (rc != DAB_OK) return rc;
     }
     EnsGeom g = base;
     g.aligned16 = (reinterpret_cast<uintptr_t>(d_bits) % 16 == 0 && stream_stride % 16 == 0 && g.nb_fic_bits % 16 == 0 && g.nb_cif_bits % 16 == 0) ? 1 : 0;
     const bool has_msc = g.nb_cif_bits > 0 && e->jobs_per_cif > (g.fic_enabled ? 1 : 0);
+    const bool split = e->decode_stream != nullptr;
+    cudaStream_t first = e->stream, rest = split ? e->decode_stream : e->stream;
+    const int8_t* fic_bits = d_bits;
+    size_t fic_stride = stream_stride;
+    const int32_t* frames = d_frames_in_call;
+    if (split) {
+        if (e->done_pending) DAB_CUDA_CHECK(cudaStreamWaitEvent(first, e->ev_done, 0));
+        if (g.fic_enabled && g.nb_fic_bits > 0) {
+            DAB_CUDA_CHECK(e->d_fic_copy.reserve(size_t(g.n_streams) * size_t(g.nb_fic_bits)));
+            DAB_CUDA_CHECK(cudaMemcpy2DAsync(e->d_fic_copy.ptr, size_t(g.nb_fic_bits), d_bits, stream_stride, size_t(g.nb_fic_bits), size_t(g.n_streams),
+                                             cudaMemcpyDeviceToDevice, first));
+            fic_bits = e->d_fic_copy.ptr;
+            fic_stride = size_t(g.nb_fic_bits);
+        }
+        if (d_frames_in_call) {
+            DAB_CUDA_CHECK(e->d_frames_copy.reserve(size_t(g.n_streams)));
+            DAB_CUDA_CHECK(cudaMemcpyAsync(e->d_frames_copy.ptr, d_frames_in_call, size_t(g.n_streams) * sizeof(int32_t), cudaMemcpyDeviceToDevice, first));
+            frames = e->d_frames_copy.ptr;
+        }
+    }
+    const dim3 grid(unsigned((g.plane_len + ENS_CHUNK - 1) / ENS_CHUNK), unsigned(g.nb_cifs), unsigned(g.n_streams));
     if (has_msc) {
-        const dim3 grid(unsigned((g.plane_len + ENS_CHUNK - 1) / ENS_CHUNK), unsigned(g.nb_cifs), unsigned(g.n_streams));
-        ens_push_kernel<<<grid, ENS_CHUNK, 0, e->stream>>>(g, d_bits, stream_stride, d_frames_in_call, slot, e->d_cif_count.ptr, e->d_ring.ptr);
-        ens_deint_kernel<<<grid, ENS_CHUNK, 0, e->stream>>>(g, d_frames_in_call, slot, e->d_cif_count.ptr, e->d_ring.ptr, e->d_deint.ptr);
-        e->launches += 2;
+        ens_push_kernel<<<grid, ENS_CHUNK, 0, first>>>(g, d_bits, stream_stride, d_frames_in_call, slot, e->d_cif_count.ptr, e->d_ring.ptr);
+        e->launches++;
+    }
+    if (split) {
+        DAB_CUDA_CHECK(cudaEventRecord(e->ev_pushed, first));
+        DAB_CUDA_CHECK(cudaStreamWaitEvent(rest, e->ev_pushed, 0));
+    }
+    if (has_msc) {
+        ens_deint_kernel<<<grid, ENS_CHUNK, 0, rest>>>(g, frames, slot, e->d_cif_count.ptr, e->d_ring.ptr, e->d_deint.ptr);
+        e->launches++;
     }
     const long long total_jobs = (long long)(e->jobs_per_cif) * g.nb_cifs * g.n_streams;
     if (e->jobs_per_cif > 0 && vitl_use_lanes(total_jobs)) {
         DAB_CUDA_CHECK(e->d_lane_scratch.reserve(size_t(e->lane_plan.rows()) * 32u));
         EnsOut o{e->d_fib_bytes.ptr, e->d_fib_valid.ptr, e->d_fic_error.ptr, e->d_msc_bytes.ptr, e->d_msc_nbytes.ptr, e->d_msc_error.ptr};
-        ens_viterbi_lanes_kernel<<<unsigned(e->lane_plan.n_warps()), VITL_THREADS, 0, e->stream>>>(
-            g, d_bits, stream_stride, d_frames_in_call, slot, e->d_deint.ptr, e->d_subs.ptr, e->d_stored.ptr, e->d_schedules.ptr, e->d_prbs.ptr, o,
+        ens_viterbi_lanes_kernel<<<unsigned(e->lane_plan.n_warps()), VITL_THREADS, 0, rest>>>(
+            g, fic_bits, fic_stride, frames, slot, e->d_deint.ptr, e->d_subs.ptr, e->d_stored.ptr, e->d_schedules.ptr, e->d_prbs.ptr, o,
             e->groups_per_slot, e->d_groups.ptr, e->d_warp_row.ptr, e->d_lane_scratch.ptr);
         e->launches++;
     } else if (e->jobs_per_cif > 0) {
         const size_t smem = size_t(VIT_WARPS_PER_CTA) * (size_t(e->window_steps) * sizeof(uint2) + sizeof(DevSchedule));
         DAB_CUDA_CHECK(cudaFuncSetAttribute(ens_viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_smem_optin));
         const long long total = (long long)(e->jobs_per_cif) * g.nb_cifs * g.n_streams;
-        const unsigned grid = unsigned((total + VIT_WARPS_PER_CTA - 1) / VIT_WARPS_PER_CTA);
+        const unsigned vgrid = unsigned((total + VIT_WARPS_PER_CTA - 1) / VIT_WARPS_PER_CTA);
         EnsOut o{e->d_fib_bytes.ptr, e->d_fib_valid.ptr, e->d_fic_error.ptr, e->d_msc_bytes.ptr, e->d_msc_nbytes.ptr, e->d_msc_error.ptr};
-        ens_viterbi_kernel<<<grid, VIT_WARPS_PER_CTA * 32, smem, e->stream>>>(g, d_bits, stream_stride, d_frames_in_call, slot, e->d_deint.ptr,
-                                                                            e->d_subs.ptr, e->d_stored.ptr, e->d_schedules.ptr, e->d_prbs.ptr, o,
-                                                                            e->jobs_per_cif, e->d_long_rank.ptr, e->d_scratch.ptr,
-                                                                            e->scratch_steps, e->window_steps);
+        ens_viterbi_kernel<<<vgrid, VIT_WARPS_PER_CTA * 32, smem, rest>>>(g, fic_bits, fic_stride, frames, slot, e->d_deint.ptr,
+                                                                         e->d_subs.ptr, e->d_stored.ptr, e->d_schedules.ptr, e->d_prbs.ptr, o,
+                                                                         e->jobs_per_cif, e->d_long_rank.ptr, e->d_scratch.ptr,
+                                                                         e->scratch_steps, e->window_steps);
         e->launches++;
     }
     {
         const int n = g.n_streams * g.max_subs;
-        ens_commit_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(g, d_frames_in_call, slot, e->d_cif_count.ptr, e->d_subs.ptr, e->d_stored.ptr,
-                                                                 e->d_decoded.ptr);
+        ens_commit_kernel<<<(n + 255) / 256, 256, 0, rest>>>(g, frames, slot, e->d_cif_count.ptr, e->d_subs.ptr, e->d_stored.ptr,
+                                                            e->d_decoded.ptr);
         e->launches++;
+    }
+    if (split) {
+        DAB_CUDA_CHECK(cudaEventRecord(e->ev_done, rest));
+        e->done_pending = true;
     }
     DAB_CUDA_CHECK(cudaGetLastError());
     return DAB_OK;
@@ -660,6 +710,9 @@ void dab_ensemble_destroy(dab_ensemble* h) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
+    if (e->decode_stream) cudaStreamSynchronize(e->decode_stream);
+    if (e->ev_pushed) cudaEventDestroy(e->ev_pushed);
+    if (e->ev_done) cudaEventDestroy(e->ev_done);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -668,6 +721,22 @@ int dab_ensemble_set_cuda_stream(dab_ensemble* h, void* cuda_stream) {
     auto* e = reinterpret_cast<Ensemble*>(h);
     if (!e) return set_error(DAB_ERR_INVALID, "null handle");
     e->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->own_stream;
+    return DAB_OK;
+}
+
+int dab_ensemble_set_decode_stream(dab_ensemble* h, void* cuda_stream) {
+    auto* e = reinterpret_cast<Ensemble*>(h);
+    if (!e) return set_error(DAB_ERR_INVALID, "null handle");
+    std::lock_guard<std::mutex> lock(e->mtx);
+    DeviceGuard device_guard;
+    DAB_CUDA_CHECK(cudaSetDevice(e->device));
+    { int rc_sync = sync_streams(e); if (rc_sync != DAB_OK) return rc_sync; }
+    if (cuda_stream && !e->ev_pushed) {
+        DAB_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_pushed, cudaEventDisableTiming));
+        DAB_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming));
+    }
+    e->decode_stream = static_cast<cudaStream_t>(cuda_stream);
+    e->done_pending = false;
     return DAB_OK;
 }
 
@@ -693,7 +762,7 @@ int dab_ensemble_set_subchannels(dab_ensemble* h, int stream, const dab_subchann
     // the de-interleaver counters live on the device: fetch, carry over for unchanged descriptors, write back
     const size_t K = size_t(g.max_subs);
     std::vector<int32_t> stored(size_t(g.n_streams) * K);
-    DAB_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    { int rc_sync = sync_streams(e); if (rc_sync != DAB_OK) return rc_sync; }
     DAB_CUDA_CHECK(cudaMemcpy(stored.data(), e->d_stored.ptr, stored.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
     auto same = [](const dab_subchannel& a, const dab_subchannel& b) {
         return a.start_address == b.start_address && a.length == b.length && (a.is_uep != 0) == (b.is_uep != 0) &&
@@ -780,7 +849,7 @@ int dab_ensemble_decode_frames(dab_ensemble* h, const int8_t* bits, const uint8_
     }
     int rc = decode_device(e, e->d_in.ptr, pitch, mask, 0);
     // `bits` / present32 are caller / stack memory: the staged copies must have left them before returning
-    DAB_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    { int rc_sync = sync_streams(e); if (rc_sync != DAB_OK) return rc_sync; }
     return rc;
 }
 
@@ -810,7 +879,7 @@ int dab_ensemble_read_fic(dab_ensemble* h, int stream, uint8_t* fib_bytes, uint8
     std::lock_guard<std::mutex> lock(e->mtx);
     DeviceGuard device_guard;
     DAB_CUDA_CHECK(cudaSetDevice(e->device));
-    DAB_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    { int rc_sync = sync_streams(e); if (rc_sync != DAB_OK) return rc_sync; }
     const size_t C = size_t(g.nb_cifs);
     if (fib_bytes && g.fib_group_bytes > 0)
         DAB_CUDA_CHECK(cudaMemcpy(fib_bytes, e->d_fib_bytes.ptr + size_t(stream) * C * g.fib_group_bytes, C * g.fib_group_bytes, cudaMemcpyDeviceToHost));
@@ -828,7 +897,7 @@ int dab_ensemble_read_msc(dab_ensemble* h, int stream, int cif, int sub_index, u
     if (sub_index < 0 || size_t(sub_index) >= e->subs[size_t(stream)].size()) return set_error(DAB_ERR_INVALID, "stream %d has no sub-channel slot %d", stream, sub_index);
     DeviceGuard device_guard;
     DAB_CUDA_CHECK(cudaSetDevice(e->device));
-    DAB_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    { int rc_sync = sync_streams(e); if (rc_sync != DAB_OK) return rc_sync; }
     int32_t decoded = 0, n = 0;
     DAB_CUDA_CHECK(cudaMemcpy(&decoded, e->d_decoded.ptr + stream, sizeof(int32_t), cudaMemcpyDeviceToHost));
     const size_t idx = (size_t(stream) * g.nb_cifs + cif) * size_t(g.max_subs) + size_t(sub_index);
@@ -851,7 +920,7 @@ int dab_ensemble_sync(dab_ensemble* h) {
     if (!e) return set_error(DAB_ERR_INVALID, "null handle");
     DeviceGuard device_guard;
     DAB_CUDA_CHECK(cudaSetDevice(e->device));
-    DAB_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    { int rc_sync = sync_streams(e); if (rc_sync != DAB_OK) return rc_sync; }
     return DAB_OK;
 }
 

@@ -45,6 +45,10 @@ class EnsembleDecoder:
     def set_cuda_stream(self, stream_ptr):
         capi.check(self.L.dab_ensemble_set_cuda_stream(self.h, stream_ptr))
 
+    def set_decode_stream(self, stream_ptr):
+        """second CUDA stream for everything after the ingest of a frame (dab_ensemble_set_decode_stream); None / 0 switches it off"""
+        capi.check(self.L.dab_ensemble_set_decode_stream(self.h, stream_ptr or None))
+
     def set_subchannels(self, stream, subs):
         subs = list(subs)
         arr = (capi.Subchannel * max(len(subs), 1))(*subs)

@@ -344,6 +344,12 @@ typedef struct dab_ensemble dab_ensemble;
 DAB_API dab_ensemble* dab_ensemble_create(const dab_parameters* params, const dab_ensemble_options* options, int* status);
 DAB_API void dab_ensemble_destroy(dab_ensemble* h);
 DAB_API int dab_ensemble_set_cuda_stream(dab_ensemble* h, void* cuda_stream);
+/* Optional second stream (NULL: off).  With it dab_ensemble_decode_frames_device only INGESTS on the handle's stream (soft bits ->
+ * de-interleaver ring, FIC soft bits and frames_in_call staged): once the work queued on that stream so far has run the caller may
+ * overwrite d_bits / d_frames_in_call, e.g. by demodulating the next frame.  De-interleave, Viterbi, descramble, CRC and commit run on
+ * the decode stream, concurrently with whatever the caller queues on the handle's stream next; the results are valid once the
+ * decode stream has run (queue the read-back on it, or dab_ensemble_sync).  The next ingest waits for the previous decode. */
+DAB_API int dab_ensemble_set_decode_stream(dab_ensemble* h, void* cuda_stream);
 /* The sub-channel set of one stream (stream = -1: every stream), i.e. which MSC_Decoder objects exist
  * (basic_radio.cpp:100-153).  A sub-channel whose descriptor is unchanged keeps its de-interleaver history, a new one starts
  * empty and yields no bytes until 16 CIFs have been consumed (cif_deinterleaver.cpp:40-43). */

@@ -210,3 +210,59 @@ def test_schedules_are_garbage_collected_across_reconfigurations(ens, oracle):
         dec.decode_frames(frames[f])
         _check_stream(dec, 0, want[f], len(layout), f"frame {f}")
     dec.close()
+
+
+def test_decode_stream_overlaps_the_next_frame(ens, oracle, pkg):
+    """dab_ensemble_set_decode_stream: only the ingest of a frame stays on the stream that produced the soft bits; de-interleave, Viterbi,
+    descramble, CRC and commit run on a second stream while the demodulator already overwrites its soft-bit buffer with the next
+    frame.  A decoder in that mode must report, frame after frame, exactly what a decoder that is synchronised after every call reports."""
+    import dabgen
+    import torch
+    ofdm = importlib.import_module("dab-radio_b200.ofdm")
+    n_streams, n_frames, block = 4, 8, 196104   # one frame per call at most: one soft-bit slot per stream
+    d = ofdm.OfdmDemodBatch(1, n_streams=n_streams, max_block_samples=block)
+    layout = [(0, 48, 0, 0, 2, 0), (48, 35, 1, 4, 0, 0), (100, 27, 0, 0, 0, 1), (200, 96, 0, 0, 3, 0)]
+    serial = ens.EnsembleDecoder(1, n_streams=n_streams, max_subchannels=4)
+    split = ens.EnsembleDecoder(1, n_streams=n_streams, max_subchannels=4)
+    for dec in (serial, split):
+        dec.set_subchannels(-1, [ens.subchannel(*a) for a in layout])
+    work, side = torch.cuda.Stream(), torch.cuda.Stream()
+    d.set_cuda_stream(work.cuda_stream)
+    split.set_cuda_stream(work.cuda_stream)
+    split.set_decode_stream(side.cuda_stream)
+    serial.set_cuda_stream(work.cuda_stream)
+    xs = [dabgen.make_stream(1, n_frames + 1, seed=70 + s, cfo_hz=-300.0 * s, start=777 * s + 5, snr_db=14.0) for s in range(n_streams)]
+
+    def snapshot(dec):
+        out = []
+        for s in range(n_streams):
+            b, v, e = dec.read_fic(s)
+            out.append((b.copy(), v.copy(), np.array(e).copy()))
+            for c in range(4):
+                for k in range(len(layout)):
+                    gb, n, ge = dec.read_msc(s, c, k)
+                    out.append((np.array(gb).copy(), int(n), int(ge)))
+        return out
+
+    def same(a, b):
+        return len(a) == len(b) and all(all(np.array_equal(np.asarray(x), np.asarray(y)) for x, y in zip(p, q)) for p, q in zip(a, b))
+
+    expected = None
+    decoded_calls = 0
+    for off in range(0, xs[0].size - block + 1, block):
+        d.process_batch([x[off:off + block] for x in xs])   # overwrites the soft bits the split decoder ingested in the last round
+        d.sync()
+        if expected is not None:
+            assert same(snapshot(split), expected), f"call at sample {off}: the overlapped decoder differs from the synchronised one"
+        d_bits, n_bits, slots, d_fic = d.device_bits()
+        assert slots == 1
+        serial.decode_frames_device(d_bits, n_bits, d_fic, 0)
+        serial.sync()
+        expected = snapshot(serial)
+        split.decode_frames_device(d_bits, n_bits, d_fic, 0)   # not synchronised: the next process_batch races with it by design
+        decoded_calls += 1
+    assert same(snapshot(split), expected)
+    assert decoded_calls >= n_frames and sum(len(f) for f in d.frames) >= n_streams * (n_frames - 2)
+    assert any(int(item[1]) > 0 for item in expected if isinstance(item[1], int))   # sub-channel bytes did come out
+    for h in (d, serial, split):
+        h.close()
