@@ -103,7 +103,7 @@ struct ControlSmem {
     // `nat` (natural-order spectrum between two transforms) aliases exchange 1 and the L1 window batch aliases the (contiguous) exchanges: both
     // are only alive while no transform is in flight (every hand-over is separated by a CTA barrier)
     static_assert(G::E1_SIZE >= NFFT, "nat must fit into exchange 1");
-    static_assert(size_t(G::E1_SIZE + G::E2_SIZE) * sizeof(float2) >= size_t(CTRL_L1_BATCH) * sizeof(float), "L1 batch must fit into the exchanges");
+    static_assert(size_t(G::E1_SIZE + G::E2_SIZE) * sizeof(float2) >= size_t(CTRL_L1_BATCH) * sizeof(float) && CTRL_L1_BATCH >= 2 * THREADS, "L1 batch must fit into the exchanges");
     static constexpr size_t bytes() { return size_t(G::TW1_SIZE + G::TW2_SIZE + G::E1_SIZE + G::E2_SIZE) * sizeof(float2) + 32 * sizeof(float2) + 64; }
 };
 
@@ -236,10 +236,28 @@ struct Control {
                 const int count = int(min(int64_t(CTRL_L1_BATCH), n_windows - w0));
                 l1_windows(l1buf, st.call_begin + w0 * L, L, K, count);
                 __syncthreads();
+                // avg <- beta avg + (1 - beta) x_w over the windows in order (:941-947).  The recurrence is linear: a thread runs it over
+                // its own run of m consecutive windows starting from zero, r_t, and the runs are chained as avg <- beta^m avg + r_t.
+                // Same value up to float rounding (the signal average is compared at 1e-4), and thread 0 walks 128 partial
+                // results instead of up to 1024 windows while the other 127 threads wait.
+                const float beta = st.cfg.signal_l1_update_beta;
+                const int m = (count + THREADS - 1) / THREADS;
+                float* part = l1buf;   // (r_t, beta^len_t) pairs, written over the window averages once every thread has read its run
+                {
+                    float r = 0.0f, bp = 1.0f;
+                    const int lo = min(tid * m, count), hi = min(lo + m, count);
+                    for (int w = lo; w < hi; w++) {
+                        r = beta * r + (1.0f - beta) * l1buf[w];
+                        bp *= beta;
+                    }
+                    __syncthreads();
+                    part[2 * tid] = r;
+                    part[2 * tid + 1] = bp;
+                }
+                __syncthreads();
                 if (tid == 0) {
-                    const float beta = st.cfg.signal_l1_update_beta;
                     float avg = st.l1_average;
-                    for (int w = 0; w < count; w++) avg = beta * avg + (1.0f - beta) * l1buf[w];
+                    for (int t = 0; t < THREADS; t++) avg = part[2 * t + 1] * avg + part[2 * t];
                     st.l1_average = avg;
                 }
                 __syncthreads();
