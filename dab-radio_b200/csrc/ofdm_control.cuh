@@ -12,7 +12,8 @@
 // UpdateSignalAverage (ofdm_demodulator.cpp:934-950) runs first in the reference's Process(); here its value is only needed when a
 // stream searches for the NULL symbol or when the call is over, so it is folded lazily: the pass in which a stream finishes its
 // block sums the block's window averages and folds them into the running average in window order (a searching stream does it the
-// moment FindNullPowerDip needs the thresholds).  Two other homes for the window sums were built and measured -- inside the frame
+// moment FindNullPowerDip needs the thresholds; from pass 1 on every other CTA of an SM folds before its synchronisation transforms
+// so that the memory-bound and the issue-bound phases of co-resident CTAs overlap).  Two other homes for the window sums were built and measured -- inside the frame
 // kernel while the samples sit in shared memory, and a kernel of their own on a side stream beside the frame kernel -- and dropped:
 // profiles/r02_step_probes.md.
 #pragma once
@@ -90,7 +91,7 @@ struct ControlGeom {
     int n_sm;                      // SMs of the device: CTAs b and b + n_sm share an SM in the first wave (phase staggering)
 };
 
-constexpr int CTRL_L1_BATCH = 1024;  // windows whose L1 averages are computed in parallel before the sequential scan
+constexpr int CTRL_L1_BATCH = 1024;  // windows whose L1 averages are computed in parallel before they are folded / searched in order
 
 template <int NFFT>
 struct ControlSmem {
